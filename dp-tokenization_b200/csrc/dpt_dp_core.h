@@ -1,0 +1,101 @@
+// The shortest-tokenization DP on one word, host/device.
+//
+// Closed-form restatement of /root/reference/packages/dp_tokenize.py:24-84:
+//   forward  len_dp[i] = min(i, min_{j<i, s[j:i] in V} len_dp[j]+1)          (:27-47, phantom init :28)
+//   reach[i] = some optimal predecessor chain reaches 0                        (paths dropped at :66-69)
+//   M[i]     = longest single token (in units of `charlen`) on any optimal complete path to i
+//   select   = first segmentation in the DFS order of :57-69 (largest split first) whose longest
+//              token equals M[n]                                               (:82-84)
+// All three forward quantities are packed into ONE ordered 64-bit key per position
+//      key = len << 32 | notreach << 31 | (0x7FFFFFFF - M)
+// so the relaxation over an incoming edge is a single unsigned min.  Two predecessor distances are
+// kept per position:  A = largest j among edges with minimal (len, notreach)   -> "got" branch
+//                     B = largest j among edges attaining the minimal key      -> "not yet got" branch
+// which makes the backward selection a pointer chase independent of M[n].
+#pragma once
+#include "dpt_common.h"
+
+#define DPT_KEY_LOW 0x7FFFFFFFull
+#define DPT_KEY_NOTREACH 0x80000000ull
+
+DPT_HD uint64_t dpt_key_phantom(uint32_t unit_index) { return ((uint64_t)unit_index << 32) | 0xFFFFFFFFull; }
+DPT_HD uint64_t dpt_key_origin() { return DPT_KEY_LOW; }
+DPT_HD uint64_t dpt_key_extend(uint64_t kj, uint32_t charlen) {
+    const uint64_t lowj = kj & DPT_KEY_LOW;
+    const uint64_t lowe = DPT_KEY_LOW - charlen;
+    return (kj & ~DPT_KEY_LOW) + (1ull << 32) + (lowj < lowe ? lowj : lowe);
+}
+DPT_HD uint32_t dpt_key_len(uint64_t k) { return (uint32_t)(k >> 32); }
+DPT_HD bool dpt_key_reach(uint64_t k) { return (k & DPT_KEY_NOTREACH) == 0; }
+DPT_HD uint32_t dpt_key_longest(uint64_t k) { return (uint32_t)(DPT_KEY_LOW - (k & DPT_KEY_LOW)); }
+
+// Forward pass over the normalised bytes s[0..n).  best/A/B have n+1 entries.
+// kEmit=false skips A/B (count pass).
+template <bool kEmit>
+DPT_HD void dpt_forward(const DptVocabView& V, const uint8_t* s, int32_t n, const uint8_t* unit_starts,
+                        uint64_t* best, uint16_t* A, uint16_t* B) {
+    const bool bytes_mode = V.unit_mode == 0 && unit_starts == nullptr;
+    uint32_t u = 0;
+    for (int32_t p = 0; p <= n; ++p) {
+        const bool b = (p == 0 || p == n) ? true
+                       : unit_starts      ? unit_starts[p] != 0
+                       : bytes_mode       ? true
+                                          : dpt_is_cp_start(s[p]);
+        best[p] = b ? dpt_key_phantom(u) : ~0ull;
+        if (b) ++u;
+        if (kEmit) {
+            A[p] = 0;
+            B[p] = 0;
+        }
+    }
+    best[0] = dpt_key_origin();
+    for (int32_t j = 0; j < n; ++j) {
+        const uint64_t kj = best[j];
+        if (kj == ~0ull) continue;  // not a unit boundary
+        uint32_t entry = DPT_DA_ROOT_ENTRY;
+        uint32_t cl = 0;
+        const int32_t stop = (n - j) < (int32_t)V.lmax ? n : j + (int32_t)V.lmax;
+        for (int32_t i = j + 1; i <= stop; ++i) {
+            const uint32_t c = s[i - 1];
+            if (!dpt_da_step(V.da, entry, c)) break;
+            cl += (V.unit_mode == 0 || dpt_is_cp_start(c)) ? 1u : 0u;
+            if ((entry & DPT_DA_TERMINAL) && best[i] != ~0ull) {
+                const uint64_t k = dpt_key_extend(kj, cl);
+                const uint64_t bi = best[i];
+                if (kEmit && (k >> 31) <= (bi >> 31)) A[i] = (uint16_t)(i - j);
+                if (k <= bi) {
+                    best[i] = k;
+                    if (kEmit) B[i] = (uint16_t)(i - j);
+                }
+            }
+        }
+    }
+}
+
+// Backward selection + id emission.  Writes len tokens to out_ids[0..len) in text order (filled from
+// the back).  Returns false (and writes nothing) when the word is untokenizable.
+DPT_HD bool dpt_backward_emit(const DptVocabView& V, const uint8_t* s, int32_t n, const uint64_t* best,
+                              const uint16_t* A, const uint16_t* B, int32_t* out_ids, int64_t out_cap) {
+    const uint64_t kn = best[n];
+    if (!dpt_key_reach(kn)) return false;
+    const uint32_t target = dpt_key_longest(kn);
+    int64_t slot = (int64_t)dpt_key_len(kn) - 1;
+    bool got = false;
+    int32_t i = n;
+    while (i > 0) {
+        const int32_t d = got ? A[i] : B[i];
+        const int32_t j = i - d;
+        DptHashState h = dpt_hash_init(V.ph_salt);
+        uint32_t cl = 0;
+        for (int32_t p = j; p < i; ++p) {
+            const uint32_t c = s[p];
+            dpt_hash_byte(h, c);
+            cl += (V.unit_mode == 0 || dpt_is_cp_start(c)) ? 1u : 0u;
+        }
+        if (!got && cl == target) got = true;
+        if (slot >= 0 && slot < out_cap) out_ids[slot] = dpt_ph_lookup(V, h);
+        --slot;
+        i = j;
+    }
+    return true;
+}

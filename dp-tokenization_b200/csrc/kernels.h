@@ -1,0 +1,40 @@
+// Internal interface between the C ABI (cabi.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+struct dpt_vocab;
+
+namespace dpt {
+
+extern std::atomic<int64_t> g_launches;
+
+int64_t encode_words_workspace_fixed(int64_t n_words);
+int64_t pretokenize_workspace(int64_t n_bytes, int64_t n_docs);
+
+// d_n_out: int64[4] = {n_ids, n_words, long-pool capacity (positions), long-pool required}
+int encode_words(const dpt_vocab* v, const uint8_t* d_text, const int64_t* d_word_offs, int64_t n_words,
+                 int64_t n_bytes_for_counter, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens,
+                 uint8_t* d_word_flags, int64_t* d_word_tok_offs, int64_t* d_counters, int64_t* d_n_out, void* d_ws,
+                 int64_t ws_bytes, cudaStream_t st, std::string& err);
+
+// d_n_out: int64[2] = {n_words, n_norm_bytes}
+int pretokenize_spm(const dpt_vocab* v, const uint8_t* d_text, int64_t n_bytes, const int64_t* d_doc_offs, int64_t n_docs,
+                    uint8_t* d_norm, int64_t norm_cap, int64_t* d_norm_doc_offs, int64_t* d_word_offs, int64_t word_cap,
+                    int64_t* d_doc_first_word, uint8_t* d_doc_flags, int64_t* d_n_out, void* d_ws, int64_t ws_bytes,
+                    cudaStream_t st, std::string& err);
+
+int doc_tok_offsets(const int64_t* d_doc_first_word, int64_t n_docs, const int64_t* d_tok_offs, int64_t n_words,
+                    int64_t* d_doc_tok_offs, cudaStream_t st);
+
+int roundtrip_check(const dpt_vocab* v, const int32_t* d_ids, const int64_t* d_doc_tok_offs, const uint8_t* d_text,
+                    const int64_t* d_doc_offs, int64_t n_docs, int32_t skip_bos, uint8_t* d_ok, cudaStream_t st);
+
+int lattice_word(const dpt_vocab* v, const uint8_t* d_text, int32_t n_bytes, const uint8_t* d_unit_starts,
+                 int32_t* d_len_dp, int32_t* d_pred_offs, int32_t* d_pred, int32_t pred_cap, int32_t* d_n_out,
+                 int32_t* d_unit_of, cudaStream_t st);
+
+}  // namespace dpt

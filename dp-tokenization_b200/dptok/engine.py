@@ -1,0 +1,197 @@
+"""Host driver above the C ABI: owns device buffers (torch tensors), streams and capacity retries.
+
+PyTorch is plumbing here (device memory, streams, torch.distributed); every result comes from the
+kernels in ``csrc/`` through ``include/dptok.h``.  No CPU execution path exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import lib, check
+from .vocab import CompiledVocab
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("dptok needs a CUDA device: the shortest-tokenization path has no CPU fallback")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+@dataclass
+class EncodeResult:
+    ids: torch.Tensor            # int32[n_ids] device
+    word_lens: torch.Tensor      # int32[n_words] device  (len_dp[n], dp_tokenize.py:70)
+    word_flags: torch.Tensor     # uint8[n_words] device  (WF_* bits)
+    word_tok_offs: Optional[torch.Tensor]  # int64[n_words+1] device
+    counters: torch.Tensor       # int64[4] device {bytes, words, tokens, untokenizable}
+    n_ids: int
+    n_words: int
+    doc_tok_offs: Optional[torch.Tensor] = None  # int64[n_docs+1] device
+    doc_flags: Optional[torch.Tensor] = None     # uint8[n_docs] device
+
+
+class Engine:
+    """One compiled vocabulary on one GPU."""
+
+    def __init__(self, vocab: CompiledVocab, device: Optional[int] = None):
+        _require_cuda()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.vocab = vocab.upload(self.device)
+        self._ws: Optional[torch.Tensor] = None
+
+    # ---- buffers -------------------------------------------------------------------------
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- PRESPLIT: words already split (and normalised) by the caller ---------------------------
+    def encode_words(self, text: torch.Tensor, word_offs: torch.Tensor, want_tok_offs: bool = False,
+                     ids_cap: Optional[int] = None) -> EncodeResult:
+        """``text`` uint8 device tensor, ``word_offs`` int64[n_words+1] device tensor."""
+        assert text.dtype == torch.uint8 and word_offs.dtype == torch.int64
+        assert text.is_cuda and word_offs.is_cuda
+        n_words = word_offs.numel() - 1
+        n_bytes = text.numel()
+        dev = self.device
+        if ids_cap is None:
+            ids_cap = n_bytes // 2 + n_words + 64
+        worst = 0
+        with torch.cuda.device(dev):
+            while True:
+                ids = torch.empty(max(ids_cap, 1), dtype=torch.int32, device=dev)
+                lens = torch.empty(max(n_words, 1), dtype=torch.int32, device=dev)
+                flags = torch.empty(max(n_words, 1), dtype=torch.uint8, device=dev)
+                tok_offs = torch.empty(n_words + 1, dtype=torch.int64, device=dev) if want_tok_offs else None
+                counters = torch.empty(4, dtype=torch.int64, device=dev)
+                n_out = torch.empty(8, dtype=torch.int64, device=dev)
+                ws_bytes = lib.dpt_encode_words_workspace(n_bytes, n_words, worst)
+                ws = self._workspace(ws_bytes)
+                check(lib.dpt_encode_words(self.vocab.handle, _ptr(text), _ptr(word_offs), n_words, n_bytes, _ptr(ids),
+                                           ids_cap, _ptr(lens), _ptr(flags), _ptr(tok_offs), _ptr(counters), _ptr(n_out),
+                                           _ptr(ws), ws.numel(), self._stream()))
+                h = n_out.cpu().tolist()  # synchronises the stream
+                retry = False
+                if h[_cabi.NOUT_IDS] > ids_cap:
+                    ids_cap = h[_cabi.NOUT_IDS]
+                    retry = True
+                if h[_cabi.NOUT_POOL_REQ] > h[_cabi.NOUT_POOL_CAP]:
+                    worst = 1
+                    retry = True
+                if not retry:
+                    break
+        return EncodeResult(ids[:h[0]], lens[:n_words], flags[:n_words], tok_offs, counters, h[0], n_words)
+
+    # ---- corpus path: raw documents -> ids ------------------------------------------------------
+    def encode_corpus(self, text: torch.Tensor, doc_offs: torch.Tensor, rule: int,
+                      ids_cap: Optional[int] = None, word_cap: Optional[int] = None) -> EncodeResult:
+        """``text`` uint8 device tensor of concatenated non-empty documents; ``doc_offs`` int64[n_docs+1]."""
+        assert text.dtype == torch.uint8 and doc_offs.dtype == torch.int64 and text.is_cuda and doc_offs.is_cuda
+        n_bytes = text.numel()
+        n_docs = doc_offs.numel() - 1
+        dev = self.device
+        if ids_cap is None:
+            ids_cap = n_bytes // 2 + 2 * n_docs + 64
+        if word_cap is None:
+            word_cap = n_bytes // 3 + 2 * n_docs + 64
+        worst = 0
+        with torch.cuda.device(dev):
+            while True:
+                ids = torch.empty(ids_cap, dtype=torch.int32, device=dev)
+                lens = torch.empty(word_cap, dtype=torch.int32, device=dev)
+                flags = torch.empty(word_cap, dtype=torch.uint8, device=dev)
+                doc_tok = torch.empty(n_docs + 1, dtype=torch.int64, device=dev)
+                doc_flags = torch.empty(n_docs, dtype=torch.uint8, device=dev)
+                counters = torch.empty(4, dtype=torch.int64, device=dev)
+                n_out = torch.zeros(8, dtype=torch.int64, device=dev)
+                ws_bytes = lib.dpt_encode_corpus_workspace(rule, n_bytes, n_docs, word_cap, worst)
+                ws = self._workspace(ws_bytes)
+                rc = lib.dpt_encode_corpus(self.vocab.handle, rule, _ptr(text), n_bytes, _ptr(doc_offs), n_docs, _ptr(ids),
+                                           ids_cap, _ptr(lens), _ptr(flags), word_cap, _ptr(doc_tok), _ptr(doc_flags),
+                                           _ptr(counters), _ptr(n_out), _ptr(ws), ws.numel(), worst, self._stream())
+                if rc not in (_cabi.OK, _cabi.ECAPACITY):
+                    check(rc)
+                h = n_out.cpu().tolist()
+                retry = False
+                if h[_cabi.NOUT_WORDS] > word_cap:
+                    word_cap = h[_cabi.NOUT_WORDS] + 64
+                    retry = True
+                if h[_cabi.NOUT_NORM_REQ] > h[_cabi.NOUT_NORM_CAP] or h[_cabi.NOUT_POOL_REQ] > h[_cabi.NOUT_POOL_CAP]:
+                    if worst:
+                        raise _cabi.DptError(_cabi.ECAPACITY, "worst-case workspace still too small")
+                    worst = 1
+                    retry = True
+                if h[_cabi.NOUT_IDS] > ids_cap:
+                    ids_cap = h[_cabi.NOUT_IDS] + 64
+                    retry = True
+                if rc == _cabi.ECAPACITY and not retry:
+                    check(rc)
+                if not retry:
+                    break
+        nw = h[_cabi.NOUT_WORDS]
+        return EncodeResult(ids[:h[0]], lens[:nw], flags[:nw], None, counters, h[0], nw, doc_tok, doc_flags)
+
+    # ---- lattice of one word (enumerate-all API) --------------------------------------------------
+    def lattice(self, data: bytes, unit_starts: Optional[Sequence[int]] = None):
+        """Returns (len_dp: list[int], preds: list[list[int]]) over unit positions 0..n_units."""
+        n = len(data)
+        dev = self.device
+        with torch.cuda.device(dev):
+            text = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
+            us = None
+            if unit_starts is not None:
+                flags = np.zeros(n, dtype=np.uint8)
+                flags[[p for p in unit_starts if p < n]] = 1
+                us = torch.from_numpy(flags).to(dev)
+            pred_cap = max(64, 8 * (n + 1))
+            while True:
+                len_dp = torch.empty(n + 2, dtype=torch.int32, device=dev)
+                pred_offs = torch.empty(n + 3, dtype=torch.int32, device=dev)
+                pred = torch.empty(pred_cap, dtype=torch.int32, device=dev)
+                scratch = torch.empty(n + 2, dtype=torch.int32, device=dev)
+                n_out = torch.zeros(2, dtype=torch.int32, device=dev)
+                check(lib.dpt_lattice_word(self.vocab.handle, _ptr(text), n, _ptr(us), _ptr(len_dp), _ptr(pred_offs),
+                                           _ptr(pred), pred_cap, _ptr(n_out), _ptr(scratch), self._stream()))
+                n_units, n_pred = n_out.cpu().tolist()
+                if n_pred <= pred_cap:
+                    break
+                pred_cap = n_pred
+            ld = len_dp[:n_units + 1].cpu().tolist()
+            po = pred_offs[:n_units + 2].cpu().tolist()
+            pr = pred[:n_pred].cpu().tolist()
+        preds = [pr[po[u]:po[u + 1]] for u in range(n_units + 1)]
+        return ld, preds
+
+    # ---- decode / round trip on device ---------------------------------------
+    def roundtrip_ok(self, res: EncodeResult, text: torch.Tensor, doc_offs: torch.Tensor, skip_bos: bool) -> torch.Tensor:
+        n_docs = doc_offs.numel() - 1
+        ok = torch.empty(n_docs, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.dpt_roundtrip_check(self.vocab.handle, _ptr(res.ids), _ptr(res.doc_tok_offs), _ptr(text),
+                                          _ptr(doc_offs), n_docs, 1 if skip_bos else 0, _ptr(ok), self._stream()))
+        return ok
+
+
+def launch_count() -> int:
+    return int(lib.dpt_launch_count())
+
+
+def pack_documents(docs: Sequence[bytes]):
+    """list of byte strings -> (uint8 array, int64 offsets) on the host."""
+    offs = np.zeros(len(docs) + 1, dtype=np.int64)
+    np.cumsum([len(d) for d in docs], out=offs[1:])
+    text = np.frombuffer(b"".join(docs), dtype=np.uint8)
+    return text, offs

@@ -1,0 +1,211 @@
+/*
+ * dptok.h - C ABI of the B200-native shortest-tokenization path.
+ *
+ * The reference (smfsamir/dp-tokenization) has no FFI layer: its boundary is
+ * the Python signatures of packages/dp_tokenize.py and
+ * packages/tokenizer_utils.py.  This header is the C boundary a binding for
+ * that surface calls (ctypes stub: dp-tokenization_b200/dptok/_cabi.py; see
+ * INTEGRATION.md).  Every entry point names the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - pointers named d_* are DEVICE pointers owned by the caller (PyTorch
+ *     tensors' data_ptr()); the library owns only the dpt_vocab handle and the
+ *     device copy of the compiled vocabulary hanging off it.
+ *   - all device work is enqueued on the caller's `stream` (a cudaStream_t
+ *     passed as void*; NULL = legacy default stream); nothing synchronises
+ *     unless stated.
+ *   - every function returns a dpt_status (0 = ok); dpt_last_error() gives a
+ *     thread-local message.  Nothing aborts, nothing drops into a debugger
+ *     (the reference calls ipdb.set_trace() at tokenizer_utils.py:72-73).
+ *   - an untokenizable word is DATA, not an error: flag bit + phantom length
+ *     (dp_tokenize.py:28,70) and no ids.
+ *   - the handle is immutable after dpt_vocab_upload(): share it freely across
+ *     host threads and streams.  One process per GPU in the sharded driver.
+ *   - there is no CPU execution path behind these calls: without a CUDA device
+ *     every compute entry point returns DPT_ECUDA.
+ */
+#ifndef DPTOK_H
+#define DPTOK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dpt_vocab dpt_vocab;
+
+enum dpt_status {
+    DPT_OK = 0,
+    DPT_EINVAL = 1,     /* bad argument */
+    DPT_ECUDA = 2,      /* CUDA runtime error / no device */
+    DPT_ECAPACITY = 3,  /* a caller-provided buffer is too small; retry bigger */
+    DPT_ENOMEM = 4,
+    DPT_ESTATE = 5      /* e.g. vocab not uploaded to this device */
+};
+
+/* unit_mode: what one DP position and one unit of "token length" mean.
+ *   BYTES      - byte-level BPE after the inverse bytes_to_unicode map
+ *                (tokenizer_utils.py:149-151: one unit per mapped char).
+ *   CODEPOINTS - SentencePiece-style vocab of UTF-8 strings; the DP of
+ *                dp_tokenize.py:27-47 runs over code points and the tie-break
+ *                of dp_tokenize.py:82 counts code points.                     */
+enum dpt_unit_mode { DPT_UNIT_BYTES = 0, DPT_UNIT_CODEPOINTS = 1 };
+
+/* Pre-tokenization rule.
+ *   PRESPLIT  - caller supplies word offsets (pretokenize_with_llama /
+ *               pre_tokenize_str run on the host; tokenizer_utils.py:24-31,157-159)
+ *   SPM_LLAMA - normaliser Prepend(U+2581) + Replace(' ',U+2581), byte-fallback
+ *               expansion of out-of-vocab characters to literal "<0xHH>" text,
+ *               a word starts at every U+2581 (tokenizer_utils.py:12-17,24-31)
+ *   GPT2      - ByteLevel(use_regex=True) split
+ *   LLAMA3    - Llama-3 split regex
+ *   BLOOM     - BLOOM split regex (tokenizer_utils.py:157-159 target)          */
+enum dpt_rule {
+    DPT_RULE_PRESPLIT = 0,
+    DPT_RULE_SPM_LLAMA = 1,
+    DPT_RULE_GPT2 = 2,
+    DPT_RULE_LLAMA3 = 3,
+    DPT_RULE_BLOOM = 4
+};
+
+/* per-word flag bits written by the encode calls */
+#define DPT_WF_UNTOKENIZABLE 0x01u /* reference returns [] (dp_tokenize.py:66-70) */
+#define DPT_WF_DOC_FIRST     0x02u /* first word of a document                     */
+#define DPT_WF_LONG          0x04u /* went through the global-scratch long path    */
+
+/* per-document flag bits written by dpt_encode_corpus */
+#define DPT_DF_AMBIGUOUS     0x01u /* SPM_LLAMA: run of >=2 U+2581; word split depends on BPE
+                                      merge order -> caller must pre-split this doc on the host */
+
+/* indices into the int64 counters[4] vector (SURVEY.md section 5 "metrics") */
+enum { DPT_CTR_BYTES = 0, DPT_CTR_WORDS = 1, DPT_CTR_TOKENS = 2, DPT_CTR_UNTOKENIZABLE = 3 };
+
+typedef struct dpt_vocab_info {
+    int32_t n_tokens;        /* distinct non-empty byte strings compiled           */
+    int32_t unit_mode;
+    int32_t n_nodes;         /* trie nodes                                         */
+    int32_t n_slots;         /* double-array slots (4 B each)                      */
+    int32_t max_token_bytes; /* Lmax                                               */
+    int32_t ph_buckets;      /* perfect hash: seed table entries                   */
+    int32_t ph_slots;        /* perfect hash: id table entries                     */
+    int32_t marker_leading_only; /* 1 if no token has U+2581 after a non-U+2581 char
+                                    (then SPM_LLAMA boundaries are exact for single spaces) */
+    int32_t byte_fallback;   /* 1 if all 256 "<0xHH>" strings are tokens           */
+    int32_t device;          /* device the blob is uploaded to, -1 if none         */
+    int64_t blob_bytes;      /* size of the device-resident compiled vocabulary    */
+} dpt_vocab_info;
+
+/* ---- vocabulary compiler: replaces `vocab = set(tok.get_vocab())` (tokenizer_utils.py:57),
+ *      `vocab_to_index` (tokenizer_utils.py:105-113) and the `in vocabulary` hash probe of
+ *      dp_tokenize.py:39.  Builds a double-array byte trie + a perfect hash bytes->id.
+ *      bytes/offs: token k is bytes[offs[k] .. offs[k+1]); ids[k] its id (any int32 >= 0).
+ *      Host-only; no CUDA needed. */
+int dpt_vocab_create(const uint8_t* bytes, const int64_t* offs, const int32_t* ids,
+                     int32_t n_tokens, int32_t unit_mode, dpt_vocab** out);
+void dpt_vocab_destroy(dpt_vocab* v);
+int dpt_vocab_get_info(const dpt_vocab* v, dpt_vocab_info* out);
+/* host-side exact lookup through the perfect hash (+ verify): id or -1 */
+int dpt_vocab_lookup(const dpt_vocab* v, const uint8_t* s, int32_t len, int32_t* id_out);
+/* serialise the compiled vocabulary (the only thing worth caching).
+ * Call with buf=NULL to get the size in *need. */
+int dpt_vocab_serialize(const dpt_vocab* v, uint8_t* buf, int64_t cap, int64_t* need);
+int dpt_vocab_deserialize(const uint8_t* buf, int64_t len, dpt_vocab** out);
+/* copy the compiled vocabulary into HBM of `device` (synchronous) */
+int dpt_vocab_upload(dpt_vocab* v, int device);
+
+/* ---- status vector written by the encode calls: device int64[8]
+ *      [0] ids required      (compare with ids_cap)      [1] words found (compare with word_cap)
+ *      [2] long-word pool positions required             [3] long-word pool capacity
+ *      [4] normalised-text bytes required (SPM_LLAMA)    [5] normalised-text capacity
+ *      A value above its capacity means the corresponding outputs were truncated: retry with
+ *      larger buffers / worst_case=1 workspace.                                             */
+#define DPT_NOUT_IDS 0
+#define DPT_NOUT_WORDS 1
+#define DPT_NOUT_POOL_REQ 2
+#define DPT_NOUT_POOL_CAP 3
+#define DPT_NOUT_NORM_REQ 4
+#define DPT_NOUT_NORM_CAP 5
+
+/* ---- workspace sizing (bytes of caller-owned device scratch).  worst_case=0 sizes the
+ *      variable parts for typical text; worst_case=1 can never overflow. */
+int64_t dpt_pretokenize_workspace(int64_t n_bytes, int64_t n_docs);
+int64_t dpt_encode_words_workspace(int64_t n_bytes, int64_t n_words, int32_t worst_case);
+int64_t dpt_encode_corpus_workspace(int32_t rule, int64_t n_bytes, int64_t n_docs, int64_t word_cap,
+                                    int32_t worst_case);
+
+/* ---- boundary kernel: replaces pretokenize_with_llama / pre_tokenize_str
+ *      (tokenizer_utils.py:24-31,157-159) for the rule classes above.
+ *      d_text: concatenated NON-EMPTY documents, d_doc_offs[n_docs+1] their byte offsets.
+ *      SPM_LLAMA: the text is normalised into d_norm_text (capacity norm_cap bytes) as
+ *      "<s>" + U+2581 + text with ' '->U+2581 and out-of-vocab characters spelled "<0xHH>"
+ *      per byte, exactly the concatenated token strings the reference's DP sees; '<s>' is a
+ *      word of its own (tokenizer_utils.py:26-30).  d_norm_doc_offs[n_docs+1] and
+ *      d_word_offs[<=word_cap+1] index d_norm_text; d_doc_first_word[n_docs] is the word index
+ *      of each document's '<s>' word (may be NULL).
+ *      d_n_out: device int64[2] = {n_words, n_norm_bytes} (compare with the capacities).
+ *      d_doc_flags: uint8[n_docs] (DPT_DF_*), may be NULL. */
+int dpt_pretokenize(const dpt_vocab* v, int32_t rule,
+                    const uint8_t* d_text, int64_t n_bytes,
+                    const int64_t* d_doc_offs, int64_t n_docs,
+                    uint8_t* d_norm_text, int64_t norm_cap, int64_t* d_norm_doc_offs,
+                    int64_t* d_word_offs, int64_t word_cap, int64_t* d_doc_first_word,
+                    uint8_t* d_doc_flags, int64_t* d_n_out,
+                    void* d_workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- the DP: replaces compute_shortest_tokenizations + obtain_longest_token + the id map
+ *      (dp_tokenize.py:24-84, tokenizer_utils.py:70-80,165-174) for n_words pre-split words.
+ *      Word w is d_text[d_word_offs[w] .. d_word_offs[w+1]) - already normalised bytes.
+ *      d_ids: capacity ids_cap int32, ids of all words concatenated in word order
+ *             (untokenizable words contribute none).
+ *      d_word_lens[w]  = len_dp[n] of dp_tokenize.py:70 (phantom value when untokenizable)
+ *      d_word_flags[w] = DPT_WF_* bits
+ *      d_word_tok_offs = optional int64[n_words+1] offsets of each word's ids in d_ids (NULL ok)
+ *      d_counters      = device int64[4] {bytes, words, tokens, untokenizable}, OVERWRITTEN
+ *                        (bytes = n_text_bytes as given)
+ *      d_n_out         = device int64[8] status vector (above)
+ *      Asynchronous: returns after enqueueing on `stream`. */
+int dpt_encode_words(const dpt_vocab* v,
+                     const uint8_t* d_text, const int64_t* d_word_offs, int64_t n_words,
+                     int64_t n_text_bytes,
+                     int32_t* d_ids, int64_t ids_cap,
+                     int32_t* d_word_lens, uint8_t* d_word_flags, int64_t* d_word_tok_offs,
+                     int64_t* d_counters, int64_t* d_n_out,
+                     void* d_workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- corpus throughput path: pretokenize + DP + compaction over raw documents resident in HBM
+ *      (the per-document loops of main_analyze_s2orc.py:269-298 and
+ *      main_biomed_translation.py:71-82).  Outputs as dpt_encode_words plus
+ *      d_doc_tok_offs[n_docs+1] (token offset of each document in d_ids; for SPM_LLAMA each
+ *      document's ids start with the id of '<s>' exactly as dp_tokenize_llama's output does) and
+ *      d_doc_flags[n_docs].  d_word_lens / d_word_flags have capacity word_cap. */
+int dpt_encode_corpus(const dpt_vocab* v, int32_t rule,
+                      const uint8_t* d_text, int64_t n_bytes,
+                      const int64_t* d_doc_offs, int64_t n_docs,
+                      int32_t* d_ids, int64_t ids_cap,
+                      int32_t* d_word_lens, uint8_t* d_word_flags, int64_t word_cap,
+                      int64_t* d_doc_tok_offs, uint8_t* d_doc_flags,
+                      int64_t* d_counters, int64_t* d_n_out,
+                      void* d_workspace, int64_t workspace_bytes, int32_t worst_case, void* stream);
+
+/* ---- lattice of ONE word for the enumerate-all API (dp_tokenize.py:27-47):
+ *      len_dp[0..n_units] and, per unit position, the ascending predecessor list
+ *      (segment_index_dp of dp_tokenize.py:30-47) in CSR form.
+ *      d_unit_starts: uint8[n_bytes], 1 where a unit starts (NULL = derive from unit_mode).
+ *      d_len_dp: int32[n_units+1]; d_pred_offs: int32[n_units+2]; d_pred: int32[pred_cap]
+ *      (unit indices); d_scratch: int32[n_bytes+1].  d_n_out: int32[2] = {n_units, n_pred}. */
+int dpt_lattice_word(const dpt_vocab* v, const uint8_t* d_text, int32_t n_bytes,
+                     const uint8_t* d_unit_starts,
+                     int32_t* d_len_dp, int32_t* d_pred_offs, int32_t* d_pred, int32_t pred_cap,
+                     int32_t* d_n_out, int32_t* d_scratch, void* stream);
+
+const char* dpt_last_error(void);
+const char* dpt_version(void);
+/* number of kernel launches issued by this library in the calling process (bench "gpu_launches") */
+int64_t dpt_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPTOK_H */
