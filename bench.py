@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Benchmark of the shortest-tokenization hot path (BASELINE.json metric: corpus bytes/s & tokens/s per GPU,
+% of HBM roofline).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun launches it for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+A step = one pass of the whole path (boundary/normalise -> DP -> compaction -> counters [+ NCCL count
+reduction]) over one batch of synthetic S2ORC-shaped text.  Workload at N=1 = BASELINE.json configs[1]:
+Llama-2-shaped 32k SentencePiece-BPE vocab, 100 MB of abstracts.  Multi-GPU = document-sharded, each rank its own
+100 MB shard (weak scaling), counters all-reduced once per step.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "dp-tokenization_b200"))
+
+METRIC = "corpus_bytes_per_sec"
+UNIT = "bytes/s"
+ASSET = "llama2_32k"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = f"/tmp/dpt_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_reference_leg(n_sample_bytes: int, budget_s: float):
+    """The reference's CPU path (oracle port, kind 'port') on all host cores, bounded sample."""
+    from dptok import synth
+    from oracle import cpu_baseline
+    docs = synth.sample_text(n_sample_bytes, seed=0)
+    r = cpu_baseline.run(ASSET, docs, budget_s=budget_s)
+    return r
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    per_step = []
+    total = {"bytes": 0, "tokens": 0, "seconds": 0.0}
+    cores = os.cpu_count() or 1
+    for k in range(args.warmup + args.steps):
+        r = cpu_reference_leg(4_000_000, budget_s=4.0 if k < args.warmup else 8.0)
+        if k >= args.warmup:
+            per_step.append(r)
+            for key in total:
+                total[key] += r[key]
+        cores = r["cores"]
+    v = total["bytes"] / total["seconds"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total["seconds"] / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "tokens_per_sec": total["tokens"] / total["seconds"],
+        "config": {"workload": "configs[1]: Llama-2-shaped 32k SentencePiece-BPE vocab, synthetic S2ORC-shaped abstracts",
+                   "vocab": ASSET, "note": "reference CPU path = oracle port of packages/dp_tokenize.py + "
+                   "tokenizer_utils.dp_tokenize_llama (pure-Python reference cannot travel to the GPU box)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{total['bytes']} bytes of the same synthetic corpus (seed 0) per {args.steps} steps, "
+                                   f"multiprocessing over documents"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size-mb", type=float, default=100.0, help="corpus bytes per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from dptok import _cabi, assets, engine as eng_mod, synth
+    from dptok.engine import Engine
+    from dptok.sharded import reduce_counters
+    from dptok.vocab import CompiledVocab
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: dptok has no CPU fallback"}))
+        return 2
+    torch.cuda.set_device(local_rank)
+    dev = torch.cuda.current_device()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- workload: this rank's shard (documents are independent; each rank generates its own) ----
+    n_bytes_target = int(args.size_mb * 1e6)
+    lexicon = synth.make_lexicon(200_000, seed=0)
+    text, doc_offs = synth.gen_documents(n_bytes_target, seed=rank, lexicon=lexicon)
+    n_bytes, n_docs = len(text), len(doc_offs) - 1
+    tok = assets.load_hf(ASSET)
+    t2i = tok.get_vocab()
+    engine = Engine(CompiledVocab.from_token_map(t2i, "spm"), dev)
+    h_text = torch.from_numpy(text).pin_memory()
+    h_offs = torch.from_numpy(doc_offs).pin_memory()
+    d_text = h_text.to(dev, non_blocking=True)
+    d_offs = h_offs.to(dev, non_blocking=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        res = engine.encode_corpus(d_text, d_offs, _cabi.RULE_SPM_LLAMA)
+        stats = reduce_counters(res.counters, None) if world > 1 else None
+        return res, stats
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        res, _ = step()
+    n_tokens, n_words = res.n_ids, res.n_words
+    ids_cap, word_cap = res.n_ids + 1024, res.n_words + 1024
+
+    # ---- timed region: K steps, device time by CUDA events, L2 flushed between steps --------------
+    launches0 = eng_mod.launch_count()
+    eng_mod.profile_enable(True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        ev[k][0].record()
+        res = engine.encode_corpus(d_text, d_offs, _cabi.RULE_SPM_LLAMA, ids_cap=ids_cap, word_cap=word_cap)
+        if world > 1:
+            reduce_counters(res.counters, None)
+        ev[k][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    eng_mod.profile_enable(False)
+    launches = eng_mod.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+    prof = eng_mod.profile_report()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([n_bytes, n_tokens, n_words], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    total_ms = float(t.item())
+    g_bytes, g_tokens, g_words = [int(x) for x in tot.tolist()]
+    value = g_bytes * args.steps / (total_ms / 1e3)
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    ab = n_bytes + 4 * n_tokens + 4 * n_words   # algorithmic bytes per step on this rank
+    roofline = None
+    if prof:
+        name, cnt, ms = prof[0]
+        per_launch_ms = ms / cnt
+        launches_per_step = cnt / args.steps
+        achieved = ab / launches_per_step / (per_launch_ms / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": ms / sum(r[2] for r in prof),
+                    "algorithmic_bytes_per_step": ab,
+                    "whole_path_achieved_gbs": ab * args.steps / (total_ms / 1e3) / 1e9,
+                    "kernels_ms_per_step": {r[0]: r[2] / args.steps for r in prof}}
+        tr = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        if os.path.isfile(tr):
+            try:
+                roofline["traffic"] = json.load(open(tr)).get(name)
+            except Exception:
+                pass
+
+    # ---- end to end through the public API with HOST buffers -------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_ids = torch.empty(ids_cap, dtype=torch.int32).pin_memory()
+        h_doc = torch.empty(n_docs + 1, dtype=torch.int64).pin_memory()
+        h_ctr = torch.empty(4, dtype=torch.int64).pin_memory()
+        d_in = torch.empty_like(d_text)
+        d_in_offs = torch.empty_like(d_offs)
+
+        def e2e_step():
+            d_in.copy_(h_text, non_blocking=True)
+            d_in_offs.copy_(h_offs, non_blocking=True)
+            r = engine.encode_corpus(d_in, d_in_offs, _cabi.RULE_SPM_LLAMA, ids_cap=ids_cap, word_cap=word_cap)
+            if world > 1:
+                reduce_counters(r.counters, None)
+            h_ids[:r.n_ids].copy_(r.ids, non_blocking=True)
+            h_doc.copy_(r.doc_tok_offs, non_blocking=True)
+            h_ctr.copy_(r.counters, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return r
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r = e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": g_bytes * args.steps / float(tt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(n_bytes + 8 * (n_docs + 1)),
+               "d2h_bytes_per_step": int(4 * r.n_ids + 8 * (n_docs + 1) + 32),
+               "tokens_per_sec": g_tokens * args.steps / float(tt.item())}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_leg(16_000_000, budget_s=15.0)
+        cpu = {"value": r["bytes_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "tokens_per_sec": r["tokens_per_s"],
+               "sample": f"{r['bytes']} bytes / {r['docs']} documents of the same synthetic corpus generator (seed 0), "
+                         f"{r['seconds']:.1f} s, reference algorithm (enumerating DP) under multiprocessing"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "tokens_per_sec": g_tokens * args.steps / (total_ms / 1e3),
+            "bytes_per_token": g_bytes / max(g_tokens, 1),
+            "config": {"workload": "configs[1]: Llama-2-shaped 32k SentencePiece-BPE vocab, 100 MB synthetic S2ORC-shaped "
+                                   "abstracts per GPU", "vocab": ASSET, "bytes_per_gpu": n_bytes, "docs_per_gpu": n_docs,
+                       "words_per_gpu": n_words, "tokens_per_gpu": n_tokens, "parallelism": f"doc-sharded x{world}",
+                       "l2": "256 MiB buffer written between timed steps (L2 flush)", "timing": "CUDA events per step"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "wall_s_timed_region": t_wall, "step_ms": step_ms,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

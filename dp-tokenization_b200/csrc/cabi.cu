@@ -79,6 +79,18 @@ extern "C" {
 const char* dpt_last_error(void) { return g_err.c_str(); }
 const char* dpt_version(void) { return "dptok-b200 0.1 (sm_100a)"; }
 int64_t dpt_launch_count(void) { return dpt::g_launches.load(); }
+void dpt_profile_enable(int32_t on) { dpt::profile_enable(on); }
+int dpt_profile_report(char* buf, int64_t cap, int64_t* need) {
+    static thread_local std::string pending;
+    if (!need) return fail(DPT_EINVAL, "dpt_profile_report: null argument");
+    if (pending.empty()) pending = dpt::profile_report();
+    *need = (int64_t)pending.size() + 1;
+    if (!buf) return DPT_OK;
+    if (cap < *need) return fail(DPT_ECAPACITY, "dpt_profile_report: buffer too small");
+    std::memcpy(buf, pending.c_str(), pending.size() + 1);
+    pending.clear();
+    return DPT_OK;
+}
 
 int dpt_vocab_create(const uint8_t* bytes, const int64_t* offs, const int32_t* ids, int32_t n_tokens, int32_t unit_mode,
                      dpt_vocab** out) {

@@ -84,6 +84,7 @@ DPT_HD bool dpt_backward_emit(const DptVocabView& V, const uint8_t* s, int32_t n
     int32_t i = n;
     while (i > 0) {
         const int32_t d = got ? A[i] : B[i];
+        if (d <= 0 || d > i) break;  // cannot happen on a reachable path; never spin on corrupt state
         const int32_t j = i - d;
         DptHashState h = dpt_hash_init(V.ph_salt);
         uint32_t cl = 0;

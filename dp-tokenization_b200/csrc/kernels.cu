@@ -5,9 +5,13 @@
 // tile kernel in fused.cu, which handles the common short-word case at speed.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <map>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/dptok.h"
 #include "dpt_dp_core.h"
@@ -506,8 +510,67 @@ __global__ void k_roundtrip(DptVocabView V, const int32_t* __restrict__ ids, con
 // ---------------------------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------------------------
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
+struct ProfRec {
+    const char* name;
+    cudaEvent_t a, b;
+};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static std::atomic<int> g_prof_on{0};
+
+struct ProfScope {
+    const char* name;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr;
+    ProfScope(const char* n, cudaStream_t s) : name(n), st(s) {
+        if (g_prof_on.load(std::memory_order_relaxed)) {
+            cudaEventCreate(&a);
+            cudaEventRecord(a, st);
+        }
+    }
+    ~ProfScope() {
+        if (a) {
+            cudaEvent_t b;
+            cudaEventCreate(&b);
+            cudaEventRecord(b, st);
+            std::lock_guard<std::mutex> lk(g_prof_mu);
+            g_prof.push_back({name, a, b});
+        }
+    }
+};
+
+void profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
+
+// "name launches total_ms\n" per kernel, sorted by total time; clears the records.  Synchronises.
+std::string profile_report() {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::map<std::string, std::pair<int64_t, double>> agg;
+    for (auto& r : g_prof) {
+        cudaEventSynchronize(r.b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        auto& e = agg[r.name];
+        e.first += 1;
+        e.second += ms;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    std::vector<std::pair<std::string, std::pair<int64_t, double>>> v(agg.begin(), agg.end());
+    std::sort(v.begin(), v.end(), [](auto& x, auto& y) { return x.second.second > y.second.second; });
+    std::string out;
+    char line[256];
+    for (auto& e : v) {
+        snprintf(line, sizeof line, "%s %lld %.6f\n", e.first.c_str(), (long long)e.second.first, e.second.second);
+        out += line;
+    }
+    return out;
+}
+
 #define DPT_LAUNCH(kernel, grid, block, stream, ...)                        \
     do {                                                                    \
+        ProfScope _prof(#kernel, (stream));                                 \
         kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);              \
         ++g_launches;                                                       \
     } while (0)
@@ -574,7 +637,7 @@ int encode_words(const dpt_vocab* v, const uint8_t* d_text, const int64_t* d_wor
     uint16_t* pool_b = cv.take<uint16_t>(pool_cap > 0 ? pool_cap : 0);
 
     cudaMemsetAsync(d_counters, 0, 4 * sizeof(int64_t), st);
-    cudaMemsetAsync(d_n_out, 0, 4 * sizeof(int64_t), st);
+    cudaMemsetAsync(d_n_out, 0, 8 * sizeof(int64_t), st);
     cudaMemsetAsync(ctl, 0, sizeof(LongCtl), st);
     cudaMemsetAsync(totals, 0, 4 * sizeof(int64_t), st);
     if (n_words > 0) {

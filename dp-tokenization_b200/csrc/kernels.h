@@ -11,6 +11,8 @@ struct dpt_vocab;
 namespace dpt {
 
 extern std::atomic<int64_t> g_launches;
+void profile_enable(int on);
+std::string profile_report();
 
 int64_t encode_words_workspace_fixed(int64_t n_words);
 int64_t pretokenize_workspace(int64_t n_bytes, int64_t n_docs);

@@ -65,6 +65,8 @@ SIGNATURES = {
     "dpt_last_error": (C.c_char_p, []),
     "dpt_version": (C.c_char_p, []),
     "dpt_launch_count": (_i64, []),
+    "dpt_profile_enable": (None, [_i32]),
+    "dpt_profile_report": (C.c_int, [C.c_char_p, _i64, C.POINTER(_i64)]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -189,6 +189,23 @@ def launch_count() -> int:
     return int(lib.dpt_launch_count())
 
 
+def profile_enable(on: bool):
+    lib.dpt_profile_enable(1 if on else 0)
+
+
+def profile_report():
+    """-> list of (kernel name, launches, total_ms) sorted by time; synchronises and clears."""
+    need = C.c_int64()
+    check(lib.dpt_profile_report(None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    check(lib.dpt_profile_report(buf, need.value, C.byref(need)))
+    rows = []
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        rows.append((name, int(cnt), float(ms)))
+    return rows
+
+
 def pack_documents(docs: Sequence[bytes]):
     """list of byte strings -> (uint8 array, int64 offsets) on the host."""
     offs = np.zeros(len(docs) + 1, dtype=np.int64)

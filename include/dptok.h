@@ -200,10 +200,24 @@ int dpt_lattice_word(const dpt_vocab* v, const uint8_t* d_text, int32_t n_bytes,
                      int32_t* d_len_dp, int32_t* d_pred_offs, int32_t* d_pred, int32_t pred_cap,
                      int32_t* d_n_out, int32_t* d_scratch, void* stream);
 
+/* ---- decode / round-trip check on device (tokenizer_utils.py:82-84,176-179; the asserts at
+ *      main_analyze_s2orc.py:85 and main_biomed_translation.py:78): ids -> bytes via the
+ *      id->string table (CODEPOINTS vocab: U+2581 -> ' ', "<0xHH>" tokens -> that byte, the one
+ *      leading space of the Prepend normaliser dropped), compared with the RAW text of each
+ *      document.  skip_bos=1 ignores the first id of every document.  d_ok: uint8[n_docs]. */
+int dpt_roundtrip_check(const dpt_vocab* v, const int32_t* d_ids, const int64_t* d_doc_tok_offs,
+                        const uint8_t* d_text, const int64_t* d_doc_offs, int64_t n_docs,
+                        int32_t skip_bos, uint8_t* d_ok, void* stream);
+
 const char* dpt_last_error(void);
 const char* dpt_version(void);
 /* number of kernel launches issued by this library in the calling process (bench "gpu_launches") */
 int64_t dpt_launch_count(void);
+/* per-kernel device timing with CUDA events on the launching stream (bench.py roofline leg):
+ * enable, run, then fetch "kernel_name launches total_ms" lines (call with buf=NULL for the size;
+ * the report synchronises and clears the records). */
+void dpt_profile_enable(int32_t on);
+int dpt_profile_report(char* buf, int64_t cap, int64_t* need);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,320 @@
+"""GPU parity tests: the CUDA path, called through the reference-shaped Python surface and the C ABI, against
+the committed golden vectors (outputs of the unmodified reference) and against the CPU oracle on the same
+seeded inputs.  Bit-exact: token ids, per-word lengths, tie choices, counters.  Run with ``-m gpu`` on a B200.
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from helpers import bytelevel_table, pack, sha1_json, vocab_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.cuda.current_device()
+
+
+def _to_dev(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-shaped surface: packages.dp_tokenize
+# ------------------------------------------------------------------------------------------------
+def test_known_answers_through_reference_surface(dev):
+    """tests/test_tokenization_algorithms.py:32-48 verbatim, plus the full returns the reference gives."""
+    from packages.dp_tokenize import compute_shortest_tokenizations, obtain_longest_token
+    V = ["un", "desirable"] + ["und", "esirable"] + list("undesirable")
+    shortest_tokenizations, shortest_length = compute_shortest_tokenizations("undesirable", V, False, "")
+    assert ["un", "desirable"] in shortest_tokenizations
+    assert ["und", "esirable"] in shortest_tokenizations
+    V = list("desireableish") + ["desire", "able", "ish"] + ["des", "ireable", "ish"]
+    shortest_tokenizations, shortest_length = compute_shortest_tokenizations("desireableish", V, False, "")
+    assert ["desire", "able", "ish"] in shortest_tokenizations
+    assert ["des", "ireable", "ish"] in shortest_tokenizations
+
+    k = load_golden("known_answers.json")
+    for r in k["shortest"]:
+        got = compute_shortest_tokenizations(r["s"], r["vocab"], False, "")
+        assert got == (r["all"], r["len"])
+        assert obtain_longest_token(got[0]) == r["sel"]
+    for r in k["phantom"]:
+        assert compute_shortest_tokenizations(r["s"], set(r["vocab"]), False, "") == ([], r["len"])
+    sm = k["strip_marker"]
+    assert compute_shortest_tokenizations(sm["s"], sm["vocab"], True, sm["marker"]) == (sm["all"], sm["len"])
+    # a 5th positional argument is accepted (tokenizer_utils.py:71)
+    assert compute_shortest_tokenizations("abcd", k["shortest"][2]["vocab"], False, None, 1)[1] == 2
+    with pytest.raises(IndexError):
+        compute_shortest_tokenizations("", ["a"], False, "")
+    with pytest.raises(ValueError):
+        obtain_longest_token([])
+    # list-of-units input with multi-character units (test_llama_tokenizer builds such lists, :58-68)
+    units = ["▁t", "h", "e", "▁", "w"]
+    vocab = {"▁t", "h", "e", "▁", "w", "▁the", "he", "▁w"}
+    from oracle import dp_oracle
+    assert compute_shortest_tokenizations(units, vocab, False, None) == dp_oracle.enumerate_shortest(units, vocab)
+
+
+def test_c0_full_return_every_word(dev):
+    """Config C0: the FULL return of compute_shortest_tokenizations for 10,000 words (first 2,500 through the
+    enumerate-all API; all 10,000 through the batched select-on-device path)."""
+    from packages.dp_tokenize import compute_shortest_tokenizations, obtain_longest_token
+    from dptok.engine import Engine
+    from dptok.vocab import CompiledVocab
+    g = load_golden("c0_toy.json.gz")
+    vocab = set(g["vocab"])
+    for r in g["rows"][:2500]:
+        got, length = compute_shortest_tokenizations(r["w"], vocab, False, "")
+        assert length == r["len"] and len(got) == r["n"] and sha1_json(got) == r["sha1"], r["w"]
+        if got:
+            assert obtain_longest_token(got) == r["sel"]
+    eng = Engine(CompiledVocab.from_token_map({t: k for k, t in enumerate(g["vocab"])}, "spm"))
+    text, offs = pack([r["w"].encode() for r in g["rows"]])
+    res = eng.encode_words(_to_dev(text, dev), _to_dev(offs, dev), want_tok_offs=True)
+    ids = res.ids.cpu().numpy()
+    lens = res.word_lens.cpu().numpy()
+    flags = res.word_flags.cpu().numpy()
+    to = res.word_tok_offs.cpu().numpy()
+    n_untok = 0
+    for k, r in enumerate(g["rows"]):
+        assert lens[k] == r["len"]
+        if r["sel"] is None:
+            assert flags[k] & 1 and to[k + 1] == to[k]
+            n_untok += 1
+        else:
+            assert not (flags[k] & 1)
+            assert [g["vocab"][i] for i in ids[to[k]:to[k + 1]]] == r["sel"]
+    c = res.counters.cpu().tolist()
+    assert c == [len(text), len(g["rows"]), len(ids), n_untok]
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-shaped surface: packages.tokenizer_utils
+# ------------------------------------------------------------------------------------------------
+def test_llama_adapter_golden(dev):
+    from dptok import assets
+    from packages.tokenizer_utils import dp_tokenize_llama, pretokenize_with_llama, _BiMap
+    g = load_golden("llama_adapter.json.gz")
+    tok = assets.load_hf(g["tokenizer"])
+    dp_encode_llama, invert_dp_tokenize = dp_tokenize_llama(tok)
+    split = pretokenize_with_llama(tok, _BiMap(tok.get_vocab()))
+    for r in g["rows"]:
+        encoding = dp_encode_llama(r["text"])
+        assert encoding == r["ids"], r["text"][:60]
+        assert invert_dp_tokenize(encoding) == r["text"]
+        assert len(encoding) <= r["default_len"]
+        assert split(r["text"]) == r["words"]
+    # batched call = same ids
+    texts = [r["text"] for r in g["rows"]]
+    assert dp_encode_llama.batch(texts) == [r["ids"] for r in g["rows"]]
+    # 'raw' option (tokenizer_utils.py:33-50)
+    enc_raw, _ = dp_tokenize_llama(tok, "raw")
+    for r in g["raw"]:
+        if "ids" in r:
+            assert enc_raw(r["text"]) == r["ids"]
+
+
+def test_bytelevel_adapter_golden(dev):
+    from dptok import assets
+    from packages.tokenizer_utils import dp_tokenize_bloom
+    g = load_golden("bytelevel_adapter.json.gz")
+    for name, rows in g.items():
+        tok = assets.load_hf(name)
+        dp_encode_bloom, invert_dp_tokenize = dp_tokenize_bloom(tok, None)
+        for r in rows:
+            encoding_dp = dp_encode_bloom(r["text"])
+            assert encoding_dp == r["ids"], (name, r["text"][:60])
+            assert invert_dp_tokenize(encoding_dp) == r["text"]
+            assert len(encoding_dp) <= r["default_len"]
+        assert dp_encode_bloom.batch([r["text"] for r in rows]) == [r["ids"] for r in rows]
+
+
+# ------------------------------------------------------------------------------------------------
+# C ABI at scale against the oracle
+# ------------------------------------------------------------------------------------------------
+def _llama_engine(name, dev):
+    from dptok import assets
+    from dptok.engine import Engine
+    from dptok.vocab import CompiledVocab
+    tok = assets.load_hf(name)
+    t2i = tok.get_vocab()
+    return tok, t2i, Engine(CompiledVocab.from_token_map(t2i, "spm"), dev)
+
+
+def test_corpus_path_vs_oracle_llama32k(dev):
+    """8 MB of S2ORC-shaped text, Llama-2-shaped 32k vocab: ids, per-word lengths, flags, counters and document
+    offsets bit-exact against the C oracle run on independently normalised words; the device word split is
+    additionally checked against the tokenizer-driven split of the reference on a document sample."""
+    from dptok import _cabi, synth
+    from oracle import adapters
+    from oracle.c_oracle import COracle
+    tok, t2i, eng = _llama_engine("llama2_32k", dev)
+    text, doc_offs = synth.gen_documents(8_000_000, seed=0, newline_headers=True)
+    raw = text.tobytes()
+    n_docs = len(doc_offs) - 1
+    res = eng.encode_corpus(_to_dev(text, dev), _to_dev(doc_offs, dev), _cabi.RULE_SPM_LLAMA)
+    vocab = set(t2i)
+    words = []
+    first_word = []
+    for d in range(n_docs):
+        first_word.append(len(words))
+        words += [w.encode() for w in adapters.spm_normalise(raw[doc_offs[d]:doc_offs[d + 1]].decode(), vocab)]
+    wtext, woffs = pack(words)
+    o_ids, o_lens, o_untok = COracle(vocab_bytes(t2i, "spm"), 1).encode_words(wtext, woffs)
+    assert res.n_words == len(words)
+    assert np.array_equal(res.word_lens.cpu().numpy(), o_lens)
+    assert np.array_equal(res.word_flags.cpu().numpy() & 1, o_untok)
+    assert np.array_equal(res.ids.cpu().numpy(), o_ids)
+    assert res.counters.cpu().tolist() == [len(raw), len(words), len(o_ids), int(o_untok.sum())]
+    assert not res.doc_flags.cpu().numpy().any()
+    tok_of_word = np.concatenate([[0], np.cumsum(np.where(o_untok == 0, o_lens, 0))])
+    assert np.array_equal(res.doc_tok_offs.cpu().numpy(), tok_of_word[first_word + [len(words)]])
+    # the rule itself vs. the reference's tokenizer-driven split
+    for d in random.Random(0).sample(range(n_docs), 60):
+        doc = raw[doc_offs[d]:doc_offs[d + 1]].decode()
+        assert [w.decode() for w in words[first_word[d]:(first_word + [len(words)])[d + 1]]] == adapters.llama_words(tok, doc)
+    # decode + round trip on device (main_analyze_s2orc.py:85)
+    ok = eng.roundtrip_ok(res, _to_dev(text, dev), _to_dev(doc_offs, dev), skip_bos=True)
+    assert bool(ok.all())
+    # a corrupted id must be caught
+    bad = res.ids.clone()
+    bad[5] = bad[5] + 1 if int(bad[5]) + 1 < len(t2i) else 3
+    res_bad = type(res)(bad, res.word_lens, res.word_flags, None, res.counters, res.n_ids, res.n_words, res.doc_tok_offs,
+                        res.doc_flags)
+    assert not bool(eng.roundtrip_ok(res_bad, _to_dev(text, dev), _to_dev(doc_offs, dev), skip_bos=True)[0])
+
+
+def test_presplit_bytelevel_vs_oracle_gpt2_50k(dev):
+    """Byte-level path (GPT-2-shaped 50k vocab): words from the installed `tokenizers` pre-tokenizer
+    (tokenizer_utils.py:157-159), DP on the GPU, against the C oracle."""
+    from dptok import assets, synth
+    from dptok.engine import Engine
+    from dptok.vocab import CompiledVocab
+    from oracle.c_oracle import COracle
+    tok = assets.load_tokenizer("gpt2_50k")
+    v2i = {t: k for k, t in enumerate(assets.load_spec("gpt2_50k")["model"]["vocab"])}
+    eng = Engine(CompiledVocab.from_token_map(v2i, "bytelevel"), dev)
+    text, doc_offs = synth.gen_sentence_pairs(3_000_000, seed=0)
+    raw = text.tobytes()
+    u2b = {c: b for b, c in bytelevel_table().items()}
+    words = []
+    for d in range(len(doc_offs) - 1):
+        for piece, _span in tok.pre_tokenizer.pre_tokenize_str(raw[doc_offs[d]:doc_offs[d + 1]].decode()):
+            words.append(bytes(u2b[c] for c in piece))
+    assert b"".join(words) == raw          # byte-level pieces tile the text
+    wtext, woffs = pack(words)
+    res = eng.encode_words(_to_dev(wtext, dev), _to_dev(woffs, dev))
+    o_ids, o_lens, o_untok = COracle(vocab_bytes(v2i, "bytelevel"), 0).encode_words(wtext, woffs)
+    assert np.array_equal(res.ids.cpu().numpy(), o_ids)
+    assert np.array_equal(res.word_lens.cpu().numpy(), o_lens)
+    assert not o_untok.any() and not (res.word_flags.cpu().numpy() & 1).any()
+
+
+def test_edge_cases_long_oov_untokenizable(dev):
+    """Ragged inputs: 1-byte words, words longer than the local-state limit (long path, thousands of bytes),
+    out-of-vocabulary characters (literal <0xHH> expansion), untokenizable words (phantom lengths), a vocabulary
+    with long tokens; capacity retry paths."""
+    from dptok.engine import Engine
+    from dptok.vocab import CompiledVocab
+    from oracle.c_oracle import COracle
+    rng = random.Random(11)
+    alpha = "abcdeé▁日"
+    toks = set(alpha[:6])
+    for _ in range(400):
+        toks.add("".join(rng.choice(alpha) for _ in range(rng.randint(2, 9))))
+    toks.add("ab" * 40)            # an 80-byte token
+    toks.add("é" * 50)             # 100 bytes, 50 code points
+    t2i = {t: k + 5 for k, t in enumerate(sorted(toks))}
+    eng = Engine(CompiledVocab.from_token_map(t2i, "spm"), dev)
+    words = []
+    for k in range(6000):
+        n = rng.choice([1, 1, 2, 3, 5, 8, 13, 21, 34, 63, 64, 65, 66, 100, 200])
+        if k % 500 == 0:
+            n = rng.randint(1500, 6000)
+        w = "".join(rng.choice(alpha) for _ in range(n))
+        if k % 97 == 0:
+            w = "ab" * rng.randint(30, 90)
+        if k % 89 == 0:
+            w = "é" * rng.randint(40, 120)
+        words.append(w.encode())
+    wtext, woffs = pack(words)
+    o_ids, o_lens, o_untok = COracle(vocab_bytes(t2i, "spm"), 1).encode_words(wtext, woffs)
+    assert 0 < o_untok.sum() < len(words)    # '▁' and '日' alone are not tokens: some words are untokenizable
+    for ids_cap in (None, 16):               # 16 forces the ids-capacity retry
+        res = eng.encode_words(_to_dev(wtext, dev), _to_dev(woffs, dev), ids_cap=ids_cap)
+        assert np.array_equal(res.word_lens.cpu().numpy(), o_lens)
+        assert np.array_equal(res.word_flags.cpu().numpy() & 1, o_untok)
+        assert np.array_equal(res.ids.cpu().numpy(), o_ids)
+    long_flag = (res.word_flags.cpu().numpy() & 4) != 0
+    assert np.array_equal(long_flag, (woffs[1:] - woffs[:-1]) > 64)
+
+
+def test_spm_rule_oov_and_ambiguous_docs(dev):
+    """Device rule on text with OOV characters (CJK, dashes), newlines/tabs, and documents whose split is
+    ambiguous (double spaces): flagged, and the public adapter still returns the reference's ids for them."""
+    from dptok import _cabi, assets
+    from dptok.engine import pack_documents
+    from oracle import adapters
+    tok, t2i, eng = _llama_engine("llama2_2k", dev)
+    from packages.tokenizer_utils import dp_tokenize_llama
+    enc, dec = dp_tokenize_llama(tok)
+    rng = random.Random(3)
+    pieces = ["plai", "gout", "é", "ï", "日", "本", "\n", "\t", ",", "Zeta", "(x)", "12", "—", "naïve", "%", "trot"]
+    docs = []
+    for k in range(400):
+        ws = ["".join(rng.choice(pieces) for _ in range(rng.randint(1, 4))) for _ in range(rng.randint(1, 12))]
+        sep = "  " if k % 10 == 0 else " "
+        docs.append(sep.join(ws))
+    text, offs = pack_documents([d.encode() for d in docs])
+    res = eng.encode_corpus(_to_dev(text, dev), _to_dev(offs, dev), _cabi.RULE_SPM_LLAMA)
+    flags = res.doc_flags.cpu().numpy()
+    ids = res.ids.cpu().numpy()
+    dto = res.doc_tok_offs.cpu().numpy()
+    for k, d in enumerate(docs):
+        expect = adapters.llama_encode(tok, d)
+        assert bool(flags[k]) == ("  " in d)
+        if not flags[k]:
+            assert ids[dto[k]:dto[k + 1]].tolist() == expect
+        assert enc(d) == expect and dec(expect) == d
+    assert enc.batch(docs[:50]) == [adapters.llama_encode(tok, d) for d in docs[:50]]
+
+
+def test_full_size_properties_100mb(dev):
+    """BASELINE.json configs[1] at full size (100 MB, Llama-2-shaped 32k vocab): size-independent properties -
+    device decode round-trips every document, counters are consistent, the DP never uses more tokens than the
+    default BPE, two runs are identical - plus exact oracle parity on a 1,500-document sample."""
+    from dptok import _cabi, synth
+    from oracle import adapters
+    from oracle.c_oracle import COracle
+    tok, t2i, eng = _llama_engine("llama2_32k", dev)
+    text, doc_offs = synth.gen_documents(100_000_000, seed=0)
+    n_docs = len(doc_offs) - 1
+    d_text, d_offs = _to_dev(text, dev), _to_dev(doc_offs, dev)
+    res = eng.encode_corpus(d_text, d_offs, _cabi.RULE_SPM_LLAMA)
+    c = res.counters.cpu().tolist()
+    assert c[0] == len(text) and c[1] == res.n_words and c[2] == res.n_ids and c[3] == 0
+    assert int(res.word_lens.sum()) == res.n_ids
+    assert bool(eng.roundtrip_ok(res, d_text, d_offs, skip_bos=True).all())
+    dto = res.doc_tok_offs.cpu().numpy()
+    assert dto[0] == 0 and dto[-1] == res.n_ids and (np.diff(dto) > 0).all()
+    res2 = eng.encode_corpus(d_text, d_offs, _cabi.RULE_SPM_LLAMA)
+    assert torch.equal(res.ids, res2.ids) and torch.equal(res.word_lens, res2.word_lens)
+    ids = res.ids.cpu().numpy()
+    raw = text.tobytes()
+    vocab = set(t2i)
+    co = COracle(vocab_bytes(t2i, "spm"), 1)
+    sample = random.Random(1).sample(range(n_docs), 1500)
+    for d in sample:
+        doc = raw[doc_offs[d]:doc_offs[d + 1]].decode()
+        wtext, woffs = pack([w.encode() for w in adapters.spm_normalise(doc, vocab)])
+        o_ids, _, _ = co.encode_words(wtext, woffs)
+        assert np.array_equal(ids[dto[d]:dto[d + 1]], o_ids)
+    for d in sample[:40]:
+        doc = raw[doc_offs[d]:doc_offs[d + 1]].decode()
+        assert dto[d + 1] - dto[d] <= len(tok.encode(doc))
