@@ -371,10 +371,10 @@ __global__ void k_finish_counters(unsigned long long* __restrict__ counters, int
         counters[DPT_CTR_BYTES] = (unsigned long long)n_bytes;
         counters[DPT_CTR_WORDS] = (unsigned long long)n_words;
         counters[DPT_CTR_TOKENS] = (unsigned long long)total_tokens[0];
-        n_out[0] = total_tokens[0];
-        n_out[1] = n_words;
-        n_out[2] = pool_cap;
-        n_out[3] = (int64_t)ctl->pool_used;
+        n_out[DPT_NOUT_IDS] = total_tokens[0];
+        n_out[DPT_NOUT_WORDS] = n_words;
+        n_out[DPT_NOUT_POOL_REQ] = (int64_t)ctl->pool_used;
+        n_out[DPT_NOUT_POOL_CAP] = pool_cap;
     }
 }
 

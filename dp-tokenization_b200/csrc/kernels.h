@@ -17,7 +17,7 @@ std::string profile_report();
 int64_t encode_words_workspace_fixed(int64_t n_words);
 int64_t pretokenize_workspace(int64_t n_bytes, int64_t n_docs);
 
-// d_n_out: int64[4] = {n_ids, n_words, long-pool capacity (positions), long-pool required}
+// d_n_out: int64[8] status vector (DPT_NOUT_* in include/dptok.h)
 int encode_words(const dpt_vocab* v, const uint8_t* d_text, const int64_t* d_word_offs, int64_t n_words,
                  int64_t n_bytes_for_counter, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens,
                  uint8_t* d_word_flags, int64_t* d_word_tok_offs, int64_t* d_counters, int64_t* d_n_out, void* d_ws,

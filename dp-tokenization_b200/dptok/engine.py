@@ -71,7 +71,7 @@ class Engine:
             ids_cap = n_bytes // 2 + n_words + 64
         worst = 0
         with torch.cuda.device(dev):
-            while True:
+            for attempt in range(4):
                 ids = torch.empty(max(ids_cap, 1), dtype=torch.int32, device=dev)
                 lens = torch.empty(max(n_words, 1), dtype=torch.int32, device=dev)
                 flags = torch.empty(max(n_words, 1), dtype=torch.uint8, device=dev)
@@ -89,10 +89,14 @@ class Engine:
                     ids_cap = h[_cabi.NOUT_IDS]
                     retry = True
                 if h[_cabi.NOUT_POOL_REQ] > h[_cabi.NOUT_POOL_CAP]:
+                    if worst:
+                        raise _cabi.DptError(_cabi.ECAPACITY, f"worst-case workspace still too small: {h}")
                     worst = 1
                     retry = True
                 if not retry:
                     break
+            else:
+                raise _cabi.DptError(_cabi.ECAPACITY, f"capacity retries exhausted: {h}")
         return EncodeResult(ids[:h[0]], lens[:n_words], flags[:n_words], tok_offs, counters, h[0], n_words)
 
     # ---- corpus path: raw documents -> ids ------------------------------------------------------
@@ -109,7 +113,7 @@ class Engine:
             word_cap = n_bytes // 3 + 2 * n_docs + 64
         worst = 0
         with torch.cuda.device(dev):
-            while True:
+            for attempt in range(5):
                 ids = torch.empty(ids_cap, dtype=torch.int32, device=dev)
                 lens = torch.empty(word_cap, dtype=torch.int32, device=dev)
                 flags = torch.empty(word_cap, dtype=torch.uint8, device=dev)
@@ -131,7 +135,7 @@ class Engine:
                     retry = True
                 if h[_cabi.NOUT_NORM_REQ] > h[_cabi.NOUT_NORM_CAP] or h[_cabi.NOUT_POOL_REQ] > h[_cabi.NOUT_POOL_CAP]:
                     if worst:
-                        raise _cabi.DptError(_cabi.ECAPACITY, "worst-case workspace still too small")
+                        raise _cabi.DptError(_cabi.ECAPACITY, f"worst-case workspace still too small: {h}")
                     worst = 1
                     retry = True
                 if h[_cabi.NOUT_IDS] > ids_cap:
@@ -141,6 +145,8 @@ class Engine:
                     check(rc)
                 if not retry:
                     break
+            else:
+                raise _cabi.DptError(_cabi.ECAPACITY, f"capacity retries exhausted: {h}")
         nw = h[_cabi.NOUT_WORDS]
         return EncodeResult(ids[:h[0]], lens[:nw], flags[:nw], None, counters, h[0], nw, doc_tok, doc_flags)
 
