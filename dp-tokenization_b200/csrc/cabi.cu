@@ -201,7 +201,7 @@ int dpt_vocab_deserialize(const uint8_t* buf, int64_t len, dpt_vocab** out) {
         delete v;
         return fail(DPT_EINVAL, "dpt_vocab_deserialize: truncated or corrupt buffer");
     }
-    v->rebuild_host_view();
+    v->derive_facts();
     *out = v;
     return DPT_OK;
 }
@@ -305,7 +305,7 @@ static int64_t corpus_norm_cap(int64_t n_bytes, int64_t n_docs, int worst) {
     return worst ? 6 * n_bytes + 6 * n_docs + 64 : n_bytes + n_bytes / 8 + 6 * n_docs + 4096;
 }
 
-int64_t dpt_encode_corpus_workspace(int32_t rule, int64_t n_bytes, int64_t n_docs, int64_t word_cap, int32_t worst_case) {
+int64_t dpt_encode_corpus_general_workspace(int32_t rule, int64_t n_bytes, int64_t n_docs, int64_t word_cap, int32_t worst_case) {
     (void)rule;
     int64_t b = 0;
     const int64_t norm_cap = corpus_norm_cap(n_bytes, n_docs, worst_case);
@@ -319,16 +319,17 @@ int64_t dpt_encode_corpus_workspace(int32_t rule, int64_t n_bytes, int64_t n_doc
     return b + 4096;
 }
 
-int dpt_encode_corpus(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, int64_t n_bytes, const int64_t* d_doc_offs,
-                      int64_t n_docs, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens, uint8_t* d_word_flags,
-                      int64_t word_cap, int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters,
-                      int64_t* d_n_out, void* d_workspace, int64_t workspace_bytes, int32_t worst_case, void* stream) {
-    if (int rc = check_ready(v, "dpt_encode_corpus")) return rc;
+int dpt_encode_corpus_general(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, int64_t n_bytes,
+                              const int64_t* d_doc_offs, int64_t n_docs, int32_t* d_ids, int64_t ids_cap,
+                              int32_t* d_word_lens, uint8_t* d_word_flags, int64_t word_cap, int64_t* d_doc_tok_offs,
+                              uint8_t* d_doc_flags, int64_t* d_counters, int64_t* d_n_out, void* d_workspace,
+                              int64_t workspace_bytes, int32_t worst_case, void* stream) {
+    if (int rc = check_ready(v, "dpt_encode_corpus_general")) return rc;
     if (rule != DPT_RULE_SPM_LLAMA)
-        return fail(DPT_EINVAL, "dpt_encode_corpus: only DPT_RULE_SPM_LLAMA runs its boundary rule on device in this "
+        return fail(DPT_EINVAL, "dpt_encode_corpus_general: only DPT_RULE_SPM_LLAMA runs its boundary rule on device in this "
                                 "build; use dpt_encode_words with host pre-split words");
     if (!d_doc_tok_offs || !d_n_out || word_cap <= 0) return fail(DPT_EINVAL, "dpt_encode_corpus: bad argument");
-    if (workspace_bytes < dpt_encode_corpus_workspace(rule, n_bytes, n_docs, word_cap, worst_case))
+    if (workspace_bytes < dpt_encode_corpus_general_workspace(rule, n_bytes, n_docs, word_cap, worst_case))
         return fail(DPT_ECAPACITY, "dpt_encode_corpus: workspace too small (see dpt_encode_corpus_workspace)");
     cudaStream_t st = (cudaStream_t)stream;
     char* base = (char*)d_workspace;
@@ -376,6 +377,27 @@ int dpt_encode_corpus(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, i
     rc = dpt::doc_tok_offsets(first_word, n_docs, tok_offs, n_words, d_doc_tok_offs, st);
     if (rc) return fail(rc, "dpt_encode_corpus: doc offsets kernel failed");
     return DPT_OK;
+}
+
+// ---- fused single-launch corpus entry (fused.cu): asynchronous, no host synchronisation ----------------
+int64_t dpt_encode_corpus_workspace(int32_t rule, int64_t n_bytes) {
+    (void)rule;
+    return dpt::encode_corpus_fused_workspace(n_bytes);
+}
+
+int dpt_encode_corpus(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, int64_t n_bytes, const int64_t* d_doc_offs,
+                      int64_t n_docs, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens, uint8_t* d_word_flags,
+                      int64_t word_cap, int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters,
+                      int64_t* d_n_out, void* d_workspace, int64_t workspace_bytes, void* stream) {
+    if (int rc = check_ready(v, "dpt_encode_corpus")) return rc;
+    if (rule != DPT_RULE_SPM_LLAMA)
+        return fail(DPT_EINVAL, "dpt_encode_corpus: rule not available on device in this build; pre-split on the host "
+                                "and call dpt_encode_words");
+    std::string err;
+    const int rc = dpt::encode_corpus_fused(v, rule, d_text, n_bytes, d_doc_offs, n_docs, d_ids, ids_cap, d_word_lens,
+                                            d_word_flags, word_cap, d_doc_tok_offs, d_doc_flags, d_counters, d_n_out,
+                                            d_workspace, workspace_bytes, (cudaStream_t)stream, err);
+    return rc ? fail(rc, err) : DPT_OK;
 }
 
 int dpt_lattice_word(const dpt_vocab* v, const uint8_t* d_text, int32_t n_bytes, const uint8_t* d_unit_starts,

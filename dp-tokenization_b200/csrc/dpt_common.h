@@ -46,6 +46,14 @@ struct DptVocabView {
     int32_t id_space;          // max id + 1
     uint32_t marker_entry;     // DA entry after consuming U+2581 from the root (0 if absent)
     uint32_t ascii_single[4];  // bit c set  <=>  the 1-byte string c is a token
+    uint32_t marker_slot;      // slot index of that node (slot_id[marker_slot] = id of the bare marker)
+    // the word "<s>" every SPM_LLAMA document starts with (tokenizer_utils.py:26-30), solved once at compile time
+    int32_t bos_len;           // len_dp[n] of the word "<s>"
+    int32_t bos_ntok;          // ids it contributes (0 when untokenizable)
+    int32_t bos_ids[3];
+    // all 256 single bytes are tokens (byte-level) / U+2581 alone is a token (code points): then no position
+    // is unreachable for in-vocabulary characters and the phantom init of dp_tokenize.py:28 never undercuts
+    int32_t fast_ok;
 };
 
 // One trie step.  `entry` is the slot VALUE of the current node (it carries the base), not its

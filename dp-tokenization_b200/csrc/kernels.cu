@@ -519,26 +519,21 @@ static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
 static std::atomic<int> g_prof_on{0};
 
-struct ProfScope {
-    const char* name;
-    cudaStream_t st;
-    cudaEvent_t a = nullptr;
-    ProfScope(const char* n, cudaStream_t s) : name(n), st(s) {
-        if (g_prof_on.load(std::memory_order_relaxed)) {
-            cudaEventCreate(&a);
-            cudaEventRecord(a, st);
-        }
+ProfScope::ProfScope(const char* n, cudaStream_t s) : name(n), st(s) {
+    if (g_prof_on.load(std::memory_order_relaxed)) {
+        cudaEventCreate(&a);
+        cudaEventRecord(a, st);
     }
-    ~ProfScope() {
-        if (a) {
-            cudaEvent_t b;
-            cudaEventCreate(&b);
-            cudaEventRecord(b, st);
-            std::lock_guard<std::mutex> lk(g_prof_mu);
-            g_prof.push_back({name, a, b});
-        }
+}
+ProfScope::~ProfScope() {
+    if (a) {
+        cudaEvent_t b;
+        cudaEventCreate(&b);
+        cudaEventRecord(b, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.push_back({name, a, b});
     }
-};
+}
 
 void profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
 

@@ -3,7 +3,10 @@
 // operation of dp_tokenize.py:39.  Host-only C++; the result is uploaded to HBM as one blob.
 #include "vocab.h"
 
+#include "dpt_dp_core.h"
+
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -80,6 +83,70 @@ void dpt_vocab::rebuild_host_view() {
     h_view.id_space = id_space;
     h_view.marker_entry = marker_entry;
     for (int k = 0; k < 4; ++k) h_view.ascii_single[k] = ascii_single[k];
+    h_view.marker_slot = marker_slot;
+    h_view.bos_len = bos_len;
+    h_view.bos_ntok = bos_ntok;
+    for (int k = 0; k < 3; ++k) h_view.bos_ids[k] = bos_ids[k];
+    h_view.fast_ok = fast_ok;
+}
+
+void dpt_vocab::derive_facts() {
+    dpt_vocab* v = this;
+    {
+        uint32_t e = DPT_DA_ROOT_ENTRY, slot = 0;
+        bool ok = dpt_da_step(v->da.data(), e, DPT_MARK0) && dpt_da_step(v->da.data(), e, DPT_MARK1) &&
+                  dpt_da_step_idx(v->da.data(), e, DPT_MARK2, slot);
+        v->marker_entry = ok ? e : 0u;
+        v->marker_slot = ok ? slot : 0u;
+        for (int k = 0; k < 4; ++k) v->ascii_single[k] = 0;
+        int n_single = 0;
+        for (uint32_t c = 0; c < 256; ++c) {
+            uint32_t e1 = DPT_DA_ROOT_ENTRY;
+            if (dpt_da_step(v->da.data(), e1, c) && (e1 & DPT_DA_TERMINAL)) {
+                if (c < 128) v->ascii_single[c >> 5] |= 1u << (c & 31);
+                ++n_single;
+            }
+        }
+        v->fast_ok = v->unit_mode == 0 ? (n_single == 256) : (ok && (e & DPT_DA_TERMINAL));
+        v->byte_fallback = 1;
+        for (int b = 0; b < 256; ++b) {
+            char lit[8];
+            snprintf(lit, sizeof lit, "<0x%02X>", b);
+            uint32_t e2 = DPT_DA_ROOT_ENTRY, slot2 = 0;
+            bool hit = true;
+            for (int p = 0; p < 6 && hit; ++p) hit = dpt_da_step_idx(v->da.data(), e2, (uint8_t)lit[p], slot2);
+            v->byte_token_id[b] = (hit && (e2 & DPT_DA_TERMINAL)) ? v->slot_id[slot2] : -1;
+            if (v->byte_token_id[b] < 0) v->byte_fallback = 0;
+        }
+        v->marker_leading_only = 1;
+        for (int32_t r = 0; r < v->n_tokens && v->marker_leading_only; ++r) {
+            const uint8_t* s = v->tok_bytes.data() + v->tok_offs[r];
+            const int32_t len = (int32_t)(v->tok_offs[r + 1] - v->tok_offs[r]);
+            bool seen_other = false;
+            for (int32_t p = 0; p < len;) {
+                const bool mark = p + 2 < len && s[p] == DPT_MARK0 && s[p + 1] == DPT_MARK1 && s[p + 2] == DPT_MARK2;
+                if (mark && seen_other) {
+                    v->marker_leading_only = 0;
+                    break;
+                }
+                if (!mark) seen_other = true;
+                p += mark ? 3 : 1;
+            }
+        }
+    }
+    rebuild_host_view();
+    // the word "<s>" (tokenizer_utils.py:26-30: '<s>' is a word of its own), solved with the same DP
+    {
+        const uint8_t bos[3] = {'<', 's', '>'};
+        uint64_t best[4];
+        uint16_t A[4], B[4];
+        dpt_forward<true>(h_view, bos, 3, nullptr, best, A, B);
+        bos_len = (int32_t)dpt_key_len(best[3]);
+        bos_ntok = 0;
+        bos_ids[0] = bos_ids[1] = bos_ids[2] = 0;
+        if (dpt_key_reach(best[3]) && dpt_backward_emit(h_view, bos, 3, best, A, B, bos_ids, 3)) bos_ntok = bos_len;
+    }
+    rebuild_host_view();
 }
 
 int dpt_vocab_build(const uint8_t* bytes, const int64_t* offs, const int32_t* ids, int32_t n_in,
@@ -228,43 +295,6 @@ int dpt_vocab_build(const uint8_t* bytes, const int64_t* offs, const int32_t* id
         v->da[nd.slot] = e;
     }
 
-    // ---- derived facts
-    {
-        uint32_t e = DPT_DA_ROOT_ENTRY;
-        bool ok = dpt_da_step(v->da.data(), e, DPT_MARK0) && dpt_da_step(v->da.data(), e, DPT_MARK1) &&
-                  dpt_da_step(v->da.data(), e, DPT_MARK2);
-        v->marker_entry = ok ? e : 0u;
-        for (uint32_t c = 0; c < 128; ++c) {
-            uint32_t e1 = DPT_DA_ROOT_ENTRY;
-            if (dpt_da_step(v->da.data(), e1, c) && (e1 & DPT_DA_TERMINAL)) v->ascii_single[c >> 5] |= 1u << (c & 31);
-        }
-        v->byte_fallback = 1;
-        for (int b = 0; b < 256; ++b) {
-            char lit[8];
-            snprintf(lit, sizeof lit, "<0x%02X>", b);
-            uint32_t e2 = DPT_DA_ROOT_ENTRY, slot = 0;
-            bool hit = true;
-            for (int p = 0; p < 6 && hit; ++p) hit = dpt_da_step_idx(v->da.data(), e2, (uint8_t)lit[p], slot);
-            v->byte_token_id[b] = (hit && (e2 & DPT_DA_TERMINAL)) ? v->slot_id[slot] : -1;
-            if (v->byte_token_id[b] < 0) v->byte_fallback = 0;
-        }
-        v->marker_leading_only = 1;
-        for (int32_t r = 0; r < v->n_tokens && v->marker_leading_only; ++r) {
-            const uint8_t* s = v->tok_bytes.data() + v->tok_offs[r];
-            const int32_t len = (int32_t)(v->tok_offs[r + 1] - v->tok_offs[r]);
-            bool seen_other = false;
-            for (int32_t p = 0; p < len;) {
-                const bool mark = p + 2 < len && s[p] == DPT_MARK0 && s[p + 1] == DPT_MARK1 && s[p + 2] == DPT_MARK2;
-                if (mark && seen_other) {
-                    v->marker_leading_only = 0;
-                    break;
-                }
-                if (!mark) seen_other = true;
-                p += mark ? 3 : 1;
-            }
-        }
-    }
-
     // ---- perfect hash (compress, hash, displace)
     const uint32_t n = (uint32_t)v->n_tokens;
     const uint32_t nb = next_pow2(std::max<uint32_t>(1, (n + 3) / 4));
@@ -325,6 +355,7 @@ int dpt_vocab_build(const uint8_t* bytes, const int64_t* offs, const int32_t* id
         return 1;
     }
     v->rebuild_host_view();
+    v->derive_facts();
     *out = v;
     return 0;
 }

@@ -15,6 +15,9 @@ struct dpt_vocab {
     uint32_t lmax = 0;
     uint32_t ph_salt = 0;
     uint32_t marker_entry = 0;
+    uint32_t marker_slot = 0;
+    int32_t bos_len = 0, bos_ntok = 0, bos_ids[3] = {0, 0, 0};
+    int32_t fast_ok = 0;
     uint32_t ascii_single[4] = {0, 0, 0, 0};
     int32_t marker_leading_only = 1;
     int32_t byte_fallback = 0;
@@ -37,6 +40,7 @@ struct dpt_vocab {
     DptVocabView h_view{};  // pointers into the host vectors
 
     void rebuild_host_view();
+    void derive_facts();  // marker/bos/fast_ok/byte tokens from the built arrays (also after deserialize)
 };
 
 int dpt_vocab_build(const uint8_t* bytes, const int64_t* offs, const int32_t* ids, int32_t n_tokens,

@@ -101,8 +101,14 @@ class Engine:
 
     # ---- corpus path: raw documents -> ids ------------------------------------------------------
     def encode_corpus(self, text: torch.Tensor, doc_offs: torch.Tensor, rule: int,
-                      ids_cap: Optional[int] = None, word_cap: Optional[int] = None) -> EncodeResult:
-        """``text`` uint8 device tensor of concatenated non-empty documents; ``doc_offs`` int64[n_docs+1]."""
+                      ids_cap: Optional[int] = None, word_cap: Optional[int] = None,
+                      force_general: bool = False) -> EncodeResult:
+        """``text`` uint8 device tensor of concatenated non-empty documents; ``doc_offs`` int64[n_docs+1]
+        (``doc_offs[0] == 0``, ``doc_offs[-1] == len(text)``).
+
+        One launch of the fused tile kernel (``dpt_encode_corpus``).  If it reports a word too long for its
+        in-kernel arena the batch is rerun through the general multi-kernel CUDA path
+        (``dpt_encode_corpus_general``) - same outputs, any word length."""
         assert text.dtype == torch.uint8 and doc_offs.dtype == torch.int64 and text.is_cuda and doc_offs.is_cuda
         n_bytes = text.numel()
         n_docs = doc_offs.numel() - 1
@@ -111,6 +117,44 @@ class Engine:
             ids_cap = n_bytes // 2 + 2 * n_docs + 64
         if word_cap is None:
             word_cap = n_bytes // 3 + 2 * n_docs + 64
+        if force_general:
+            return self._encode_corpus_general(text, doc_offs, rule, ids_cap, word_cap)
+        with torch.cuda.device(dev):
+            ws = self._workspace(lib.dpt_encode_corpus_workspace(rule, n_bytes))
+            for attempt in range(4):
+                ids = torch.empty(ids_cap, dtype=torch.int32, device=dev)
+                lens = torch.empty(word_cap, dtype=torch.int32, device=dev)
+                flags = torch.empty(word_cap, dtype=torch.uint8, device=dev)
+                doc_tok = torch.empty(n_docs + 1, dtype=torch.int64, device=dev)
+                doc_flags = torch.empty(n_docs, dtype=torch.uint8, device=dev)
+                counters = torch.empty(4, dtype=torch.int64, device=dev)
+                n_out = torch.empty(8, dtype=torch.int64, device=dev)
+                check(lib.dpt_encode_corpus(self.vocab.handle, rule, _ptr(text), n_bytes, _ptr(doc_offs), n_docs, _ptr(ids),
+                                            ids_cap, _ptr(lens), _ptr(flags), word_cap, _ptr(doc_tok), _ptr(doc_flags),
+                                            _ptr(counters), _ptr(n_out), _ptr(ws), ws.numel(), self._stream()))
+                h = n_out.cpu().tolist()  # synchronises the stream
+                if h[_cabi.NOUT_FALLBACK]:
+                    return self._encode_corpus_general(text, doc_offs, rule, max(ids_cap, h[_cabi.NOUT_IDS] + 64),
+                                                       max(word_cap, h[_cabi.NOUT_WORDS] + 64))
+                retry = False
+                if h[_cabi.NOUT_WORDS] > word_cap:
+                    word_cap = h[_cabi.NOUT_WORDS] + 64
+                    retry = True
+                if h[_cabi.NOUT_IDS] > ids_cap:
+                    ids_cap = h[_cabi.NOUT_IDS] + 64
+                    retry = True
+                if not retry:
+                    break
+            else:
+                raise _cabi.DptError(_cabi.ECAPACITY, f"capacity retries exhausted: {h}")
+        nw = h[_cabi.NOUT_WORDS]
+        return EncodeResult(ids[:h[0]], lens[:nw], flags[:nw], None, counters, h[0], nw, doc_tok, doc_flags)
+
+    def _encode_corpus_general(self, text, doc_offs, rule, ids_cap, word_cap) -> EncodeResult:
+        """General multi-kernel CUDA path (normalise -> DP count -> scan -> DP emit): any word length."""
+        n_bytes = text.numel()
+        n_docs = doc_offs.numel() - 1
+        dev = self.device
         worst = 0
         with torch.cuda.device(dev):
             for attempt in range(5):
@@ -121,11 +165,12 @@ class Engine:
                 doc_flags = torch.empty(n_docs, dtype=torch.uint8, device=dev)
                 counters = torch.empty(4, dtype=torch.int64, device=dev)
                 n_out = torch.zeros(8, dtype=torch.int64, device=dev)
-                ws_bytes = lib.dpt_encode_corpus_workspace(rule, n_bytes, n_docs, word_cap, worst)
+                ws_bytes = lib.dpt_encode_corpus_general_workspace(rule, n_bytes, n_docs, word_cap, worst)
                 ws = self._workspace(ws_bytes)
-                rc = lib.dpt_encode_corpus(self.vocab.handle, rule, _ptr(text), n_bytes, _ptr(doc_offs), n_docs, _ptr(ids),
-                                           ids_cap, _ptr(lens), _ptr(flags), word_cap, _ptr(doc_tok), _ptr(doc_flags),
-                                           _ptr(counters), _ptr(n_out), _ptr(ws), ws.numel(), worst, self._stream())
+                rc = lib.dpt_encode_corpus_general(self.vocab.handle, rule, _ptr(text), n_bytes, _ptr(doc_offs), n_docs,
+                                                   _ptr(ids), ids_cap, _ptr(lens), _ptr(flags), word_cap, _ptr(doc_tok),
+                                                   _ptr(doc_flags), _ptr(counters), _ptr(n_out), _ptr(ws), ws.numel(), worst,
+                                                   self._stream())
                 if rc not in (_cabi.OK, _cabi.ECAPACITY):
                     check(rc)
                 h = n_out.cpu().tolist()

@@ -47,7 +47,7 @@ def host_sim():
     srcs = [os.path.join(ROOT, "tests", "host_sim", "sim.cpp"), os.path.join(PKG, "csrc", "vocab.cpp")]
     deps = srcs + [os.path.join(PKG, "csrc", h) for h in os.listdir(os.path.join(PKG, "csrc")) if h.endswith(".h")]
     if not os.path.isfile(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(PKG, "csrc"),
+        subprocess.check_call(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", "-I", os.path.join(PKG, "csrc"),
                                "-o", out] + srcs)
     lib = C.CDLL(out)
     lib.sim_vocab_create.restype = C.c_void_p
@@ -59,4 +59,8 @@ def host_sim():
     lib.sim_spm_normalise.restype = C.c_int64
     lib.sim_spm_normalise.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.sim_encode_corpus_fused.restype = C.c_int32
+    lib.sim_encode_corpus_fused.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                            C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
     return lib

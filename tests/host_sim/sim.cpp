@@ -2,13 +2,59 @@
 // Lets the CPU test-suite exercise the exact per-word code the CUDA kernels run, against the oracle,
 // before any GPU time is spent.  Never linked into the product library; nothing under
 // dp-tokenization_b200/ loads it.
+#include <barrier>
 #include <cstring>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "dpt_dp_core.h"
 #include "dpt_rules.h"
+#include "dpt_tile.h"
 #include "vocab.h"
+
+// ---- std::thread emulation of one CUDA block for dpt_tile.h (the fused kernel's source, verbatim) ----------
+namespace {
+struct HostShared {
+    std::barrier<> bar;
+    std::vector<uint32_t> vals;
+    explicit HostShared(int n) : bar(n), vals(n) {}
+};
+struct HostBlk {
+    int tid_, nt_;
+    HostShared* sh;
+    int tid() const { return tid_; }
+    int nthreads() const { return nt_; }
+    void sync() const { sh->bar.arrive_and_wait(); }
+    void atomic_or(uint32_t* p, uint32_t v) const { __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+    void atomic_add(uint32_t* p, uint32_t v) const { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+    void atomic_add_u64(unsigned long long* p, unsigned long long v) const { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+    unsigned take_ticket(unsigned int* p) const { return __atomic_fetch_add(p, 1u, __ATOMIC_RELAXED); }
+    uint32_t exclusive_scan(uint32_t v, uint32_t*, uint32_t& total) const {
+        sh->vals[tid_] = v;
+        sync();
+        uint32_t ex = 0, tot = 0;
+        for (int k = 0; k < nt_; ++k) {
+            if (k < tid_) ex += sh->vals[k];
+            tot += sh->vals[k];
+        }
+        total = tot;
+        sync();
+        return ex;
+    }
+    // one emulated CTA processes the tiles in order, so the predecessor's inclusive prefix is always there
+    void lookback(const dpt::TileParams& P, dpt::TileSmem& S, int tile) const {
+        if (tid_ != 0) return;
+        const unsigned long long pw = tile ? (P.desc_w[tile - 1] & dpt::TL_DESC_MASK) : 0ull;
+        const unsigned long long pt = tile ? (P.desc_t[tile - 1] & dpt::TL_DESC_MASK) : 0ull;
+        P.desc_w[tile] = (2ull << 62) | (pw + (S.tile_tot >> 16));
+        P.desc_t[tile] = (2ull << 62) | (pt + (S.tile_tot & 0xFFFFu));
+        S.base_w = pw;
+        S.base_t = pt;
+    }
+};
+}  // namespace
 
 extern "C" {
 
@@ -86,5 +132,61 @@ int64_t sim_spm_normalise(void* vv, const uint8_t* text, int64_t n, const int64_
     if (ow < word_cap + 1) word_offs[ow] = ob;
     *n_words_out = ow;
     return ob;
+}
+
+// The fused corpus kernel's code (dpt_tile.h) on `nthreads` host threads emulating ONE CTA.  kc overrides the
+// number of trie slots "staged in shared memory" (0 = default) to exercise the global-memory lookup path.
+int32_t sim_encode_corpus_fused(void* vv, int32_t spm, const uint8_t* text, int64_t n_bytes, const int64_t* doc_offs,
+                                int64_t n_docs, int32_t* ids, int64_t ids_cap, int32_t* word_lens, uint8_t* word_flags,
+                                int64_t word_cap, int64_t* doc_tok_offs, uint8_t* doc_flags, int64_t* counters,
+                                int64_t* n_out, int32_t nthreads, int32_t kc) {
+    using namespace dpt;
+    dpt_vocab* v = (dpt_vocab*)vv;
+    const int64_t n_tiles = (n_bytes + TL_T - 1) / TL_T;
+    std::vector<unsigned long long> dw(n_tiles + 1, 0), dt(n_tiles + 1, 0);
+    unsigned int ticket = 0;
+    std::vector<uint8_t> an(TL_ARENA_POS);
+    std::vector<uint64_t> ab(TL_ARENA_POS);
+    std::vector<uint16_t> aa(TL_ARENA_POS), abb(TL_ARENA_POS);
+    TileParams P{};
+    P.V = v->h_view;
+    P.text = text;
+    P.n_bytes = n_bytes;
+    P.doc_offs = doc_offs;
+    P.n_docs = n_docs;
+    P.ids = ids;
+    P.ids_cap = ids_cap;
+    P.word_lens = word_lens;
+    P.word_flags = word_flags;
+    P.word_cap = word_cap;
+    P.doc_tok_offs = doc_tok_offs;
+    P.doc_flags = doc_flags;
+    P.counters = (unsigned long long*)counters;
+    P.n_out = n_out;
+    P.desc_w = dw.data();
+    P.desc_t = dt.data();
+    P.ticket = &ticket;
+    P.arena_norm = an.data();
+    P.arena_best = ab.data();
+    P.arena_a = aa.data();
+    P.arena_b = abb.data();
+    P.n_tiles = (int32_t)n_tiles;
+    const int32_t kmax = (int32_t)(v->da.size() < (size_t)TL_KC ? v->da.size() : (size_t)TL_KC);
+    P.kc = kc > 0 && kc < kmax ? kc : kmax;
+    P.spm = spm;
+    P.rule = spm ? 1 : 0;
+    memset(counters, 0, 32);
+    memset(n_out, 0, 64);
+    if (doc_flags) memset(doc_flags, 0, (size_t)n_docs);
+    auto S = std::make_unique<TileSmem>();
+    HostShared sh(nthreads);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([&, t] {
+            HostBlk blk{t, nthreads, &sh};
+            tl_loop(blk, P, *S, 0);
+        });
+    for (auto& x : th) x.join();
+    return 0;
 }
 }

@@ -318,3 +318,49 @@ def test_full_size_properties_100mb(dev):
     for d in sample[:40]:
         doc = raw[doc_offs[d]:doc_offs[d + 1]].decode()
         assert dto[d + 1] - dto[d] <= len(tok.encode(doc))
+
+
+def test_fused_kernel_equals_general_path(dev):
+    """The single-launch fused tile kernel and the general multi-kernel path give identical outputs on edge-case
+    input (tiny documents, double spaces, raw U+2581, OOV characters, malformed UTF-8 cut by document boundaries),
+    and a word too long for the fused kernel's arena is rerouted through the general path, not mis-solved."""
+    from dptok import _cabi
+    from dptok.engine import pack_documents
+    tok, t2i, eng = _llama_engine("llama2_2k", dev)
+    rng = random.Random(5)
+    pieces = ["plai", "gout", "é", "ï", "日", "本", "\n", "\t", ",", "Zeta", "(x)", "12", "—", "naïve", "%", "trot", "▁", "a", "I"]
+    for trial in range(6):
+        docs = []
+        for k in range(rng.choice([1, 50, 400, 5000])):
+            style = rng.random()
+            if style < 0.1:
+                d = rng.choice(["a", " ", "▁", "é", "\n", "日", "x y", " x", "x ", "  ", "a  b", "▁▁a", "a▁b", "a ▁b", "▁ a"])
+            elif style < 0.2:
+                d = "".join(rng.choice("abcdefgh ") for _ in range(rng.randint(1, 30)))
+            elif style < 0.25:
+                d = "".join(rng.choice(pieces) for _ in range(rng.randint(100, 700)))
+            else:
+                ws = ["".join(rng.choice(pieces) for _ in range(rng.randint(1, 4))) for _ in range(rng.randint(1, 12))]
+                d = rng.choice([" ", " ", " ", "  ", "▁"]).join(ws)
+            docs.append(d.encode())
+        if trial % 3 == 0:
+            blob = bytes(rng.choice([0x20, 0x41, 0x62, 0xE2, 0x96, 0x81, 0xC3, 0xA9, 0x80, 0xFF, 0x0A, 0x63])
+                         for _ in range(rng.randint(5000, 200000)))
+            cuts = sorted(set(rng.randint(1, len(blob) - 1) for _ in range(rng.randint(0, 400))))
+            docs = [blob[a:b] for a, b in zip([0] + cuts, cuts + [len(blob)])]
+        text, offs = pack_documents(docs)
+        d_text, d_offs = _to_dev(text, dev), _to_dev(offs, dev)
+        a = eng.encode_corpus(d_text, d_offs, _cabi.RULE_SPM_LLAMA)
+        b = eng.encode_corpus(d_text, d_offs, _cabi.RULE_SPM_LLAMA, force_general=True)
+        assert a.n_ids == b.n_ids and a.n_words == b.n_words
+        assert torch.equal(a.ids, b.ids) and torch.equal(a.word_lens, b.word_lens)
+        assert torch.equal(a.word_flags & 1, b.word_flags & 1)
+        assert torch.equal(a.doc_tok_offs, b.doc_tok_offs) and torch.equal(a.doc_flags, b.doc_flags)
+        assert a.counters.tolist() == b.counters.tolist()
+    docs = [b"x" * 3000 + b" y " + b"z" * 9000 + b" end", b"short doc"]
+    text, offs = pack_documents(docs)
+    d_text, d_offs = _to_dev(text, dev), _to_dev(offs, dev)
+    a = eng.encode_corpus(d_text, d_offs, _cabi.RULE_SPM_LLAMA)
+    b = eng.encode_corpus(d_text, d_offs, _cabi.RULE_SPM_LLAMA, force_general=True)
+    assert torch.equal(a.ids, b.ids) and torch.equal(a.word_lens, b.word_lens) and a.n_words == 8
+    assert bool(eng.roundtrip_ok(a, d_text, d_offs, skip_bos=True).all())

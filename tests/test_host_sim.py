@@ -8,7 +8,7 @@ import random
 import numpy as np
 
 from conftest import load_golden
-from helpers import make_sim_vocab, sim_word, vocab_bytes
+from helpers import make_sim_vocab, pack, sim_word, vocab_bytes
 from oracle import adapters, dp_oracle
 
 
@@ -131,3 +131,177 @@ def test_spm_rule_matches_reference_pretokenizer(host_sim):
         expect += adapters.llama_words(tok, d)
     assert words == expect
     host_sim.sim_vocab_destroy(ctypes.c_void_p(h))
+
+
+# ------------------------------------------------------------------------------------------------
+# The fused tile kernel's source (csrc/dpt_tile.h) executed verbatim by a std::thread emulation of one CUDA
+# block, against (a) the general path's rule + the C oracle and (b) the reference-shaped normaliser.
+# ------------------------------------------------------------------------------------------------
+def _run_fused(host_sim, h, spm, docs, nthreads=4, kc=0, ids_cap=None):
+    raw = b"".join(docs)
+    text = np.frombuffer(raw + b"\0" * 64, np.uint8).copy()
+    offs = np.zeros(len(docs) + 1, np.int64)
+    offs[1:] = np.cumsum([len(d) for d in docs])
+    n = len(raw)
+    cap = 3 * n + 3 * len(docs) + 16 if ids_cap is None else ids_cap
+    wcap = n + 2 * len(docs) + 16
+    ids = np.full(cap, -7, np.int32)
+    wl = np.full(wcap, -7, np.int32)
+    wf = np.full(wcap, 99, np.uint8)
+    dto = np.full(len(docs) + 1, -7, np.int64)
+    dfl = np.zeros(len(docs), np.uint8)
+    ctr = np.zeros(4, np.int64)
+    nout = np.zeros(8, np.int64)
+    host_sim.sim_encode_corpus_fused(h, spm, text.ctypes.data, n, offs.ctypes.data, len(docs), ids.ctypes.data, cap,
+                                     wl.ctypes.data, wf.ctypes.data, wcap, dto.ctypes.data, dfl.ctypes.data,
+                                     ctr.ctypes.data, nout.ctypes.data, nthreads, kc)
+    return dict(ids=ids[:min(nout[0], cap)], wl=wl[:nout[1]], wf=wf[:nout[1]], dto=dto, dfl=dfl, ctr=ctr, nout=nout)
+
+
+def _general_expected(host_sim, h, vb, docs):
+    """(n_words, ids, lens, untok, doc_tok_offs, doc_flags) of the general path's rule + the C oracle's DP."""
+    from oracle.c_oracle import COracle
+
+    def normalise(dlist):
+        raw = b"".join(dlist)
+        text = np.frombuffer(raw + b"\0", np.uint8)
+        offs = np.zeros(len(dlist) + 1, np.int64)
+        offs[1:] = np.cumsum([len(d) for d in dlist])
+        cap = 6 * len(raw) + 6 * len(dlist) + 16
+        out = np.zeros(cap, np.uint8)
+        wcap = len(raw) + 2 * len(dlist) + 2
+        woffs = np.zeros(wcap + 1, np.int64)
+        nw = ctypes.c_int64()
+        flags = np.zeros(len(dlist), np.uint8)
+        nb = host_sim.sim_spm_normalise(h, text.ctypes.data, len(raw), offs.ctypes.data, len(dlist), out.ctypes.data,
+                                        cap, woffs.ctypes.data, wcap, ctypes.byref(nw), flags.ctypes.data)
+        return out[:nb].copy(), woffs[:nw.value + 1].copy(), flags
+
+    wtext, woffs, flags = normalise(docs)
+    nw = len(woffs) - 1
+    o_ids, o_lens, o_untok = COracle(vb, 1).encode_words(wtext, woffs)
+    tok_of_word = np.concatenate([[0], np.cumsum(np.where(o_untok == 0, o_lens, 0))])
+    first = np.concatenate([[0], np.cumsum([len(normalise([d])[1]) - 1 for d in docs])])
+    assert first[-1] == nw
+    return nw, o_ids, o_lens, o_untok, tok_of_word[first], flags
+
+
+def _check_fused(host_sim, h, vb, docs, **kw):
+    r = _run_fused(host_sim, h, 1, docs, **kw)
+    nw, o_ids, o_lens, o_untok, o_dto, o_flags = _general_expected(host_sim, h, vb, docs)
+    assert r["nout"][6] == 0
+    assert r["nout"][1] == nw and r["nout"][0] == len(o_ids)
+    assert np.array_equal(r["wl"], o_lens)
+    assert np.array_equal(r["wf"] & 1, o_untok)
+    assert np.array_equal(r["ids"], o_ids)
+    assert np.array_equal(r["dto"], o_dto)
+    assert np.array_equal(r["dfl"], o_flags)
+    assert r["ctr"].tolist() == [sum(len(d) for d in docs), nw, len(o_ids), int(o_untok.sum())]
+    return r
+
+
+def test_fused_tile_code_s2orc_shaped_text(host_sim):
+    """Llama-2-shaped 32k vocab on S2ORC-shaped text with newline headers: ids, per-word lengths, flags, document
+    offsets and counters bit-exact with the oracle; thread count and shared-memory trie size must not matter."""
+    from dptok import assets, synth
+    tok = assets.load_hf("llama2_32k")
+    t2i = tok.get_vocab()
+    vb = vocab_bytes(t2i, "spm")
+    h = make_sim_vocab(host_sim, vb, 1)
+    text, doc_offs = synth.gen_documents(600_000, seed=3, lexicon=synth.make_lexicon(20000, seed=3), newline_headers=True)
+    raw = text.tobytes()
+    docs = [raw[doc_offs[k]:doc_offs[k + 1]] for k in range(len(doc_offs) - 1)]
+    r = _check_fused(host_sim, h, vb, docs, nthreads=8)
+    assert 0 < ((r["wf"] & 4) != 0).sum() < len(r["wf"]) // 20      # newline words took the general code, the rest did not
+    assert not r["dfl"].any()
+    # the reference-shaped normaliser gives the same words
+    words = []
+    for d in docs[:50]:
+        words += adapters.spm_normalise(d.decode(), set(t2i))
+    n50 = len(words)
+    from oracle.c_oracle import COracle
+    wtext, woffs = pack([w.encode() for w in words])
+    o_ids, o_lens, _ = COracle(vb, 1).encode_words(wtext, woffs)
+    assert np.array_equal(r["wl"][:n50], o_lens) and np.array_equal(r["ids"][:len(o_ids)], o_ids)
+    r2 = _run_fused(host_sim, h, 1, docs, nthreads=3, kc=500)
+    assert np.array_equal(r2["ids"], r["ids"]) and np.array_equal(r2["wl"], r["wl"])
+    # capacity: ids beyond ids_cap are dropped, the requirement is still reported
+    r3 = _run_fused(host_sim, h, 1, docs, nthreads=4, ids_cap=1000)
+    assert r3["nout"][0] == len(r["ids"]) and np.array_equal(r3["ids"], r["ids"][:1000])
+    host_sim.sim_vocab_destroy(ctypes.c_void_p(h))
+
+
+def test_fused_tile_code_edge_cases(host_sim):
+    """Tiny documents, trailing/leading/double spaces, raw U+2581, OOV characters, newlines, words longer than a
+    tile's look-ahead, malformed UTF-8 cut by document boundaries: fused tile code == general path + oracle."""
+    from dptok import assets
+    tok = assets.load_hf("llama2_2k")
+    t2i = tok.get_vocab()
+    vb = vocab_bytes(t2i, "spm")
+    h = make_sim_vocab(host_sim, vb, 1)
+    rng = random.Random(5)
+    pieces = ["plai", "gout", "é", "ï", "日", "本", "\n", "\t", ",", "Zeta", "(x)", "12", "—", "naïve", "%", "trot", "▁", "a", "I"]
+    for trial in range(16):
+        docs = []
+        for k in range(rng.choice([1, 3, 50, 400, 2000])):
+            style = rng.random()
+            if style < 0.1:
+                d = rng.choice(["a", " ", "▁", "é", "\n", "日", "x y", " x", "x ", "  ", "a  b", "▁▁a", "a▁b", "a ▁b", "▁ a"])
+            elif style < 0.2:
+                d = "".join(rng.choice("abcdefgh ") for _ in range(rng.randint(1, 30)))
+            elif style < 0.25:
+                d = "".join(rng.choice(pieces) for _ in range(rng.randint(100, 700)))
+            else:
+                ws = ["".join(rng.choice(pieces) for _ in range(rng.randint(1, 4))) for _ in range(rng.randint(1, 12))]
+                d = rng.choice([" ", " ", " ", "  ", "▁"]).join(ws)
+            docs.append(d.encode())
+        if trial % 4 == 0:
+            blob = bytes(rng.choice([0x20, 0x41, 0x62, 0xE2, 0x96, 0x81, 0xC3, 0xA9, 0x80, 0xFF, 0x0A, 0x63])
+                         for _ in range(rng.randint(50, 20000)))
+            cuts = sorted(set(rng.randint(1, len(blob) - 1) for _ in range(rng.randint(0, 40))))
+            docs = [blob[a:b] for a, b in zip([0] + cuts, cuts + [len(blob)])]
+        _check_fused(host_sim, h, vb, docs, nthreads=rng.choice([1, 2, 5, 8]), kc=rng.choice([0, 0, 100, 1000]))
+    # a word that runs further past its tile than the in-kernel arena allows is reported, not mis-solved
+    r = _run_fused(host_sim, h, 1, [b"x" * 3000 + b" y " + b"z" * 9000 + b" end"], nthreads=4)
+    assert r["nout"][6] >= 1
+    host_sim.sim_vocab_destroy(ctypes.c_void_p(h))
+
+
+def test_fused_tile_code_untokenizable_and_long_tokens(host_sim):
+    """Vocabulary without U+2581 alone / with missing letters / with tokens longer than the 32-bit walk mask:
+    phantom lengths, untokenizable flags and long tokens come out like the oracle's."""
+    rng = random.Random(11)
+    alpha = "abcdeé日"
+    for with_marker in (True, False):
+        toks = set(alpha[:5]) | {"▁a", "▁b", "▁é", "▁ab"}
+        if with_marker:
+            toks.add("▁")
+        for _ in range(300):
+            toks.add("".join(rng.choice(alpha) for _ in range(rng.randint(2, 7))))
+        toks.add("ab" * 30)
+        toks.add("▁" + "cd" * 25)
+        toks.add("é" * 40)
+        toks |= {"<s>", "<unk>"} | {"<0x%02X>" % b for b in range(256)}
+        toks |= set("<0x>") | set("0123456789ABCDEF")
+        t2i = {t: k + 3 for k, t in enumerate(sorted(toks))}
+        vb = vocab_bytes(t2i, "spm")
+        h = make_sim_vocab(host_sim, vb, 1)
+        docs = []
+        for k in range(300):
+            ws = []
+            for _ in range(rng.randint(1, 30)):
+                n = rng.choice([1, 1, 2, 3, 5, 8, 13, 21, 40])
+                w = "".join(rng.choice(alpha) for _ in range(n))
+                if rng.random() < 0.05:
+                    w = "ab" * rng.randint(20, 70)
+                if rng.random() < 0.05:
+                    w = "cd" * rng.randint(20, 40)
+                if rng.random() < 0.05:
+                    w = "é" * rng.randint(30, 90)
+                ws.append(w)
+            docs.append(" ".join(ws).encode())
+        r = _check_fused(host_sim, h, vb, docs, nthreads=4)
+        if not with_marker:         # no bare marker: words like "▁c…" have no segmentation at all
+            assert r["ctr"][3] > 0
+        assert ((r["wf"] & 4) != 0).sum() > 0
+        host_sim.sim_vocab_destroy(ctypes.c_void_p(h))
