@@ -379,24 +379,24 @@ int dpt_encode_corpus_general(const dpt_vocab* v, int32_t rule, const uint8_t* d
     return DPT_OK;
 }
 
-// ---- fused single-launch corpus entry (fused.cu): asynchronous, no host synchronisation ----------------
-int64_t dpt_encode_corpus_workspace(int32_t rule, int64_t n_bytes) {
+// ---- corpus pipeline entry (pipe.cu): asynchronous, no host synchronisation ---------------------------------
+int64_t dpt_encode_corpus_workspace(int32_t rule, int64_t n_bytes, int64_t n_docs, int64_t word_cap, int32_t worst_case) {
     (void)rule;
-    return dpt::encode_corpus_fused_workspace(n_bytes);
+    return dpt::encode_corpus_pipe_workspace(n_bytes, n_docs, word_cap, worst_case);
 }
 
 int dpt_encode_corpus(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, int64_t n_bytes, const int64_t* d_doc_offs,
                       int64_t n_docs, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens, uint8_t* d_word_flags,
                       int64_t word_cap, int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters,
-                      int64_t* d_n_out, void* d_workspace, int64_t workspace_bytes, void* stream) {
+                      int64_t* d_n_out, void* d_workspace, int64_t workspace_bytes, int32_t worst_case, void* stream) {
     if (int rc = check_ready(v, "dpt_encode_corpus")) return rc;
     if (rule != DPT_RULE_SPM_LLAMA)
         return fail(DPT_EINVAL, "dpt_encode_corpus: rule not available on device in this build; pre-split on the host "
                                 "and call dpt_encode_words");
     std::string err;
-    const int rc = dpt::encode_corpus_fused(v, rule, d_text, n_bytes, d_doc_offs, n_docs, d_ids, ids_cap, d_word_lens,
-                                            d_word_flags, word_cap, d_doc_tok_offs, d_doc_flags, d_counters, d_n_out,
-                                            d_workspace, workspace_bytes, (cudaStream_t)stream, err);
+    const int rc = dpt::encode_corpus_pipe(v, rule, d_text, n_bytes, d_doc_offs, n_docs, d_ids, ids_cap, d_word_lens,
+                                           d_word_flags, word_cap, d_doc_tok_offs, d_doc_flags, d_counters, d_n_out,
+                                           d_workspace, workspace_bytes, worst_case, (cudaStream_t)stream, err);
     return rc ? fail(rc, err) : DPT_OK;
 }
 

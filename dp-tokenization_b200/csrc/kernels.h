@@ -23,12 +23,12 @@ struct ProfScope {
     ~ProfScope();
 };
 
-// fused single-launch corpus path (fused.cu / dpt_tile.h)
-int64_t encode_corpus_fused_workspace(int64_t n_bytes);
-int encode_corpus_fused(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, int64_t n_bytes, const int64_t* d_doc_offs,
-                        int64_t n_docs, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens, uint8_t* d_word_flags,
-                        int64_t word_cap, int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters,
-                        int64_t* d_n_out, void* d_ws, int64_t ws_bytes, cudaStream_t st, std::string& err);
+// corpus pipeline (pipe.cu / dpt_pipe.h): scan+dedup -> DP per distinct word -> scan+emit; asynchronous
+int64_t encode_corpus_pipe_workspace(int64_t n_bytes, int64_t n_docs, int64_t word_cap, int32_t worst);
+int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, int64_t n_bytes, const int64_t* d_doc_offs,
+                       int64_t n_docs, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens, uint8_t* d_word_flags,
+                       int64_t word_cap, int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters,
+                       int64_t* d_n_out, void* d_ws, int64_t ws_bytes, int32_t worst, cudaStream_t st, std::string& err);
 
 int64_t encode_words_workspace_fixed(int64_t n_words);
 int64_t pretokenize_workspace(int64_t n_bytes, int64_t n_docs);

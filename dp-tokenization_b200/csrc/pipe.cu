@@ -1,0 +1,285 @@
+// CUDA kernels (sm_100a) of the corpus pipeline in dpt_pipe.h:  A scan+dedup -> B DP per distinct word ->
+// C scan+emit -> D counters.  Five launches per corpus, no host synchronisation in between.
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "../../include/dptok.h"
+#include "dpt_pipe.h"
+#include "kernels.h"
+#include "vocab.h"
+
+namespace dpt {
+
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+struct DevBlk {
+    __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
+    __device__ __forceinline__ int nthreads() const { return (int)blockDim.x; }
+    __device__ __forceinline__ bool persistent() const { return false; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t v) const { atomicOr(p, v); }
+    __device__ __forceinline__ void atomic_add(uint32_t* p, uint32_t v) const { atomicAdd(p, v); }
+    __device__ __forceinline__ uint32_t atomic_add_ret(uint32_t* p, uint32_t v) const { return atomicAdd(p, v); }
+    __device__ __forceinline__ unsigned long long atomic_add_u64_ret(unsigned long long* p, unsigned long long v) const {
+        return atomicAdd(p, v);
+    }
+    __device__ __forceinline__ unsigned long long load_relaxed(const unsigned long long* p) const { return ld_relaxed_gpu(p); }
+    __device__ __forceinline__ unsigned long long cas_u64(unsigned long long* p, unsigned long long expect,
+                                                          unsigned long long desired) const {
+        return atomicCAS(p, expect, desired);
+    }
+
+    // block-wide exclusive scan of one uint32 per thread; every thread must call.  sm: >= 34 words.
+    __device__ __forceinline__ uint32_t exclusive_scan(uint32_t v, uint32_t* sm, uint32_t& total) const {
+        const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (unsigned)d) inc += o;
+        }
+        if (lane == 31) sm[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = lane < nwarps ? sm[lane] : 0u;
+            uint32_t winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, winc, d);
+                if (lane >= (unsigned)d) winc += o;
+            }
+            sm[lane] = winc - w;
+            if (lane == 31) sm[32] = winc;
+        }
+        __syncthreads();
+        const uint32_t base = sm[warp];
+        total = sm[32];
+        __syncthreads();
+        return base + inc - v;
+    }
+
+    // decoupled look-back by warp 0: publish this tile's aggregate, sum the predecessors' aggregates back to the
+    // nearest inclusive prefix, publish the inclusive prefix.  descriptor = status << 62 | value
+    // (1 = aggregate, 2 = inclusive).  *out = exclusive prefix of this tile (shared memory).
+    __device__ __forceinline__ void lookback(unsigned long long* desc, int tile, unsigned long long agg,
+                                             unsigned long long* out) const {
+        if (threadIdx.x >= 32) return;
+        const int lane = threadIdx.x;
+        unsigned long long excl = 0;
+        if (tile > 0) {
+            if (lane == 0) st_relaxed_gpu(&desc[tile], (1ull << 62) | agg);
+            int base = tile - 1;
+            for (;;) {
+                const int idx = base - lane;
+                unsigned long long v = 2ull << 62;  // in front of tile 0: inclusive prefix 0
+                if (idx >= 0) {
+                    do {
+                        v = ld_relaxed_gpu(&desc[idx]);
+                    } while ((v >> 62) == 0);
+                }
+                const unsigned incl = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+                const int first = incl ? __ffs((int)incl) - 1 : 31;
+                unsigned long long c = lane <= first ? (v & PD_MASK) : 0ull;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+                excl += c;
+                if (incl) break;
+                base -= 32;
+            }
+        }
+        if (lane == 0) {
+            st_relaxed_gpu(&desc[tile], (2ull << 62) | (excl + agg));
+            *out = excl;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(PA_THREADS) k_scan_dedup(const __grid_constant__ PipeParams P) {
+    __shared__ ASmem S;
+    DevBlk blk;
+    pa_kernel(blk, P, S);
+}
+
+__global__ void __launch_bounds__(PB_THREADS) k_dp_distinct(const __grid_constant__ PipeParams P) {
+    DevBlk blk;
+    pb_thread(blk, P, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+}
+
+__global__ void __launch_bounds__(PB_THREADS) k_dp_distinct_long(const __grid_constant__ PipeParams P) {
+    DevBlk blk;
+    pb_long_thread(blk, P, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+}
+
+__global__ void __launch_bounds__(PC_THREADS) k_emit(const __grid_constant__ PipeParams P) {
+    __shared__ CSmem S;
+    DevBlk blk;
+    pc_kernel(blk, P, S);
+}
+
+__global__ void k_pipe_finish(const __grid_constant__ PipeParams P) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) pd_finish(P);
+}
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+struct PipeSizes {
+    int64_t n_tiles, n_ctiles, n_slots, odd_cap, pool_cap, lp_cap;
+};
+
+static PipeSizes pipe_sizes(int64_t n_bytes, int64_t word_cap, int worst) {
+    PipeSizes z;
+    z.n_tiles = (n_bytes + PA_T - 1) / PA_T;
+    z.n_ctiles = (word_cap + PC_TILE - 1) / PC_TILE;
+    int64_t want = worst ? word_cap : n_bytes / 48;
+    if (want < 4096) want = 4096;
+    int64_t s = 4096;
+    while (s < want) s <<= 1;
+    z.n_slots = s;
+    z.odd_cap = worst ? word_cap + 16 : n_bytes / 64 + 4096;
+    z.pool_cap = worst ? 6 * n_bytes + 3 * word_cap + 64 : n_bytes / 4 + 65536;
+    z.lp_cap = worst ? 6 * n_bytes + 8 * word_cap + 64 : n_bytes / 4 + 262144;
+    return z;
+}
+
+int64_t encode_corpus_pipe_workspace(int64_t n_bytes, int64_t n_docs, int64_t word_cap, int32_t worst) {
+    const PipeSizes z = pipe_sizes(n_bytes, word_cap, worst);
+    int64_t b = 0;
+    b += align_up(sizeof(PipeCtl), 256);
+    b += align_up(z.n_tiles * 8 + 8, 256) + align_up(z.n_ctiles * 8 + 8, 256);
+    b += align_up(z.n_slots * 8, 256);                       // tags
+    b += align_up(z.n_slots * 16, 256);                      // res
+    b += align_up(z.n_slots * 4, 256);                       // pending
+    b += align_up(word_cap * 4 + 64, 256);                   // refs
+    b += align_up((n_docs + 1) * 8, 256);                    // doc_first_word
+    b += align_up(z.odd_cap * 16, 256) * 2;                  // odd, odd_res
+    b += align_up(z.pool_cap * 4, 256);                      // pool
+    b += align_up((z.n_slots + z.odd_cap) * 4, 256);         // longq
+    b += align_up(z.lp_cap, 256) + align_up(z.lp_cap * 8, 256) + 2 * align_up(z.lp_cap * 2, 256);
+    return b + 4096;
+}
+
+int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, int64_t n_bytes, const int64_t* d_doc_offs,
+                       int64_t n_docs, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens, uint8_t* d_word_flags,
+                       int64_t word_cap, int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters,
+                       int64_t* d_n_out, void* d_ws, int64_t ws_bytes, int32_t worst, cudaStream_t st, std::string& err) {
+    if (n_bytes <= 0 || n_docs <= 0 || word_cap <= 0 || !d_text || !d_doc_offs || !d_doc_tok_offs || !d_counters ||
+        !d_n_out || !d_ids || !d_word_lens || !d_word_flags) {
+        err = "encode_corpus: bad argument";
+        return DPT_EINVAL;
+    }
+    if (rule == DPT_RULE_SPM_LLAMA && (!v->byte_fallback || !v->marker_entry || v->unit_mode != DPT_UNIT_CODEPOINTS)) {
+        err = "encode_corpus(SPM_LLAMA): vocabulary lacks U+2581 or the 256 <0xHH> byte tokens, or is not a code-point "
+              "vocabulary; pre-split on the host";
+        return DPT_EINVAL;
+    }
+    if (n_bytes >= (1ll << 37) || word_cap >= (1ll << 31)) {
+        err = "encode_corpus: batch too large (>= 128 GiB or >= 2^31 words); split it";
+        return DPT_EINVAL;
+    }
+    if (!d_ws || ws_bytes < encode_corpus_pipe_workspace(n_bytes, n_docs, word_cap, worst)) {
+        err = "encode_corpus: workspace too small (see dpt_encode_corpus_workspace)";
+        return DPT_ECAPACITY;
+    }
+    const PipeSizes z = pipe_sizes(n_bytes, word_cap, worst);
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (sm_count <= 0) sm_count = 148;
+    }
+    char* base = (char*)d_ws;
+    int64_t used = 0;
+    auto take = [&](int64_t bytes) {
+        used = align_up(used, 256);
+        char* p = base + used;
+        used += bytes;
+        return p;
+    };
+    PipeParams P{};
+    P.V = v->d_view;
+    P.text = d_text;
+    P.n_bytes = n_bytes;
+    P.doc_offs = d_doc_offs;
+    P.n_docs = n_docs;
+    P.ids = d_ids;
+    P.ids_cap = ids_cap;
+    P.word_lens = d_word_lens;
+    P.word_flags = d_word_flags;
+    P.word_cap = word_cap;
+    P.doc_tok_offs = d_doc_tok_offs;
+    P.doc_flags = d_doc_flags;
+    P.counters = (unsigned long long*)d_counters;
+    P.n_out = d_n_out;
+    // everything that must start zeroed is contiguous: one memset
+    char* zero0 = take(0);
+    P.ctl = (PipeCtl*)take(sizeof(PipeCtl));
+    P.desc_w = (unsigned long long*)take(z.n_tiles * 8 + 8);
+    P.desc_t = (unsigned long long*)take(z.n_ctiles * 8 + 8);
+    P.tags = (unsigned long long*)take(z.n_slots * 8);
+    const int64_t zero_bytes = (base + used) - zero0;
+    P.res = (uint4*)take(z.n_slots * 16);
+    P.pending = (uint32_t*)take(z.n_slots * 4);
+    P.refs = (uint32_t*)take(word_cap * 4 + 64);
+    P.doc_first_word = (int64_t*)take((n_docs + 1) * 8);
+    P.odd = (OddWord*)take(z.odd_cap * 16);
+    P.odd_res = (uint4*)take(z.odd_cap * 16);
+    P.pool = (int32_t*)take(z.pool_cap * 4);
+    P.longq = (uint32_t*)take((z.n_slots + z.odd_cap) * 4);
+    P.lp_norm = (uint8_t*)take(z.lp_cap);
+    P.lp_best = (uint64_t*)take(z.lp_cap * 8);
+    P.lp_a = (uint16_t*)take(z.lp_cap * 2);
+    P.lp_b = (uint16_t*)take(z.lp_cap * 2);
+    P.odd_cap = z.odd_cap;
+    P.pool_cap = z.pool_cap;
+    P.lp_cap = z.lp_cap;
+    P.slot_mask = (uint32_t)(z.n_slots - 1);
+    P.n_tiles = (int32_t)z.n_tiles;
+    P.n_ctiles = (int32_t)z.n_ctiles;
+    P.spm = rule == DPT_RULE_SPM_LLAMA ? 1 : 0;
+    P.rule = rule;
+
+    cudaMemsetAsync(zero0, 0, (size_t)zero_bytes, st);
+    if (d_doc_flags) cudaMemsetAsync(d_doc_flags, 0, (size_t)n_docs, st);
+    {
+        ProfScope prof("k_scan_dedup", st);
+        k_scan_dedup<<<(unsigned)z.n_tiles, PA_THREADS, 0, st>>>(P);
+        ++g_launches;
+    }
+    {
+        ProfScope prof("k_dp_distinct", st);
+        k_dp_distinct<<<(unsigned)(sm_count * 16), PB_THREADS, 0, st>>>(P);
+        ++g_launches;
+    }
+    {
+        ProfScope prof("k_dp_distinct_long", st);
+        k_dp_distinct_long<<<(unsigned)(sm_count * 2), PB_THREADS, 0, st>>>(P);
+        ++g_launches;
+    }
+    {
+        ProfScope prof("k_emit", st);
+        k_emit<<<(unsigned)z.n_ctiles, PC_THREADS, 0, st>>>(P);
+        ++g_launches;
+    }
+    {
+        ProfScope prof("k_pipe_finish", st);
+        k_pipe_finish<<<1, 32, 0, st>>>(P);
+        ++g_launches;
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        err = std::string("encode_corpus: ") + cudaGetErrorString(e);
+        return DPT_ECUDA;
+    }
+    return DPT_OK;
+}
+
+}  // namespace dpt

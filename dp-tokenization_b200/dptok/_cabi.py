@@ -18,7 +18,7 @@ RULE_PRESPLIT, RULE_SPM_LLAMA, RULE_GPT2, RULE_LLAMA3, RULE_BLOOM = range(5)
 WF_UNTOKENIZABLE, WF_DOC_FIRST, WF_LONG = 1, 2, 4
 DF_AMBIGUOUS = 1
 CTR_BYTES, CTR_WORDS, CTR_TOKENS, CTR_UNTOKENIZABLE = range(4)
-NOUT_IDS, NOUT_WORDS, NOUT_POOL_REQ, NOUT_POOL_CAP, NOUT_NORM_REQ, NOUT_NORM_CAP, NOUT_FALLBACK = range(7)
+NOUT_IDS, NOUT_WORDS, NOUT_POOL_REQ, NOUT_POOL_CAP, NOUT_NORM_REQ, NOUT_NORM_CAP, NOUT_ODD_REQ, NOUT_ODD_CAP = range(8)
 
 
 class DptError(RuntimeError):
@@ -55,11 +55,12 @@ SIGNATURES = {
     "dpt_vocab_upload": (C.c_int, [_p, C.c_int]),
     "dpt_pretokenize_workspace": (_i64, [_i64, _i64]),
     "dpt_encode_words_workspace": (_i64, [_i64, _i64, _i32]),
-    "dpt_encode_corpus_workspace": (_i64, [_i32, _i64]),
+    "dpt_encode_corpus_workspace": (_i64, [_i32, _i64, _i64, _i64, _i32]),
     "dpt_encode_corpus_general_workspace": (_i64, [_i32, _i64, _i64, _i64, _i32]),
     "dpt_pretokenize": (C.c_int, [_p, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _i64, _p]),
     "dpt_encode_words": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _p]),
-    "dpt_encode_corpus": (C.c_int, [_p, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _p]),
+    "dpt_encode_corpus": (C.c_int, [_p, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _p, _i64,
+                                    _i32, _p]),
     "dpt_encode_corpus_general": (C.c_int, [_p, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _p,
                                             _i64, _i32, _p]),
     "dpt_lattice_word": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _i32, _p, _p, _p]),

@@ -106,9 +106,10 @@ class Engine:
         """``text`` uint8 device tensor of concatenated non-empty documents; ``doc_offs`` int64[n_docs+1]
         (``doc_offs[0] == 0``, ``doc_offs[-1] == len(text)``).
 
-        One launch of the fused tile kernel (``dpt_encode_corpus``).  If it reports a word too long for its
-        in-kernel arena the batch is rerun through the general multi-kernel CUDA path
-        (``dpt_encode_corpus_general``) - same outputs, any word length."""
+        The corpus pipeline (``dpt_encode_corpus``): scan + dedup -> one DP per distinct word -> scan + emit,
+        enqueued without host synchronisation; this wrapper then reads the 64-byte status vector and retries with
+        larger buffers only if a capacity was exceeded.  ``force_general`` runs the non-deduplicating multi-kernel
+        path instead (``dpt_encode_corpus_general``; the cross-check)."""
         assert text.dtype == torch.uint8 and doc_offs.dtype == torch.int64 and text.is_cuda and doc_offs.is_cuda
         n_bytes = text.numel()
         n_docs = doc_offs.numel() - 1
@@ -119,9 +120,10 @@ class Engine:
             word_cap = n_bytes // 3 + 2 * n_docs + 64
         if force_general:
             return self._encode_corpus_general(text, doc_offs, rule, ids_cap, word_cap)
+        worst = 0
         with torch.cuda.device(dev):
-            ws = self._workspace(lib.dpt_encode_corpus_workspace(rule, n_bytes))
-            for attempt in range(4):
+            for attempt in range(5):
+                ws = self._workspace(lib.dpt_encode_corpus_workspace(rule, n_bytes, n_docs, word_cap, worst))
                 ids = torch.empty(ids_cap, dtype=torch.int32, device=dev)
                 lens = torch.empty(word_cap, dtype=torch.int32, device=dev)
                 flags = torch.empty(word_cap, dtype=torch.uint8, device=dev)
@@ -131,16 +133,18 @@ class Engine:
                 n_out = torch.empty(8, dtype=torch.int64, device=dev)
                 check(lib.dpt_encode_corpus(self.vocab.handle, rule, _ptr(text), n_bytes, _ptr(doc_offs), n_docs, _ptr(ids),
                                             ids_cap, _ptr(lens), _ptr(flags), word_cap, _ptr(doc_tok), _ptr(doc_flags),
-                                            _ptr(counters), _ptr(n_out), _ptr(ws), ws.numel(), self._stream()))
+                                            _ptr(counters), _ptr(n_out), _ptr(ws), ws.numel(), worst, self._stream()))
                 h = n_out.cpu().tolist()  # synchronises the stream
-                if h[_cabi.NOUT_FALLBACK]:
-                    return self._encode_corpus_general(text, doc_offs, rule, max(ids_cap, h[_cabi.NOUT_IDS] + 64),
-                                                       max(word_cap, h[_cabi.NOUT_WORDS] + 64))
                 retry = False
                 if h[_cabi.NOUT_WORDS] > word_cap:
                     word_cap = h[_cabi.NOUT_WORDS] + 64
                     retry = True
-                if h[_cabi.NOUT_IDS] > ids_cap:
+                if h[2] > h[3] or h[4] > h[5] or h[6] > h[7]:
+                    if worst:
+                        raise _cabi.DptError(_cabi.ECAPACITY, f"worst-case workspace still too small: {h}")
+                    worst = 1
+                    retry = True
+                if h[_cabi.NOUT_IDS] > ids_cap and not retry:
                     ids_cap = h[_cabi.NOUT_IDS] + 64
                     retry = True
                 if not retry:

@@ -127,15 +127,15 @@ int dpt_vocab_upload(dpt_vocab* v, int device);
 #define DPT_NOUT_POOL_CAP 3
 #define DPT_NOUT_NORM_REQ 4
 #define DPT_NOUT_NORM_CAP 5
-#define DPT_NOUT_FALLBACK 6 /* dpt_encode_corpus: words too long for the fused kernel (> ~2 KB past their
-                               4 KB tile); when non-zero the outputs are incomplete and the caller reruns the
-                               batch through dpt_encode_corpus_general (same outputs, any word length)      */
+#define DPT_NOUT_ODD_REQ 6  /* dpt_encode_corpus: see there */
+#define DPT_NOUT_ODD_CAP 7
 
 /* ---- workspace sizing (bytes of caller-owned device scratch).  worst_case=0 sizes the
  *      variable parts for typical text; worst_case=1 can never overflow. */
 int64_t dpt_pretokenize_workspace(int64_t n_bytes, int64_t n_docs);
 int64_t dpt_encode_words_workspace(int64_t n_bytes, int64_t n_words, int32_t worst_case);
-int64_t dpt_encode_corpus_workspace(int32_t rule, int64_t n_bytes);
+int64_t dpt_encode_corpus_workspace(int32_t rule, int64_t n_bytes, int64_t n_docs, int64_t word_cap,
+                                    int32_t worst_case);
 int64_t dpt_encode_corpus_general_workspace(int32_t rule, int64_t n_bytes, int64_t n_docs, int64_t word_cap,
                                             int32_t worst_case);
 
@@ -178,16 +178,22 @@ int dpt_encode_words(const dpt_vocab* v,
                      int64_t* d_counters, int64_t* d_n_out,
                      void* d_workspace, int64_t workspace_bytes, void* stream);
 
-/* ---- corpus throughput path: pretokenize + DP + tie-break select + compaction over raw documents
- *      resident in HBM, ONE kernel launch, no host synchronisation (the per-document loops of
+/* ---- corpus throughput path: boundary rule + DP + tie-break select + compaction over raw documents
+ *      resident in HBM; five kernel launches (scan+dedup -> DP per DISTINCT word -> long words ->
+ *      scan+emit -> counters), no host synchronisation (the per-document loops of
  *      main_analyze_s2orc.py:269-298 and main_biomed_translation.py:71-82 around
  *      tokenizer_utils.py:66-80).  d_text: concatenated NON-EMPTY documents; d_doc_offs[n_docs+1] with
  *      d_doc_offs[0] == 0 and d_doc_offs[n_docs] == n_bytes.  Outputs as dpt_encode_words plus
  *      d_doc_tok_offs[n_docs+1] (token offset of each document in d_ids; for SPM_LLAMA each
  *      document's ids start with the id of '<s>' exactly as dp_tokenize_llama's output does) and
  *      d_doc_flags[n_docs].  d_word_lens / d_word_flags have capacity word_cap.  Writes beyond a
- *      capacity are dropped and the requirement is reported in d_n_out (DPT_NOUT_IDS / _WORDS);
- *      d_n_out[DPT_NOUT_FALLBACK] != 0 means: rerun through dpt_encode_corpus_general. */
+ *      capacity are dropped and the requirement is reported in d_n_out:
+ *        [0] ids required (ids_cap)            [1] words found (word_cap)
+ *        [2] long-word scratch required / [3] capacity      [4] id-pool required / [5] capacity
+ *        [6] not-deduplicated words required / [7] capacity
+ *      a requirement above its capacity means: retry with larger buffers ([0],[1]) or with
+ *      worst_case=1 workspace ([2..7]).  Nothing is cached between calls: the word table lives in
+ *      the workspace and is rebuilt by every call. */
 int dpt_encode_corpus(const dpt_vocab* v, int32_t rule,
                       const uint8_t* d_text, int64_t n_bytes,
                       const int64_t* d_doc_offs, int64_t n_docs,
@@ -195,11 +201,12 @@ int dpt_encode_corpus(const dpt_vocab* v, int32_t rule,
                       int32_t* d_word_lens, uint8_t* d_word_flags, int64_t word_cap,
                       int64_t* d_doc_tok_offs, uint8_t* d_doc_flags,
                       int64_t* d_counters, int64_t* d_n_out,
-                      void* d_workspace, int64_t workspace_bytes, void* stream);
+                      void* d_workspace, int64_t workspace_bytes, int32_t worst_case, void* stream);
 
-/* ---- the same contract through the general multi-kernel path (normalise -> count -> scan -> emit):
- *      any word length, synchronises the stream once.  The exact-by-construction backstop of the
- *      fused kernel; also what dpt_pretokenize + dpt_encode_words compose to. */
+/* ---- the same contract WITHOUT deduplication: normalise -> DP count per word -> scan -> DP emit per word
+ *      (what dpt_pretokenize + dpt_encode_words compose to); synchronises the stream once.  Kept as
+ *      the independent cross-check of the pipeline above (tests) and for callers who want the
+ *      normalised text.  Its d_n_out layout is the one documented at DPT_NOUT_*. */
 int dpt_encode_corpus_general(const dpt_vocab* v, int32_t rule,
                               const uint8_t* d_text, int64_t n_bytes,
                               const int64_t* d_doc_offs, int64_t n_docs,

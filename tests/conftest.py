@@ -59,8 +59,9 @@ def host_sim():
     lib.sim_spm_normalise.restype = C.c_int64
     lib.sim_spm_normalise.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
-    lib.sim_encode_corpus_fused.restype = C.c_int32
-    lib.sim_encode_corpus_fused.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
-                                            C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
-                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+    lib.sim_encode_corpus_pipe.restype = C.c_int32
+    lib.sim_encode_corpus_pipe.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                           C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64,
+                                           C.c_int64, C.c_int64]
     return lib

@@ -11,10 +11,10 @@
 
 #include "dpt_dp_core.h"
 #include "dpt_rules.h"
-#include "dpt_tile.h"
+#include "dpt_pipe.h"
 #include "vocab.h"
 
-// ---- std::thread emulation of one CUDA block for dpt_tile.h (the fused kernel's source, verbatim) ----------
+// ---- std::thread emulation of one CUDA block for dpt_pipe.h (the pipeline kernels' source, verbatim) --------
 namespace {
 struct HostShared {
     std::barrier<> bar;
@@ -26,11 +26,19 @@ struct HostBlk {
     HostShared* sh;
     int tid() const { return tid_; }
     int nthreads() const { return nt_; }
-    void sync() const { sh->bar.arrive_and_wait(); }
+    bool persistent() const { return true; }  // ONE emulated CTA walks all tiles in ticket order
+    void sync() const { if (sh) sh->bar.arrive_and_wait(); }
     void atomic_or(uint32_t* p, uint32_t v) const { __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
     void atomic_add(uint32_t* p, uint32_t v) const { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
-    void atomic_add_u64(unsigned long long* p, unsigned long long v) const { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
-    unsigned take_ticket(unsigned int* p) const { return __atomic_fetch_add(p, 1u, __ATOMIC_RELAXED); }
+    uint32_t atomic_add_ret(uint32_t* p, uint32_t v) const { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+    unsigned long long atomic_add_u64_ret(unsigned long long* p, unsigned long long v) const {
+        return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+    }
+    unsigned long long load_relaxed(const unsigned long long* p) const { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+    unsigned long long cas_u64(unsigned long long* p, unsigned long long expect, unsigned long long desired) const {
+        __atomic_compare_exchange_n(p, &expect, desired, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
+        return expect;  // old value, like atomicCAS
+    }
     uint32_t exclusive_scan(uint32_t v, uint32_t*, uint32_t& total) const {
         sh->vals[tid_] = v;
         sync();
@@ -43,15 +51,12 @@ struct HostBlk {
         sync();
         return ex;
     }
-    // one emulated CTA processes the tiles in order, so the predecessor's inclusive prefix is always there
-    void lookback(const dpt::TileParams& P, dpt::TileSmem& S, int tile) const {
+    // tiles are processed in order by the one emulated CTA: the predecessor's inclusive prefix is always there
+    void lookback(unsigned long long* desc, int tile, unsigned long long agg, unsigned long long* out) const {
         if (tid_ != 0) return;
-        const unsigned long long pw = tile ? (P.desc_w[tile - 1] & dpt::TL_DESC_MASK) : 0ull;
-        const unsigned long long pt = tile ? (P.desc_t[tile - 1] & dpt::TL_DESC_MASK) : 0ull;
-        P.desc_w[tile] = (2ull << 62) | (pw + (S.tile_tot >> 16));
-        P.desc_t[tile] = (2ull << 62) | (pt + (S.tile_tot & 0xFFFFu));
-        S.base_w = pw;
-        S.base_t = pt;
+        const unsigned long long prev = tile ? (desc[tile - 1] & dpt::PD_MASK) : 0ull;
+        desc[tile] = (2ull << 62) | (prev + agg);
+        *out = prev;
     }
 };
 }  // namespace
@@ -134,21 +139,17 @@ int64_t sim_spm_normalise(void* vv, const uint8_t* text, int64_t n, const int64_
     return ob;
 }
 
-// The fused corpus kernel's code (dpt_tile.h) on `nthreads` host threads emulating ONE CTA.  kc overrides the
-// number of trie slots "staged in shared memory" (0 = default) to exercise the global-memory lookup path.
-int32_t sim_encode_corpus_fused(void* vv, int32_t spm, const uint8_t* text, int64_t n_bytes, const int64_t* doc_offs,
-                                int64_t n_docs, int32_t* ids, int64_t ids_cap, int32_t* word_lens, uint8_t* word_flags,
-                                int64_t word_cap, int64_t* doc_tok_offs, uint8_t* doc_flags, int64_t* counters,
-                                int64_t* n_out, int32_t nthreads, int32_t kc) {
+// The corpus pipeline's code (dpt_pipe.h): kernel A on `nthreads` host threads emulating one CTA, kernel B as a
+// plain loop over its threads, kernel C on PC_THREADS host threads.  n_slots (power of two, 0 = default) and
+// odd_cap/pool_cap/lp_cap (0 = default) shrink the tables to exercise probe failure and capacity reporting.
+int32_t sim_encode_corpus_pipe(void* vv, int32_t spm, const uint8_t* text, int64_t n_bytes, const int64_t* doc_offs,
+                               int64_t n_docs, int32_t* ids, int64_t ids_cap, int32_t* word_lens, uint8_t* word_flags,
+                               int64_t word_cap, int64_t* doc_tok_offs, uint8_t* doc_flags, int64_t* counters,
+                               int64_t* n_out, int32_t nthreads, int64_t n_slots, int64_t odd_cap, int64_t pool_cap,
+                               int64_t lp_cap) {
     using namespace dpt;
     dpt_vocab* v = (dpt_vocab*)vv;
-    const int64_t n_tiles = (n_bytes + TL_T - 1) / TL_T;
-    std::vector<unsigned long long> dw(n_tiles + 1, 0), dt(n_tiles + 1, 0);
-    unsigned int ticket = 0;
-    std::vector<uint8_t> an(TL_ARENA_POS);
-    std::vector<uint64_t> ab(TL_ARENA_POS);
-    std::vector<uint16_t> aa(TL_ARENA_POS), abb(TL_ARENA_POS);
-    TileParams P{};
+    PipeParams P{};
     P.V = v->h_view;
     P.text = text;
     P.n_bytes = n_bytes;
@@ -163,30 +164,80 @@ int32_t sim_encode_corpus_fused(void* vv, int32_t spm, const uint8_t* text, int6
     P.doc_flags = doc_flags;
     P.counters = (unsigned long long*)counters;
     P.n_out = n_out;
+    const int64_t n_tiles = (n_bytes + PA_T - 1) / PA_T, n_ctiles = (word_cap + PC_TILE - 1) / PC_TILE;
+    if (n_slots <= 0) {
+        n_slots = 4096;
+        while (n_slots < n_bytes / 48) n_slots <<= 1;
+    }
+    if (odd_cap <= 0) odd_cap = word_cap + 16;
+    if (pool_cap <= 0) pool_cap = 6 * n_bytes + 3 * word_cap + 64;
+    if (lp_cap <= 0) lp_cap = 6 * n_bytes + 8 * word_cap + 64;
+    PipeCtl ctl{};
+    std::vector<unsigned long long> dw(n_tiles + 1, 0), dt(n_ctiles + 1, 0), tags(n_slots, 0);
+    std::vector<uint4> res(n_slots), odd_res(odd_cap);
+    std::vector<uint32_t> pending(n_slots), refs(word_cap + 16), longq(n_slots + odd_cap);
+    std::vector<int64_t> dfw(n_docs + 1, -1);
+    std::vector<OddWord> odd(odd_cap);
+    std::vector<int32_t> pool(pool_cap);
+    std::vector<uint8_t> lpn(lp_cap);
+    std::vector<uint64_t> lpb(lp_cap);
+    std::vector<uint16_t> lpa(lp_cap), lpbb(lp_cap);
+    P.ctl = &ctl;
     P.desc_w = dw.data();
     P.desc_t = dt.data();
-    P.ticket = &ticket;
-    P.arena_norm = an.data();
-    P.arena_best = ab.data();
-    P.arena_a = aa.data();
-    P.arena_b = abb.data();
+    P.tags = tags.data();
+    P.res = res.data();
+    P.pending = pending.data();
+    P.refs = refs.data();
+    P.doc_first_word = dfw.data();
+    P.odd = odd.data();
+    P.odd_res = odd_res.data();
+    P.pool = pool.data();
+    P.longq = longq.data();
+    P.lp_norm = lpn.data();
+    P.lp_best = lpb.data();
+    P.lp_a = lpa.data();
+    P.lp_b = lpbb.data();
+    P.odd_cap = odd_cap;
+    P.pool_cap = pool_cap;
+    P.lp_cap = lp_cap;
+    P.slot_mask = (uint32_t)(n_slots - 1);
     P.n_tiles = (int32_t)n_tiles;
-    const int32_t kmax = (int32_t)(v->da.size() < (size_t)TL_KC ? v->da.size() : (size_t)TL_KC);
-    P.kc = kc > 0 && kc < kmax ? kc : kmax;
+    P.n_ctiles = (int32_t)n_ctiles;
     P.spm = spm;
     P.rule = spm ? 1 : 0;
     memset(counters, 0, 32);
     memset(n_out, 0, 64);
     if (doc_flags) memset(doc_flags, 0, (size_t)n_docs);
-    auto S = std::make_unique<TileSmem>();
-    HostShared sh(nthreads);
-    std::vector<std::thread> th;
-    for (int t = 0; t < nthreads; ++t)
-        th.emplace_back([&, t] {
-            HostBlk blk{t, nthreads, &sh};
-            tl_loop(blk, P, *S, 0);
-        });
-    for (auto& x : th) x.join();
+    {   // kernel A
+        auto S = std::make_unique<ASmem>();
+        HostShared sh(nthreads);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t)
+            th.emplace_back([&, t] {
+                HostBlk blk{t, nthreads, &sh};
+                pa_kernel(blk, P, *S);
+            });
+        for (auto& x : th) x.join();
+    }
+    {   // kernels B (no block-level cooperation: run the threads one after the other)
+        HostBlk blk{0, 1, nullptr};
+        const int64_t g = 37;
+        for (int64_t t = 0; t < g; ++t) pb_thread(blk, P, t, g);
+        for (int64_t t = 0; t < g; ++t) pb_long_thread(blk, P, t, g);
+    }
+    {   // kernel C
+        auto S = std::make_unique<CSmem>();
+        HostShared sh(PC_THREADS);
+        std::vector<std::thread> th;
+        for (int t = 0; t < PC_THREADS; ++t)
+            th.emplace_back([&, t] {
+                HostBlk blk{t, PC_THREADS, &sh};
+                pc_kernel(blk, P, *S);
+            });
+        for (auto& x : th) x.join();
+    }
+    pd_finish(P);
     return 0;
 }
 }

@@ -320,10 +320,10 @@ def test_full_size_properties_100mb(dev):
         assert dto[d + 1] - dto[d] <= len(tok.encode(doc))
 
 
-def test_fused_kernel_equals_general_path(dev):
-    """The single-launch fused tile kernel and the general multi-kernel path give identical outputs on edge-case
-    input (tiny documents, double spaces, raw U+2581, OOV characters, malformed UTF-8 cut by document boundaries),
-    and a word too long for the fused kernel's arena is rerouted through the general path, not mis-solved."""
+def test_pipeline_equals_general_path(dev):
+    """The deduplicating corpus pipeline and the general per-occurrence path give identical outputs on edge-case
+    input (tiny documents, double spaces, raw U+2581, OOV characters, malformed UTF-8 cut by document boundaries,
+    words far longer than a scan tile)."""
     from dptok import _cabi
     from dptok.engine import pack_documents
     tok, t2i, eng = _llama_engine("llama2_2k", dev)
