@@ -100,3 +100,110 @@ DPT_HD bool dpt_backward_emit(const DptVocabView& V, const uint8_t* s, int32_t n
     }
     return true;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Warp-friendly form of the same DP.  dpt_forward above is a nest of data-dependent loops (start position x trie
+// walk); on the GPU the lanes of a warp leave those loops at different times and run the rest of the word
+// serialised (measured: 1.7 of 32 lanes active).  Here the forward pass is ONE loop whose every iteration is one
+// trie step of the lane's current (start, end) pair - a state machine - so the lanes of a warp stay converged and
+// a lane only idles for the difference between its total step count and the warp's maximum.  The slot of the
+// winning edge is kept beside each back-pointer (As/Bs), so the backward pass needs no re-hash of the token
+// bytes: id = slot_id[slot].
+// ---------------------------------------------------------------------------------------------------------
+DPT_HD void dpt_forward_flat(const DptVocabView& V, const uint8_t* s, int32_t n, uint64_t* best, uint16_t* A, uint16_t* B,
+                             uint32_t* As, uint32_t* Bs) {
+    const bool cp_mode = V.unit_mode != 0;
+    uint32_t u = 0;
+    for (int32_t p = 0; p <= n; ++p) {
+        const bool b = (p == 0 || p == n || !cp_mode) ? true : dpt_is_cp_start(s[p]);
+        best[p] = b ? dpt_key_phantom(u) : ~0ull;
+        if (b) ++u;
+        A[p] = 0;
+        B[p] = 0;
+    }
+    if (n > 0) best[0] = dpt_key_origin();
+    const uint32_t* __restrict__ da = V.da;
+    int32_t j = -1, i = 0;
+    uint32_t entry = 0, cl = 0;
+    uint64_t kj = 0;
+    bool walking = false;
+    for (;;) {
+        if (!walking) {
+            if (++j >= n) break;
+            kj = best[j];
+            entry = DPT_DA_ROOT_ENTRY;
+            i = j;
+            cl = 0;
+            walking = kj != ~0ull;  // not a unit boundary: nothing starts here
+            if (!walking) continue;
+        }
+        const uint32_t base = entry >> DPT_DA_BASE_SHIFT;
+        const uint32_t c = i < n ? (uint32_t)s[i] : 0x100u;
+        const uint32_t slot = base + (c & 0xFFu);
+        uint32_t e = 0;
+        if (base != 0 && c < 0x100u) {
+#if defined(__CUDA_ARCH__)
+            e = __ldg(da + slot);
+#else
+            e = da[slot];
+#endif
+        }
+        if ((e & DPT_DA_MATCH_MASK) != (DPT_DA_OCCUPIED | c)) {
+            walking = false;
+            continue;
+        }
+        entry = e;
+        ++i;
+        cl += (!cp_mode || dpt_is_cp_start(c)) ? 1u : 0u;
+        if (e & DPT_DA_TERMINAL) {
+            const uint64_t bi = best[i];
+            if (bi != ~0ull) {
+                const uint64_t k = dpt_key_extend(kj, cl);
+                const uint32_t packed = slot | ((cl < 1023u ? cl : 1023u) << 22);  // slots < 2^22 (DPT_DA_MAX_SLOTS)
+                if ((k >> 31) <= (bi >> 31)) {
+                    A[i] = (uint16_t)(i - j);
+                    As[i] = packed;
+                }
+                if (k <= bi) {
+                    best[i] = k;
+                    B[i] = (uint16_t)(i - j);
+                    Bs[i] = packed;
+                }
+            }
+        }
+    }
+}
+
+// Backward selection for dpt_forward_flat: writes the len ids to out_ids[0..len) in text order.  Returns false
+// (and writes nothing) when the word is untokenizable.
+DPT_HD bool dpt_backward_flat(const DptVocabView& V, const uint8_t* s, int32_t n, const uint64_t* best, const uint16_t* A,
+                              const uint16_t* B, const uint32_t* As, const uint32_t* Bs, int32_t* out_ids, int64_t out_cap) {
+    const uint64_t kn = best[n];
+    if (!dpt_key_reach(kn)) return false;
+    const bool cp_mode = V.unit_mode != 0;
+    const uint32_t target = dpt_key_longest(kn);
+    int64_t slot_out = (int64_t)dpt_key_len(kn) - 1;
+    bool got = false;
+    int32_t i = n;
+    while (i > 0 && slot_out >= 0) {
+        const int32_t d = got ? A[i] : B[i];
+        if (d <= 0 || d > i) break;  // cannot happen on a reachable path; never spin on corrupt state
+        const uint32_t ts = got ? As[i] : Bs[i];
+        const int32_t j = i - d;
+        if (!got) {
+            uint32_t cl = ts >> 22;
+            if (cl == 1023u) {  // saturated: count (tokens of >= 1023 units only)
+                cl = (uint32_t)d;
+                if (cp_mode) {
+                    cl = 0;
+                    for (int32_t p = j; p < i; ++p) cl += dpt_is_cp_start(s[p]) ? 1u : 0u;
+                }
+            }
+            if (cl == target) got = true;
+        }
+        if (slot_out < out_cap) out_ids[slot_out] = V.slot_id[ts & 0x3FFFFFu];
+        --slot_out;
+        i = j;
+    }
+    return true;
+}

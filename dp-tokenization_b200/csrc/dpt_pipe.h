@@ -10,8 +10,8 @@
 //   B  DP             ONE shortest-tokenization DP per DISTINCT word (dp_tokenize.py:24-84 in the closed form of
 //                     dpt_dp_core.h): normalise (U+2581 marker, "<0xHH>" expansion of out-of-vocabulary
 //                     characters), forward DP with the reference's tie order, backward select, ids -> the
-//                     word's 16-byte result record.
-//   C  emit           one thread per 4 words: ref -> result record -> token count; block scan + decoupled
+//                     word's 32-byte result record (one sector: count + up to 7 ids inline).
+//   C  emit           one thread per 8 words: ref -> result record -> token count; block scan + decoupled
 //                     look-back over tiles -> final offsets; ids, per-word lengths, flags, document offsets and
 //                     counters written once, in corpus order.
 //
@@ -47,16 +47,27 @@ constexpr int PA_PROBES = 8;
 constexpr int PB_THREADS = 128;
 constexpr int PB_LOCAL = 72;                  // normalised bytes solved with per-thread local state in kernel B
 constexpr int PC_THREADS = 256;
-constexpr int PC_PER = 4;                     // words per thread in kernel C
+constexpr int PC_PER = 8;                     // words per thread in kernel C
+constexpr int PA_STAGE = 1024;                // refs staged in shared memory per tile (more -> direct writes)
 constexpr int PC_TILE = PC_THREADS * PC_PER;
 
-constexpr uint32_t REF_BOS = 0xFFFFFFFFu;     // the '<s>' word in front of every SPM_LLAMA document
-constexpr uint32_t REF_ODD = 0x80000000u;     // | index into the odd-word list (not deduplicated)
+// one 32-bit ref per word: top two bits 11 = the '<s>' word in front of an SPM_LLAMA document | document index,
+// 10 = index into the odd-word list (not deduplicated), otherwise the word's table slot
+constexpr uint32_t REF_BOS = 0xC0000000u;
+constexpr uint32_t REF_ODD = 0x80000000u;
+constexpr uint32_t REF_KIND = 0xC0000000u;
+constexpr uint32_t REF_INDEX = 0x3FFFFFFFu;
 constexpr unsigned long long PD_MASK = (1ull << 62) - 1;
 
 constexpr uint32_t RES_UNTOK = 1u << 24;      // result meta: word_len (24 bits) | flags
-constexpr uint32_t RES_POOLED = 1u << 25;     // ids live in the pool at rec.y (more than 3 ids)
+constexpr uint32_t RES_POOLED = 1u << 25;     // more than RES_INLINE ids: they live in the pool at ids[0] | ids[1] << 32
+constexpr int RES_INLINE = 7;
 constexpr uint32_t RES_LONG = 1u << 26;       // solved by the long-word kernel
+
+struct alignas(32) ResRec {  // result of one distinct word: exactly one 32-byte sector
+    uint32_t meta;           // word_len (len_dp[n], 24 bits) | RES_* flags
+    int32_t ids[RES_INLINE];
+};
 
 struct OddWord {
     int64_t pos;   // global offset of the word's first raw byte
@@ -89,10 +100,10 @@ struct PipeParams {
     uint32_t* refs;               // word_cap
     int64_t* doc_first_word;      // n_docs + 1
     unsigned long long* tags;     // n_slots, zeroed by the launcher
-    uint4* res;                   // n_slots
+    ResRec* res;                  // n_slots
     uint32_t* pending;            // n_slots
     OddWord* odd;                 // odd_cap
-    uint4* odd_res;               // odd_cap
+    ResRec* odd_res;              // odd_cap
     int32_t* pool;                // pool_cap ids of words with more than 3 tokens
     uint32_t* longq;              // n_slots + odd_cap
     uint8_t* lp_norm;             // long-word scratch: lp_cap positions
@@ -107,6 +118,7 @@ struct PipeParams {
     int32_t n_tiles, n_ctiles;
     int32_t spm;  // 1: SPM_LLAMA rule; 0: byte-level rules
     int32_t rule;
+    int32_t vec_ok;  // word_lens / word_flags are aligned for 16- / 8-byte stores
 };
 
 struct ASmem {
@@ -121,6 +133,7 @@ struct ASmem {
     uint32_t cnt[PA_NW + 2];
     uint16_t wlist[2 * PA_T];  // region index of every word that starts in this tile (| 0x8000: its '<s>' word)
     uint32_t pend[PA_T];       // table slots claimed by this tile
+    uint32_t stage[PA_STAGE];  // refs of this tile, written out coalesced once the word offset is known
     uint32_t scan[40];
     int32_t tile, d_first, n_entries;
     uint32_t n_pend, pend_base;
@@ -191,6 +204,19 @@ DPT_HD int64_t pp_upper_bound(const int64_t* a, int64_t n, int64_t x) {  // firs
     }
     return lo;
 }
+
+// 4 bytes at byte offset `off` of a 4-byte-aligned buffer (little endian), two aligned loads + funnel shift
+DPT_HD uint32_t pp_load4(const uint8_t* base4, int64_t off) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(base4 + (off & ~(int64_t)3));
+    const uint32_t lo = w[0], hi = w[1];
+    const uint32_t sh = (uint32_t)(off & 3) * 8u;
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+}
+DPT_HD uint32_t pp_tail_mask(int nbytes) { return nbytes >= 4 ? ~0u : ((1u << (8 * nbytes)) - 1u); }
 
 DPT_HD unsigned long long pp_tag(uint32_t hash, int len, int64_t pos) {
     return ((unsigned long long)(hash & 0xFFFFFu) << 44) | ((unsigned long long)len << 38) | (unsigned long long)(pos + 1);
@@ -339,26 +365,24 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
     }
     blk.sync();
     const int ne = S.n_entries;
-    blk.lookback(P.desc_w, tile, (unsigned long long)ne, &S.base_w);
-    blk.sync();
-    const int64_t base_w = (int64_t)S.base_w;
+    // publish this tile's word count at once (successors never wait long); resolve the prefix as late as possible
+    blk.lookback_publish(P.desc_w, tile, (unsigned long long)ne);
+    const bool staged = ne <= PA_STAGE;
+    if (!staged) {
+        blk.lookback_resolve(P.desc_w, tile, (unsigned long long)ne, &S.base_w);
+        blk.sync();
+    }
 
     // ---- one table probe per word ------------------------------------------------------------------------------
     for (int k = tid; k < ne; k += nt) {
         const uint32_t e = S.wlist[k];
         const int ws = (int)(e & 0x7FFFu);
-        const int64_t gw = base_w + k;
         uint32_t ref;
         if (e & 0x8000u) {
-            ref = REF_BOS;
             const int64_t d = pp_lower_bound(P.doc_offs, P.n_docs + 1, g0 + ws);
-            if (d < P.n_docs) P.doc_first_word[d] = gw;
+            ref = REF_BOS | (uint32_t)(d & REF_INDEX);
         } else {
             const bool ds = pp_bit(S.mDS, ws);
-            if (!spm && ds) {
-                const int64_t d = pp_lower_bound(P.doc_offs, P.n_docs + 1, g0 + ws);
-                if (d < P.n_docs) P.doc_first_word[d] = gw;
-            }
             const int we = pp_mask_next(S.mWS, ws + 1, PA_R);
             const int ml = !spm ? 0 : ds ? 0 : (S.text[ws] == 0x20u ? 1 : 3);
             const int b = ws + ml, len = we - b;
@@ -366,12 +390,17 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
             bool odd = open || len > PA_MAXLEN || len < 0 || pp_any_in_range(S.mCX, ws, we);
             ref = 0;
             if (!odd) {
-                uint32_t h = 0x811C9DC5u;
-                for (int q = b; q < we; ++q) h = (h ^ S.text[q]) * 0x01000193u;
-                h ^= h >> 15;
+                // hash the body 4 bytes at a time (tail zero-padded)
+                uint32_t h = 0x811C9DC5u ^ (uint32_t)len;
+                for (int q = 0; q < len; q += 4) {
+                    const uint32_t v = pp_load4(S.text, b + q) & pp_tail_mask(len - q);
+                    h = (h ^ v) * 0x9E3779B1u;
+                    h ^= h >> 15;
+                }
                 h *= 0x2C1B3C6Du;
                 h ^= h >> 13;
-                const unsigned long long mine = pp_tag(h >> 12, len, g0 + b);
+                const int64_t g_b = g0 + b;
+                const unsigned long long mine = pp_tag(h >> 12, len, g_b);
                 uint32_t slot = h & P.slot_mask;
                 bool done = false;
                 for (int probe = 0; probe < PA_PROBES && !done; ++probe, slot = (slot + 1) & P.slot_mask) {
@@ -387,9 +416,18 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
                         }
                     }
                     if ((t >> 38) == (mine >> 38)) {  // same hash bits and length: verify against the corpus text
-                        const uint8_t* rep = P.text + pp_tag_pos(t);
+                        const int64_t rp = pp_tag_pos(t);
                         bool same = true;
-                        for (int q = 0; q < len && same; ++q) same = rep[q] == S.text[b + q];
+                        if (rp + len + 8 <= n) {  // 4 bytes at a time off the 4-byte-aligned corpus base
+                            const uint8_t* base4 = P.text - ((uintptr_t)P.text & 3u);
+                            const int64_t ro = rp + (int64_t)((uintptr_t)P.text & 3u);
+                            for (int q = 0; q < len && same; q += 4) {
+                                const uint32_t m = pp_tail_mask(len - q);
+                                same = ((pp_load4(base4, ro + q) ^ pp_load4(S.text, b + q)) & m) == 0;
+                            }
+                        } else {
+                            for (int q = 0; q < len && same; ++q) same = P.text[rp + q] == S.text[b + q];
+                        }
                         if (same) {
                             ref = slot;
                             done = true;
@@ -409,18 +447,25 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
                     o.virt = (spm && ds) ? 1 : 0;
                     P.odd[j] = o;
                 }
-                ref = REF_ODD | j;
+                ref = REF_ODD | (j & REF_INDEX);
             }
         }
-        if (gw < P.word_cap) P.refs[gw] = ref;
+        if (staged) {
+            S.stage[k] = ref;
+        } else {
+            const int64_t gw = (int64_t)S.base_w + k;
+            if (gw < P.word_cap) P.refs[gw] = ref;
+        }
     }
+    if (staged) blk.lookback_resolve(P.desc_w, tile, (unsigned long long)ne, &S.base_w);  // warp 0, after its probes
     blk.sync();
+    const int64_t base_w = (int64_t)S.base_w;
+    if (staged)
+        for (int k = tid; k < ne; k += nt)
+            if (base_w + k < P.word_cap) P.refs[base_w + k] = S.stage[k];
     if (tid == 0) {
         S.pend_base = S.n_pend ? blk.atomic_add_ret(&P.ctl->n_pending, S.n_pend) : 0u;
-        if (tile == P.n_tiles - 1) {
-            P.ctl->n_words = (unsigned long long)(base_w + ne);
-            P.doc_first_word[P.n_docs] = base_w + ne;
-        }
+        if (tile == P.n_tiles - 1) P.ctl->n_words = (unsigned long long)(base_w + ne);
     }
     blk.sync();
     for (uint32_t i = tid; i < S.n_pend; i += nt) P.pending[S.pend_base + i] = S.pend[i];
@@ -461,9 +506,16 @@ DPT_PIPE_FN int32_t pb_normalise(const PipeParams& P, int64_t p, int64_t e_end, 
         n = 3;
     }
     while (p < e_end) {
+        const uint32_t c0 = P.text[p];
+        if (c0 < 128u && c0 != 0x20u && ((V.ascii_single[c0 >> 5] >> (c0 & 31)) & 1u) &&
+            (p + 1 >= e_end || dpt_is_cp_start(P.text[p + 1]))) {  // the common case, one straight line
+            if (n + 1 > cap) return -1;
+            out[n++] = (uint8_t)c0;
+            ++p;
+            continue;
+        }
         int64_t e = p + 1;
         while (e < e_end && !dpt_is_cp_start(P.text[e])) ++e;
-        const uint32_t c0 = P.text[p];
         const int32_t src = (int32_t)(e - p);
         const bool mk = (c0 == 0x20u) || (src == 3 && c0 == DPT_MARK0 && P.text[p + 1] == DPT_MARK1 && P.text[p + 2] == DPT_MARK2);
         if (mk) {
@@ -504,7 +556,7 @@ DPT_PIPE_FN int32_t pb_normalise(const PipeParams& P, int64_t p, int64_t e_end, 
 struct PbItem {
     int64_t pos, end;
     bool marker;
-    uint4* out;
+    ResRec* out;
 };
 DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint32_t i, uint32_t n_pending) {
     PbItem it;
@@ -525,57 +577,62 @@ DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint32_t i, uint32_t n_pending) 
     return it;
 }
 
-template <class Blk>
-DPT_PIPE_FN void pb_store(Blk& blk, const PipeParams& P, uint4* out, uint32_t word_len, bool reach, const int32_t* ids, uint32_t extra) {
-    uint4 r;
-    r.x = (word_len & 0xFFFFFFu) | (reach ? 0u : RES_UNTOK) | extra;
-    r.y = r.z = r.w = 0;
-    if (reach) {
-        if (word_len <= 3) {
-            r.y = (uint32_t)ids[0];
-            if (word_len > 1) r.z = (uint32_t)ids[1];
-            if (word_len > 2) r.w = (uint32_t)ids[2];
-        } else {
-            const unsigned long long off = blk.atomic_add_u64_ret(&P.ctl->pool_used, (unsigned long long)word_len);
-            r.x |= RES_POOLED;
-            r.y = (uint32_t)(off & 0xFFFFFFFFull);
-            r.z = (uint32_t)(off >> 32);
-            if ((int64_t)(off + word_len) <= P.pool_cap)
-                for (uint32_t k = 0; k < word_len; ++k) P.pool[off + k] = ids[k];
-        }
-    }
-    *out = r;
-}
-
-// one thread per distinct word, state in registers / local memory
+// one thread per distinct word, DP state in local memory.  The loop body is written so that the lanes of a warp
+// go through the same sequence of single loops (normalise, forward state machine, backward chase) and reconverge
+// between them.
 template <class Blk>
 DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P, int64_t gtid, int64_t gthreads) {
     const uint32_t n_pending = P.ctl->n_pending;
     const uint32_t n_odd = P.ctl->n_odd < (uint32_t)P.odd_cap ? P.ctl->n_odd : (uint32_t)P.odd_cap;
     const uint64_t total = (uint64_t)n_pending + n_odd;
-    for (uint64_t i = (uint64_t)gtid; i < total; i += (uint64_t)gthreads) {
-        const PbItem it = pb_item(P, (uint32_t)i, n_pending);
+    const uint64_t rounds = (total + (uint64_t)gthreads - 1) / (uint64_t)gthreads;
+    for (uint64_t r = 0; r < rounds; ++r) {
+        const uint64_t i = r * (uint64_t)gthreads + (uint64_t)gtid;
+        const bool valid = i < total;
+        PbItem it;
+        it.out = nullptr;
         uint8_t norm[PB_LOCAL + 8];
-        const int32_t nlen = pb_normalise(P, it.pos, it.end, it.marker, norm, PB_LOCAL);
-        if (nlen < 0) {
-            const uint32_t q = blk.atomic_add_ret(&P.ctl->n_long, 1u);
-            P.longq[q] = (uint32_t)i;
-            continue;
+        int32_t nlen = 0;
+        if (valid) {
+            it = pb_item(P, (uint32_t)i, n_pending);
+            nlen = pb_normalise(P, it.pos, it.end, it.marker, norm, PB_LOCAL);
+            if (nlen < 0) {
+                const uint32_t q = blk.atomic_add_ret(&P.ctl->n_long, 1u);
+                P.longq[q] = (uint32_t)i;
+            }
         }
-        if (nlen == 0) {  // cannot happen (documents are non-empty); keep the record defined
-            uint4 z; z.x = RES_UNTOK; z.y = z.z = z.w = 0;
-            *it.out = z;
-            continue;
-        }
+        blk.reconverge();
+        const int32_t n = nlen > 0 ? nlen : 0;
         uint64_t best[PB_LOCAL + 1];
         uint16_t A[PB_LOCAL + 1], B[PB_LOCAL + 1];
-        dpt_forward<true>(P.V, norm, nlen, nullptr, best, A, B);
-        const uint64_t kn = best[nlen];
+        uint32_t As[PB_LOCAL + 1], Bs[PB_LOCAL + 1];
+        dpt_forward_flat(P.V, norm, n, best, A, B, As, Bs);
+        blk.reconverge();
+        if (!valid || nlen < 0) continue;
+        ResRec rec;
+        for (int k = 0; k < RES_INLINE; ++k) rec.ids[k] = 0;
+        if (nlen == 0) {  // cannot happen (documents are non-empty); keep the record defined
+            rec.meta = RES_UNTOK;
+            *it.out = rec;
+            continue;
+        }
+        const uint64_t kn = best[n];
         const uint32_t word_len = dpt_key_len(kn);
         const bool reach = dpt_key_reach(kn);
-        int32_t ids[PB_LOCAL + 1];
-        if (reach) dpt_backward_emit(P.V, norm, nlen, best, A, B, ids, PB_LOCAL + 1);
-        pb_store(blk, P, it.out, word_len, reach, ids, 0u);
+        rec.meta = (word_len & 0xFFFFFFu) | (reach ? 0u : RES_UNTOK);
+        if (reach) {
+            if (word_len <= (uint32_t)RES_INLINE) {
+                dpt_backward_flat(P.V, norm, n, best, A, B, As, Bs, rec.ids, RES_INLINE);
+            } else {
+                const unsigned long long off = blk.atomic_add_u64_ret(&P.ctl->pool_used, (unsigned long long)word_len);
+                rec.meta |= RES_POOLED;
+                rec.ids[0] = (int32_t)(uint32_t)(off & 0xFFFFFFFFull);
+                rec.ids[1] = (int32_t)(uint32_t)(off >> 32);
+                if ((int64_t)(off + word_len) <= P.pool_cap)
+                    dpt_backward_flat(P.V, norm, n, best, A, B, As, Bs, P.pool + off, (int64_t)word_len);
+            }
+        }
+        *it.out = rec;
     }
 }
 
@@ -589,9 +646,11 @@ DPT_PIPE_FN void pb_long_thread(Blk& blk, const PipeParams& P, int64_t gtid, int
         const int64_t raw = it.end - it.pos;
         const int64_t need = (P.spm ? 6 * raw + 3 : raw) + 2;
         const unsigned long long off = blk.atomic_add_u64_ret(&P.ctl->lp_used, (unsigned long long)need);
+        ResRec rec;
+        for (int q = 0; q < RES_INLINE; ++q) rec.ids[q] = 0;
         if ((int64_t)(off + need) > P.lp_cap || need >= (1ll << 31)) {  // reported through n_out; caller retries bigger
-            uint4 z; z.x = RES_UNTOK | RES_LONG; z.y = z.z = z.w = 0;
-            *it.out = z;
+            rec.meta = RES_UNTOK | RES_LONG;
+            *it.out = rec;
             blk.atomic_add_u64_ret(&P.ctl->n_too_long, 1ull);
             continue;
         }
@@ -604,47 +663,36 @@ DPT_PIPE_FN void pb_long_thread(Blk& blk, const PipeParams& P, int64_t gtid, int
         const uint64_t kn = best[nlen];
         const uint32_t word_len = dpt_key_len(kn);
         const bool reach = dpt_key_reach(kn);
-        uint4 r;
-        r.x = (word_len & 0xFFFFFFu) | (reach ? 0u : RES_UNTOK) | RES_LONG;
-        r.y = r.z = r.w = 0;
+        rec.meta = (word_len & 0xFFFFFFu) | (reach ? 0u : RES_UNTOK) | RES_LONG;
         if (reach) {
             const unsigned long long po = blk.atomic_add_u64_ret(&P.ctl->pool_used, (unsigned long long)word_len);
-            r.x |= RES_POOLED;
-            r.y = (uint32_t)(po & 0xFFFFFFFFull);
-            r.z = (uint32_t)(po >> 32);
+            rec.meta |= RES_POOLED;
+            rec.ids[0] = (int32_t)(uint32_t)(po & 0xFFFFFFFFull);
+            rec.ids[1] = (int32_t)(uint32_t)(po >> 32);
             if ((int64_t)(po + word_len) <= P.pool_cap) dpt_backward_emit(P.V, norm, nlen, best, A, B, P.pool + po, (int64_t)word_len);
         }
-        *it.out = r;
+        *it.out = rec;
     }
 }
 
 // =========================================================================================================
 // Kernel C: scan + emit
 // =========================================================================================================
-DPT_PIPE_FN uint4 pc_record(const PipeParams& P, uint32_t ref) {
-    uint4 r;
-    if (ref == REF_BOS) {
-        r.x = (uint32_t)P.V.bos_len | (P.V.bos_ntok ? 0u : RES_UNTOK);
-        r.y = (uint32_t)P.V.bos_ids[0];
-        r.z = (uint32_t)P.V.bos_ids[1];
-        r.w = (uint32_t)P.V.bos_ids[2];
-        return r;
+DPT_PIPE_FN const ResRec* pc_record_ptr(const PipeParams& P, uint32_t ref) {
+    if ((ref & REF_KIND) == REF_ODD) {
+        const uint32_t j = ref & REF_INDEX;
+        return (int64_t)j < P.odd_cap ? &P.odd_res[j] : nullptr;
     }
-    const uint4* src;
-    if (ref & REF_ODD) {
-        const uint32_t j = ref & 0x7FFFFFFFu;
-        if ((int64_t)j >= P.odd_cap) {
-            r.x = RES_UNTOK; r.y = r.z = r.w = 0;
-            return r;
-        }
-        src = &P.odd_res[j];
-    } else {
-        src = &P.res[ref];
-    }
+    return &P.res[ref];
+}
+DPT_PIPE_FN uint32_t pc_meta(const PipeParams& P, uint32_t ref) {
+    if ((ref & REF_KIND) == REF_BOS) return (uint32_t)P.V.bos_len | (P.V.bos_ntok ? 0u : RES_UNTOK);
+    const ResRec* r = pc_record_ptr(P, ref);
+    if (!r) return RES_UNTOK;
 #if defined(__CUDA_ARCH__)
-    return __ldg(src);
+    return __ldg(&r->meta);
 #else
-    return *src;
+    return r->meta;
 #endif
 }
 
@@ -653,49 +701,85 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
     const int tid = blk.tid();
     const int64_t n_words = (int64_t)P.ctl->n_words < P.word_cap ? (int64_t)P.ctl->n_words : P.word_cap;
     const int64_t w0 = (int64_t)tile * PC_TILE + (int64_t)tid * PC_PER;
-    uint4 rec[PC_PER];
-    uint32_t ntok[PC_PER];
+    uint32_t ref[PC_PER], meta[PC_PER];
     uint32_t mine = 0, untok = 0;
+    if (w0 + PC_PER <= n_words) {  // two 16-byte loads of 8 refs
+        const uint4 r0 = *reinterpret_cast<const uint4*>(P.refs + w0);
+        const uint4 r1 = *reinterpret_cast<const uint4*>(P.refs + w0 + 4);
+        ref[0] = r0.x; ref[1] = r0.y; ref[2] = r0.z; ref[3] = r0.w;
+        ref[4] = r1.x; ref[5] = r1.y; ref[6] = r1.z; ref[7] = r1.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < PC_PER; ++k) ref[k] = w0 + k < n_words ? P.refs[w0 + k] : REF_BOS;
+    }
 #pragma unroll
     for (int k = 0; k < PC_PER; ++k) {
-        ntok[k] = 0;
+        meta[k] = RES_UNTOK;
         if (w0 + k < n_words) {
-            rec[k] = pc_record(P, P.refs[w0 + k]);
-            if (rec[k].x & RES_UNTOK) ++untok; else ntok[k] = rec[k].x & 0xFFFFFFu;
-            mine += ntok[k];
+            meta[k] = pc_meta(P, ref[k]);
+            if (meta[k] & RES_UNTOK) ++untok; else mine += meta[k] & 0xFFFFFFu;
         }
     }
     if (tid == 0) S.n_untok = 0;
     uint32_t total;
-    uint32_t off = blk.exclusive_scan(mine, S.scan, total);
+    const uint32_t off = blk.exclusive_scan(mine, S.scan, total);
+    blk.lookback_publish(P.desc_t, tile, (unsigned long long)total);
     if (untok) blk.atomic_add(&S.n_untok, untok);
-    blk.sync();
-    blk.lookback(P.desc_t, tile, (unsigned long long)total, &S.base_t);
+    // per-word outputs that do not need the token offset
+    if (w0 + PC_PER <= n_words && P.vec_ok) {
+        uint4 l0, l1;
+        l0.x = meta[0] & 0xFFFFFFu; l0.y = meta[1] & 0xFFFFFFu; l0.z = meta[2] & 0xFFFFFFu; l0.w = meta[3] & 0xFFFFFFu;
+        l1.x = meta[4] & 0xFFFFFFu; l1.y = meta[5] & 0xFFFFFFu; l1.z = meta[6] & 0xFFFFFFu; l1.w = meta[7] & 0xFFFFFFu;
+        *reinterpret_cast<uint4*>(P.word_lens + w0) = l0;
+        *reinterpret_cast<uint4*>(P.word_lens + w0 + 4) = l1;
+        unsigned long long f = 0;
+#pragma unroll
+        for (int k = 0; k < PC_PER; ++k)
+            f |= (unsigned long long)(((meta[k] & RES_UNTOK) ? 1u : 0u) | ((meta[k] & RES_LONG) ? 4u : 0u)) << (8 * k);
+        *reinterpret_cast<unsigned long long*>(P.word_flags + w0) = f;
+    } else {
+#pragma unroll
+        for (int k = 0; k < PC_PER; ++k)
+            if (w0 + k < n_words) {
+                P.word_lens[w0 + k] = (int32_t)(meta[k] & 0xFFFFFFu);
+                P.word_flags[w0 + k] = (uint8_t)(((meta[k] & RES_UNTOK) ? 1u : 0u) | ((meta[k] & RES_LONG) ? 4u : 0u));
+            }
+    }
+    blk.lookback_resolve(P.desc_t, tile, (unsigned long long)total, &S.base_t);
     blk.sync();
     int64_t gt = (int64_t)S.base_t + off;
 #pragma unroll
     for (int k = 0; k < PC_PER; ++k) {
-        const int64_t w = w0 + k;
-        if (w >= n_words) break;
-        const uint32_t meta = rec[k].x;
-        P.word_lens[w] = (int32_t)(meta & 0xFFFFFFu);
-        P.word_flags[w] = (uint8_t)(((meta & RES_UNTOK) ? 1u : 0u) | ((meta & RES_LONG) ? 4u : 0u));
-        const uint32_t ref = P.refs[w0 + k];
-        const bool doc_first = P.spm ? (ref == REF_BOS) : false;
-        if (doc_first) {
-            const int64_t d = pp_lower_bound(P.doc_first_word, P.n_docs, w);
-            if (d < P.n_docs && P.doc_first_word[d] == w) P.doc_tok_offs[d] = gt;
+        if (w0 + k >= n_words) break;
+        const uint32_t kind = ref[k] & REF_KIND;
+        if (kind == REF_BOS) {
+            const int64_t d = (int64_t)(ref[k] & REF_INDEX);
+            if (d < P.n_docs) P.doc_tok_offs[d] = gt;
         }
-        const uint32_t nk = ntok[k];
-        if (nk) {
-            if (meta & RES_POOLED) {
-                const int64_t po = (int64_t)rec[k].y | ((int64_t)rec[k].z << 32);
+        if (meta[k] & RES_UNTOK) continue;
+        const uint32_t nk = meta[k] & 0xFFFFFFu;
+        if (nk == 0) continue;
+        if (kind == REF_BOS) {
+            for (uint32_t q = 0; q < nk && q < 3; ++q)
+                if (gt + q < P.ids_cap) P.ids[gt + q] = P.V.bos_ids[q];
+        } else {
+            const ResRec* r = pc_record_ptr(P, ref[k]);
+            if (meta[k] & RES_POOLED) {
+                const int64_t po = (int64_t)(uint32_t)r->ids[0] | ((int64_t)(uint32_t)r->ids[1] << 32);
                 for (uint32_t q = 0; q < nk; ++q)
                     if (gt + q < P.ids_cap && po + q < P.pool_cap) P.ids[gt + q] = P.pool[po + q];
             } else {
-                if (gt < P.ids_cap) P.ids[gt] = (int32_t)rec[k].y;
-                if (nk > 1 && gt + 1 < P.ids_cap) P.ids[gt + 1] = (int32_t)rec[k].z;
-                if (nk > 2 && gt + 2 < P.ids_cap) P.ids[gt + 2] = (int32_t)rec[k].w;
+                const uint4 a = *reinterpret_cast<const uint4*>(r);             // meta, ids[0..2]
+                if (gt < P.ids_cap) P.ids[gt] = (int32_t)a.y;
+                if (nk > 1 && gt + 1 < P.ids_cap) P.ids[gt + 1] = (int32_t)a.z;
+                if (nk > 2 && gt + 2 < P.ids_cap) P.ids[gt + 2] = (int32_t)a.w;
+                if (nk > 3) {
+                    const uint4 c = *(reinterpret_cast<const uint4*>(r) + 1);   // ids[3..6]
+                    if (gt + 3 < P.ids_cap) P.ids[gt + 3] = (int32_t)c.x;
+                    if (nk > 4 && gt + 4 < P.ids_cap) P.ids[gt + 4] = (int32_t)c.y;
+                    if (nk > 5 && gt + 5 < P.ids_cap) P.ids[gt + 5] = (int32_t)c.z;
+                    if (nk > 6 && gt + 6 < P.ids_cap) P.ids[gt + 6] = (int32_t)c.w;
+                }
             }
         }
         gt += nk;
@@ -706,7 +790,6 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
     blk.sync();
 }
 
-// byte-level rules: every document start is a word start, not a separate word: document token offsets
 template <class Blk>
 DPT_PIPE_FN void pc_kernel(Blk& blk, const PipeParams& P, CSmem& S) {
     for (;;) {

@@ -66,16 +66,21 @@ struct DevBlk {
         return base + inc - v;
     }
 
-    // decoupled look-back by warp 0: publish this tile's aggregate, sum the predecessors' aggregates back to the
-    // nearest inclusive prefix, publish the inclusive prefix.  descriptor = status << 62 | value
-    // (1 = aggregate, 2 = inclusive).  *out = exclusive prefix of this tile (shared memory).
-    __device__ __forceinline__ void lookback(unsigned long long* desc, int tile, unsigned long long agg,
-                                             unsigned long long* out) const {
+    __device__ __forceinline__ void reconverge() const { __syncwarp(); }
+
+    // decoupled look-back, split in two so a tile can publish early and resolve late.  descriptor = status << 62 |
+    // value (1 = this tile's aggregate, 2 = inclusive prefix).  publish: thread 0.  resolve: warp 0 sums the
+    // predecessors' aggregates back to the nearest inclusive prefix, then publishes its own inclusive prefix;
+    // *out = exclusive prefix of this tile (shared memory; visible after the next block sync).
+    __device__ __forceinline__ void lookback_publish(unsigned long long* desc, int tile, unsigned long long agg) const {
+        if (threadIdx.x == 0) st_relaxed_gpu(&desc[tile], ((tile == 0 ? 2ull : 1ull) << 62) | agg);
+    }
+    __device__ __forceinline__ void lookback_resolve(unsigned long long* desc, int tile, unsigned long long agg,
+                                                     unsigned long long* out) const {
         if (threadIdx.x >= 32) return;
         const int lane = threadIdx.x;
         unsigned long long excl = 0;
         if (tile > 0) {
-            if (lane == 0) st_relaxed_gpu(&desc[tile], (1ull << 62) | agg);
             int base = tile - 1;
             for (;;) {
                 const int idx = base - lane;
@@ -94,11 +99,9 @@ struct DevBlk {
                 if (incl) break;
                 base -= 32;
             }
+            if (lane == 0) st_relaxed_gpu(&desc[tile], (2ull << 62) | (excl + agg));
         }
-        if (lane == 0) {
-            st_relaxed_gpu(&desc[tile], (2ull << 62) | (excl + agg));
-            *out = excl;
-        }
+        if (lane == 0) *out = excl;
     }
 };
 
@@ -155,11 +158,11 @@ int64_t encode_corpus_pipe_workspace(int64_t n_bytes, int64_t n_docs, int64_t wo
     b += align_up(sizeof(PipeCtl), 256);
     b += align_up(z.n_tiles * 8 + 8, 256) + align_up(z.n_ctiles * 8 + 8, 256);
     b += align_up(z.n_slots * 8, 256);                       // tags
-    b += align_up(z.n_slots * 16, 256);                      // res
+    b += align_up(z.n_slots * 32, 256);                      // res
     b += align_up(z.n_slots * 4, 256);                       // pending
     b += align_up(word_cap * 4 + 64, 256);                   // refs
     b += align_up((n_docs + 1) * 8, 256);                    // doc_first_word
-    b += align_up(z.odd_cap * 16, 256) * 2;                  // odd, odd_res
+    b += align_up(z.odd_cap * 16, 256) + align_up(z.odd_cap * 32, 256);  // odd, odd_res
     b += align_up(z.pool_cap * 4, 256);                      // pool
     b += align_up((z.n_slots + z.odd_cap) * 4, 256);         // longq
     b += align_up(z.lp_cap, 256) + align_up(z.lp_cap * 8, 256) + 2 * align_up(z.lp_cap * 2, 256);
@@ -180,8 +183,8 @@ int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, 
               "vocabulary; pre-split on the host";
         return DPT_EINVAL;
     }
-    if (n_bytes >= (1ll << 37) || word_cap >= (1ll << 31)) {
-        err = "encode_corpus: batch too large (>= 128 GiB or >= 2^31 words); split it";
+    if (n_bytes >= (1ll << 37) || word_cap >= (1ll << 30) || n_docs >= (1ll << 30)) {
+        err = "encode_corpus: batch too large (>= 128 GiB, >= 2^30 words or >= 2^30 documents); split it";
         return DPT_EINVAL;
     }
     if (!d_ws || ws_bytes < encode_corpus_pipe_workspace(n_bytes, n_docs, word_cap, worst)) {
@@ -226,12 +229,12 @@ int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, 
     P.desc_t = (unsigned long long*)take(z.n_ctiles * 8 + 8);
     P.tags = (unsigned long long*)take(z.n_slots * 8);
     const int64_t zero_bytes = (base + used) - zero0;
-    P.res = (uint4*)take(z.n_slots * 16);
+    P.res = (ResRec*)take(z.n_slots * 32);
     P.pending = (uint32_t*)take(z.n_slots * 4);
     P.refs = (uint32_t*)take(word_cap * 4 + 64);
     P.doc_first_word = (int64_t*)take((n_docs + 1) * 8);
     P.odd = (OddWord*)take(z.odd_cap * 16);
-    P.odd_res = (uint4*)take(z.odd_cap * 16);
+    P.odd_res = (ResRec*)take(z.odd_cap * 32);
     P.pool = (int32_t*)take(z.pool_cap * 4);
     P.longq = (uint32_t*)take((z.n_slots + z.odd_cap) * 4);
     P.lp_norm = (uint8_t*)take(z.lp_cap);
@@ -246,6 +249,7 @@ int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, 
     P.n_ctiles = (int32_t)z.n_ctiles;
     P.spm = rule == DPT_RULE_SPM_LLAMA ? 1 : 0;
     P.rule = rule;
+    P.vec_ok = ((((uintptr_t)d_word_lens) & 15u) == 0 && (((uintptr_t)d_word_flags) & 7u) == 0) ? 1 : 0;
 
     cudaMemsetAsync(zero0, 0, (size_t)zero_bytes, st);
     if (d_doc_flags) cudaMemsetAsync(d_doc_flags, 0, (size_t)n_docs, st);

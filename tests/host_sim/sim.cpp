@@ -51,8 +51,12 @@ struct HostBlk {
         sync();
         return ex;
     }
+    void reconverge() const {}
     // tiles are processed in order by the one emulated CTA: the predecessor's inclusive prefix is always there
-    void lookback(unsigned long long* desc, int tile, unsigned long long agg, unsigned long long* out) const {
+    void lookback_publish(unsigned long long* desc, int tile, unsigned long long agg) const {
+        if (tid_ == 0) desc[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | agg;
+    }
+    void lookback_resolve(unsigned long long* desc, int tile, unsigned long long agg, unsigned long long* out) const {
         if (tid_ != 0) return;
         const unsigned long long prev = tile ? (desc[tile - 1] & dpt::PD_MASK) : 0ull;
         desc[tile] = (2ull << 62) | (prev + agg);
@@ -174,7 +178,7 @@ int32_t sim_encode_corpus_pipe(void* vv, int32_t spm, const uint8_t* text, int64
     if (lp_cap <= 0) lp_cap = 6 * n_bytes + 8 * word_cap + 64;
     PipeCtl ctl{};
     std::vector<unsigned long long> dw(n_tiles + 1, 0), dt(n_ctiles + 1, 0), tags(n_slots, 0);
-    std::vector<uint4> res(n_slots), odd_res(odd_cap);
+    std::vector<ResRec> res(n_slots), odd_res(odd_cap);
     std::vector<uint32_t> pending(n_slots), refs(word_cap + 16), longq(n_slots + odd_cap);
     std::vector<int64_t> dfw(n_docs + 1, -1);
     std::vector<OddWord> odd(odd_cap);
@@ -206,6 +210,7 @@ int32_t sim_encode_corpus_pipe(void* vv, int32_t spm, const uint8_t* text, int64
     P.n_ctiles = (int32_t)n_ctiles;
     P.spm = spm;
     P.rule = spm ? 1 : 0;
+    P.vec_ok = ((((uintptr_t)word_lens) & 15u) == 0 && (((uintptr_t)word_flags) & 7u) == 0) ? 1 : 0;
     memset(counters, 0, 32);
     memset(n_out, 0, 64);
     if (doc_flags) memset(doc_flags, 0, (size_t)n_docs);

@@ -230,7 +230,7 @@ def test_pipeline_code_s2orc_shaped_text(host_sim):
         assert np.array_equal(r2["dto"], r["dto"]) and r2["ctr"].tolist() == r["ctr"].tolist()
     # capacities of the internal lists are reported, never silently exceeded
     r4 = _run_fused(host_sim, h, 1, docs, nthreads=4, n_slots=256, odd_cap=100, pool_cap=10, lp_cap=50)
-    assert r4["nout"][6] > r4["nout"][7] and r4["nout"][4] > r4["nout"][5]
+    assert r4["nout"][6] > r4["nout"][7]
     # capacity: ids beyond ids_cap are dropped, the requirement is still reported
     r3 = _run_fused(host_sim, h, 1, docs, nthreads=4, ids_cap=1000)
     assert r3["nout"][0] == len(r["ids"]) and np.array_equal(r3["ids"], r["ids"][:1000])
@@ -312,4 +312,6 @@ def test_pipeline_code_untokenizable_and_long_tokens(host_sim):
         if not with_marker:         # no bare marker: words like "▁c…" have no segmentation at all
             assert r["ctr"][3] > 0
         assert ((r["wf"] & 4) != 0).sum() > 0     # words past the local-state limit took the long-word kernel
+        rp = _run_fused(host_sim, h, 1, docs, nthreads=4, pool_cap=10)
+        assert rp["nout"][4] > rp["nout"][5]      # words with more than 7 ids need the id pool: reported when too small
         host_sim.sim_vocab_destroy(ctypes.c_void_p(h))
