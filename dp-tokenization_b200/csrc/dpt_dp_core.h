@@ -207,3 +207,101 @@ DPT_HD bool dpt_backward_flat(const DptVocabView& V, const uint8_t* s, int32_t n
     }
     return true;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Compact-state variant for words of at most DPT_FLAT32_MAX normalised bytes (kernel B's per-thread local state):
+// the same ordered key in 32 bits   len << 17 | notreach << 16 | (0xFFFF - M),   back-pointers as 1-byte
+// distances, 14 bytes per position instead of 20.
+// ---------------------------------------------------------------------------------------------------------
+#define DPT_FLAT32_MAX 255
+#define DPT_K32_NONE 0xFFFFFFFFu
+DPT_HD uint32_t dpt_k32_extend(uint32_t kj, uint32_t cl) {
+    const uint32_t lowj = kj & 0xFFFFu, lowe = 0xFFFFu - cl;
+    return (kj & 0xFFFF0000u) + (1u << 17) + (lowj < lowe ? lowj : lowe);
+}
+DPT_HD uint32_t dpt_k32_len(uint32_t k) { return k >> 17; }
+DPT_HD bool dpt_k32_reach(uint32_t k) { return (k & 0x10000u) == 0; }
+DPT_HD uint32_t dpt_k32_longest(uint32_t k) { return 0xFFFFu - (k & 0xFFFFu); }
+
+DPT_HD void dpt_forward_flat32(const DptVocabView& V, const uint8_t* s, int32_t n, uint32_t* best, uint8_t* A, uint8_t* B,
+                               uint32_t* As, uint32_t* Bs) {
+    const bool cp_mode = V.unit_mode != 0;
+    uint32_t u = 0;
+    for (int32_t p = 0; p <= n; ++p) {
+        const bool b = (p == 0 || p == n || !cp_mode) ? true : dpt_is_cp_start(s[p]);
+        best[p] = b ? ((u << 17) | 0x1FFFFu) : DPT_K32_NONE;  // phantom: len = unit index, not reachable
+        if (b) ++u;
+        A[p] = 0;
+        B[p] = 0;
+    }
+    if (n > 0) best[0] = 0xFFFFu;  // origin: len 0, reachable, longest 0
+    const uint32_t* __restrict__ da = V.da;
+    int32_t j = -1, i = 0;
+    uint32_t entry = 0, cl = 0, kj = 0;
+    bool walking = false;
+    for (;;) {
+        if (!walking) {
+            if (++j >= n) break;
+            kj = best[j];
+            entry = DPT_DA_ROOT_ENTRY;
+            i = j;
+            cl = 0;
+            walking = kj != DPT_K32_NONE;
+            if (!walking) continue;
+        }
+        const uint32_t base = entry >> DPT_DA_BASE_SHIFT;
+        const uint32_t c = i < n ? (uint32_t)s[i] : 0x100u;
+        const uint32_t slot = base + (c & 0xFFu);
+        uint32_t e = 0;
+        if (base != 0 && c < 0x100u) {
+#if defined(__CUDA_ARCH__)
+            e = __ldg(da + slot);
+#else
+            e = da[slot];
+#endif
+        }
+        if ((e & DPT_DA_MATCH_MASK) != (DPT_DA_OCCUPIED | c)) {
+            walking = false;
+            continue;
+        }
+        entry = e;
+        ++i;
+        cl += (!cp_mode || dpt_is_cp_start(c)) ? 1u : 0u;
+        if (e & DPT_DA_TERMINAL) {
+            const uint32_t bi = best[i];
+            if (bi != DPT_K32_NONE) {
+                const uint32_t k = dpt_k32_extend(kj, cl);
+                const uint32_t packed = slot | (cl << 22);  // cl <= 255 here, slots < 2^22
+                if ((k >> 16) <= (bi >> 16)) {
+                    A[i] = (uint8_t)(i - j);
+                    As[i] = packed;
+                }
+                if (k <= bi) {
+                    best[i] = k;
+                    B[i] = (uint8_t)(i - j);
+                    Bs[i] = packed;
+                }
+            }
+        }
+    }
+}
+
+DPT_HD bool dpt_backward_flat32(const DptVocabView& V, int32_t n, const uint32_t* best, const uint8_t* A, const uint8_t* B,
+                                const uint32_t* As, const uint32_t* Bs, int32_t* out_ids, int64_t out_cap) {
+    const uint32_t kn = best[n];
+    if (!dpt_k32_reach(kn)) return false;
+    const uint32_t target = dpt_k32_longest(kn);
+    int64_t slot_out = (int64_t)dpt_k32_len(kn) - 1;
+    bool got = false;
+    int32_t i = n;
+    while (i > 0 && slot_out >= 0) {
+        const int32_t d = got ? A[i] : B[i];
+        if (d <= 0 || d > i) break;  // cannot happen on a reachable path; never spin on corrupt state
+        const uint32_t ts = got ? As[i] : Bs[i];
+        if (!got && (ts >> 22) == target) got = true;
+        if (slot_out < out_cap) out_ids[slot_out] = V.slot_id[ts & 0x3FFFFFu];
+        --slot_out;
+        i -= d;
+    }
+    return true;
+}

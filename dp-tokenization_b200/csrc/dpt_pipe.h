@@ -77,7 +77,8 @@ struct OddWord {
 
 struct PipeCtl {  // device-side counters, zeroed by the launcher
     unsigned int ticket_a, ticket_c;
-    unsigned int n_pending, n_odd, n_long, pad;
+    unsigned int n_pending[4];  // distinct words queued for the DP, by length class (keeps a warp's lanes alike)
+    unsigned int n_odd, n_long;
     unsigned long long pool_used, lp_used, n_words, n_untok, n_too_long;
 };
 
@@ -101,7 +102,7 @@ struct PipeParams {
     int64_t* doc_first_word;      // n_docs + 1
     unsigned long long* tags;     // n_slots, zeroed by the launcher
     ResRec* res;                  // n_slots
-    uint32_t* pending;            // n_slots
+    uint32_t* pending;            // 4 length classes x n_slots
     OddWord* odd;                 // odd_cap
     ResRec* odd_res;              // odd_cap
     int32_t* pool;                // pool_cap ids of words with more than 3 tokens
@@ -114,7 +115,7 @@ struct PipeParams {
     unsigned long long* desc_w;   // n_tiles look-back descriptors of kernel A (zeroed)
     unsigned long long* desc_t;   // n_ctiles look-back descriptors of kernel C (zeroed)
     int64_t odd_cap, pool_cap, lp_cap;
-    uint32_t slot_mask;
+    uint32_t slot_mask;           // n_slots - 1 (power of two, <= 2^30)
     int32_t n_tiles, n_ctiles;
     int32_t spm;  // 1: SPM_LLAMA rule; 0: byte-level rules
     int32_t rule;
@@ -136,7 +137,7 @@ struct ASmem {
     uint32_t stage[PA_STAGE];  // refs of this tile, written out coalesced once the word offset is known
     uint32_t scan[40];
     int32_t tile, d_first, n_entries;
-    uint32_t n_pend, pend_base;
+    uint32_t n_pend, n_pend_c[4], cur_c[4], base_c[4];
     unsigned long long base_w;
 };
 
@@ -216,6 +217,14 @@ DPT_HD uint32_t pp_load4(const uint8_t* base4, int64_t off) {
     return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
 #endif
 }
+// 4-bit mask of the bytes of x equal to the bytes of c4 (exact SWAR zero-byte test)
+DPT_HD uint32_t pp_eq4(uint32_t x, uint32_t c4) {
+    const uint32_t z = x ^ c4;
+    uint32_t t = (z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    t = ~(t | z | 0x7F7F7F7Fu);                 // 0x80 in every byte of z that is zero
+    return ((t >> 7) * 0x01020408u) >> 24;      // gather the four flag bits
+}
+DPT_HD int pp_len_class(int len) { return len <= 6 ? 0 : len <= 10 ? 1 : len <= 16 ? 2 : 3; }
 DPT_HD uint32_t pp_tail_mask(int nbytes) { return nbytes >= 4 ? ~0u : ((1u << (8 * nbytes)) - 1u); }
 
 DPT_HD unsigned long long pp_tag(uint32_t hash, int len, int64_t pos) {
@@ -278,24 +287,28 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
         if (tid == 0) {
             S.d_first = (int32_t)pp_lower_bound(P.doc_offs, P.n_docs + 1, g0 < 0 ? 0 : g0);
             S.n_pend = 0;
+            for (int c = 0; c < 4; ++c) S.n_pend_c[c] = S.cur_c[c] = 0;
         }
     }
     blk.sync();
 
     // ---- byte-class masks (one bit per byte), document starts -----------------------------------------------
-    for (int w = tid; w < PA_NW; w += nt) {
-        uint32_t cs = 0, sp = 0, m3 = 0;
-        const uint8_t* t = &S.text[32 * w];
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-            const uint32_t b = t[k];
-            cs |= (uint32_t)((b & 0xC0u) != 0x80u) << k;
-            sp |= (uint32_t)(b == 0x20u) << k;
-            m3 |= (uint32_t)(b == DPT_MARK0 && t[k + 1] == DPT_MARK1 && t[k + 2] == DPT_MARK2) << k;
+    for (int hw = tid; hw < 2 * PA_NW; hw += nt) {  // 16 bytes -> 16 mask bits per thread
+        const uint8_t* t = &S.text[16 * hw];
+        const uint4 x = *reinterpret_cast<const uint4*>(t);
+        uint32_t cs = 0xFFFFu, sp = 0, m3 = 0;
+        sp = pp_eq4(x.x, 0x20202020u) | (pp_eq4(x.y, 0x20202020u) << 4) | (pp_eq4(x.z, 0x20202020u) << 8) |
+             (pp_eq4(x.w, 0x20202020u) << 12);
+        if ((x.x | x.y | x.z | x.w) & 0x80808080u) {  // non-ASCII bytes: continuation bytes, raw U+2581 candidates
+            const uint32_t cont = pp_eq4(x.x & 0xC0C0C0C0u, 0x80808080u) | (pp_eq4(x.y & 0xC0C0C0C0u, 0x80808080u) << 4) |
+                                  (pp_eq4(x.z & 0xC0C0C0C0u, 0x80808080u) << 8) | (pp_eq4(x.w & 0xC0C0C0C0u, 0x80808080u) << 12);
+            cs = ~cont & 0xFFFFu;
+            for (int k = 0; k < 16; ++k)
+                m3 |= (uint32_t)(t[k] == DPT_MARK0 && t[k + 1] == DPT_MARK1 && t[k + 2] == DPT_MARK2) << k;
         }
-        S.mCS[w] = cs;
-        S.mSP[w] = spm ? sp : 0u;
-        S.mM3[w] = spm ? m3 : 0u;
+        reinterpret_cast<uint16_t*>(S.mCS)[hw] = (uint16_t)cs;
+        reinterpret_cast<uint16_t*>(S.mSP)[hw] = (uint16_t)(spm ? sp : 0u);
+        reinterpret_cast<uint16_t*>(S.mM3)[hw] = (uint16_t)(spm ? m3 : 0u);
     }
     for (int64_t k = (int64_t)S.d_first + tid; k <= P.n_docs; k += nt) {
         const int64_t o = P.doc_offs[k];
@@ -333,7 +346,9 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
         S.mWS[w] = ws;
         S.mCX[w] = cx;
         const uint32_t rm = pp_range_mask(w, own_lo, own_hi);
-        S.cnt[w] = (uint32_t)(pp_popc(ws & rm) + (spm ? pp_popc(ds & rm) : 0));
+        // words (and '<s>' words) that start in this tile | document starts up to here << 16
+        S.cnt[w] = (uint32_t)(pp_popc(ws & rm) + (spm ? pp_popc(ds & rm) : 0)) |
+                   ((uint32_t)pp_popc(ds & pp_range_mask(w, 0, own_hi)) << 16);
         amb &= rm;
         while (amb && P.doc_flags) {
             const int r = (w << 5) + pp_ctz(amb);
@@ -351,17 +366,27 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
         uint32_t mine = 0;
         for (int w = w0; w < w1; ++w) mine += S.cnt[w];
         uint32_t total;
-        uint32_t off = blk.exclusive_scan(mine, S.scan, total);
+        const uint32_t ex = blk.exclusive_scan(mine, S.scan, total);
+        uint32_t off = ex & 0xFFFFu;
+        uint32_t dord = ex >> 16;  // document starts in the region before this chunk
+        const bool staged_all = (total & 0xFFFFu) <= (uint32_t)PA_STAGE;
         for (int w = w0; w < w1; ++w) {
             uint32_t bits = S.mWS[w] & pp_range_mask(w, own_lo, own_hi);
+            uint32_t dsw = S.mDS[w] & pp_range_mask(w, 0, own_hi);
             while (bits) {
                 const int r = (w << 5) + pp_ctz(bits);
                 bits &= bits - 1;
-                if (spm && pp_bit(S.mDS, r)) S.wlist[off++] = (uint16_t)(r | 0x8000);
+                if (spm && pp_bit(S.mDS, r)) {
+                    // index of this document = first document of the region + document starts before r
+                    const uint32_t before = dord + (uint32_t)pp_popc(dsw & ((1u << (r & 31)) - 1u));
+                    if (staged_all) S.stage[off] = REF_BOS | (((uint32_t)S.d_first + before) & REF_INDEX);
+                    S.wlist[off++] = (uint16_t)(r | 0x8000);
+                }
                 S.wlist[off++] = (uint16_t)r;
             }
+            dord += (uint32_t)pp_popc(dsw);
         }
-        if (tid == 0) S.n_entries = (int32_t)total;
+        if (tid == 0) S.n_entries = (int32_t)(total & 0xFFFFu);
     }
     blk.sync();
     const int ne = S.n_entries;
@@ -379,6 +404,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
         const int ws = (int)(e & 0x7FFFu);
         uint32_t ref;
         if (e & 0x8000u) {
+            if (staged) continue;  // staged with its document index by the list build
             const int64_t d = pp_lower_bound(P.doc_offs, P.n_docs + 1, g0 + ws);
             ref = REF_BOS | (uint32_t)(d & REF_INDEX);
         } else {
@@ -409,7 +435,9 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
                         t = blk.cas_u64(&P.tags[slot], 0ull, mine);
                         if (t == 0) {  // first occurrence of this word: claim the slot, queue the DP
                             const uint32_t li = blk.atomic_add_ret(&S.n_pend, 1u);
-                            S.pend[li] = slot;
+                            const uint32_t cls = (uint32_t)pp_len_class(len);
+                            S.pend[li] = slot | (cls << 30);
+                            blk.atomic_add(&S.n_pend_c[cls], 1u);
                             ref = slot;
                             done = true;
                             break;
@@ -463,12 +491,15 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
     if (staged)
         for (int k = tid; k < ne; k += nt)
             if (base_w + k < P.word_cap) P.refs[base_w + k] = S.stage[k];
-    if (tid == 0) {
-        S.pend_base = S.n_pend ? blk.atomic_add_ret(&P.ctl->n_pending, S.n_pend) : 0u;
-        if (tile == P.n_tiles - 1) P.ctl->n_words = (unsigned long long)(base_w + ne);
-    }
+    for (int c = tid; c < 4; c += nt)
+        S.base_c[c] = S.n_pend_c[c] ? blk.atomic_add_ret(&P.ctl->n_pending[c], S.n_pend_c[c]) : 0u;
+    if (tid == 0 && tile == P.n_tiles - 1) P.ctl->n_words = (unsigned long long)(base_w + ne);
     blk.sync();
-    for (uint32_t i = tid; i < S.n_pend; i += nt) P.pending[S.pend_base + i] = S.pend[i];
+    for (uint32_t i = tid; i < S.n_pend; i += nt) {
+        const uint32_t v = S.pend[i], cls = v >> 30;
+        const uint32_t r = blk.atomic_add_ret(&S.cur_c[cls], 1u);
+        P.pending[(size_t)cls * ((size_t)P.slot_mask + 1) + S.base_c[cls] + r] = v & REF_INDEX;
+    }
     blk.sync();
 }
 
@@ -558,21 +589,24 @@ struct PbItem {
     bool marker;
     ResRec* out;
 };
-DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint32_t i, uint32_t n_pending) {
+DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint64_t i, const uint32_t* npc) {
     PbItem it;
-    if (i < n_pending) {
-        const uint32_t slot = P.pending[i];
+    const uint64_t p1 = npc[0], p2 = p1 + npc[1], p3 = p2 + npc[2], p4 = p3 + npc[3];
+    if (i < p4) {
+        const uint32_t cls = i < p1 ? 0u : i < p2 ? 1u : i < p3 ? 2u : 3u;
+        const uint64_t idx = i - (cls == 0 ? 0 : cls == 1 ? p1 : cls == 2 ? p2 : p3);
+        const uint32_t slot = P.pending[(size_t)cls * ((size_t)P.slot_mask + 1) + idx];
         const unsigned long long t = P.tags[slot];
         it.pos = pp_tag_pos(t);
         it.end = it.pos + pp_tag_len(t);
         it.marker = P.spm != 0;
         it.out = &P.res[slot];
     } else {
-        const OddWord o = P.odd[i - n_pending];
+        const OddWord o = P.odd[i - p4];
         it.pos = o.pos;
         it.end = o.pos + o.len;
         it.marker = o.virt != 0;
-        it.out = &P.odd_res[i - n_pending];
+        it.out = &P.odd_res[i - p4];
     }
     return it;
 }
@@ -582,9 +616,9 @@ DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint32_t i, uint32_t n_pending) 
 // between them.
 template <class Blk>
 DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P, int64_t gtid, int64_t gthreads) {
-    const uint32_t n_pending = P.ctl->n_pending;
+    const uint32_t npc[4] = {P.ctl->n_pending[0], P.ctl->n_pending[1], P.ctl->n_pending[2], P.ctl->n_pending[3]};
     const uint32_t n_odd = P.ctl->n_odd < (uint32_t)P.odd_cap ? P.ctl->n_odd : (uint32_t)P.odd_cap;
-    const uint64_t total = (uint64_t)n_pending + n_odd;
+    const uint64_t total = (uint64_t)npc[0] + npc[1] + npc[2] + npc[3] + n_odd;
     const uint64_t rounds = (total + (uint64_t)gthreads - 1) / (uint64_t)gthreads;
     for (uint64_t r = 0; r < rounds; ++r) {
         const uint64_t i = r * (uint64_t)gthreads + (uint64_t)gtid;
@@ -594,7 +628,7 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P, int64_t gtid, int64_t 
         uint8_t norm[PB_LOCAL + 8];
         int32_t nlen = 0;
         if (valid) {
-            it = pb_item(P, (uint32_t)i, n_pending);
+            it = pb_item(P, i, npc);
             nlen = pb_normalise(P, it.pos, it.end, it.marker, norm, PB_LOCAL);
             if (nlen < 0) {
                 const uint32_t q = blk.atomic_add_ret(&P.ctl->n_long, 1u);
@@ -603,10 +637,10 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P, int64_t gtid, int64_t 
         }
         blk.reconverge();
         const int32_t n = nlen > 0 ? nlen : 0;
-        uint64_t best[PB_LOCAL + 1];
-        uint16_t A[PB_LOCAL + 1], B[PB_LOCAL + 1];
+        uint32_t best[PB_LOCAL + 1];
+        uint8_t A[PB_LOCAL + 1], B[PB_LOCAL + 1];
         uint32_t As[PB_LOCAL + 1], Bs[PB_LOCAL + 1];
-        dpt_forward_flat(P.V, norm, n, best, A, B, As, Bs);
+        dpt_forward_flat32(P.V, norm, n, best, A, B, As, Bs);
         blk.reconverge();
         if (!valid || nlen < 0) continue;
         ResRec rec;
@@ -616,20 +650,20 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P, int64_t gtid, int64_t 
             *it.out = rec;
             continue;
         }
-        const uint64_t kn = best[n];
-        const uint32_t word_len = dpt_key_len(kn);
-        const bool reach = dpt_key_reach(kn);
+        const uint32_t kn = best[n];
+        const uint32_t word_len = dpt_k32_len(kn);
+        const bool reach = dpt_k32_reach(kn);
         rec.meta = (word_len & 0xFFFFFFu) | (reach ? 0u : RES_UNTOK);
         if (reach) {
             if (word_len <= (uint32_t)RES_INLINE) {
-                dpt_backward_flat(P.V, norm, n, best, A, B, As, Bs, rec.ids, RES_INLINE);
+                dpt_backward_flat32(P.V, n, best, A, B, As, Bs, rec.ids, RES_INLINE);
             } else {
                 const unsigned long long off = blk.atomic_add_u64_ret(&P.ctl->pool_used, (unsigned long long)word_len);
                 rec.meta |= RES_POOLED;
                 rec.ids[0] = (int32_t)(uint32_t)(off & 0xFFFFFFFFull);
                 rec.ids[1] = (int32_t)(uint32_t)(off >> 32);
                 if ((int64_t)(off + word_len) <= P.pool_cap)
-                    dpt_backward_flat(P.V, norm, n, best, A, B, As, Bs, P.pool + off, (int64_t)word_len);
+                    dpt_backward_flat32(P.V, n, best, A, B, As, Bs, P.pool + off, (int64_t)word_len);
             }
         }
         *it.out = rec;
@@ -639,10 +673,10 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P, int64_t gtid, int64_t 
 // long words: one thread each, state in a global scratch pool (13 bytes per normalised position)
 template <class Blk>
 DPT_PIPE_FN void pb_long_thread(Blk& blk, const PipeParams& P, int64_t gtid, int64_t gthreads) {
-    const uint32_t n_pending = P.ctl->n_pending;
+    const uint32_t npc[4] = {P.ctl->n_pending[0], P.ctl->n_pending[1], P.ctl->n_pending[2], P.ctl->n_pending[3]};
     const uint32_t n_long = P.ctl->n_long;
     for (uint64_t k = (uint64_t)gtid; k < n_long; k += (uint64_t)gthreads) {
-        const PbItem it = pb_item(P, P.longq[k], n_pending);
+        const PbItem it = pb_item(P, (uint64_t)P.longq[k], npc);
         const int64_t raw = it.end - it.pos;
         const int64_t need = (P.spm ? 6 * raw + 3 : raw) + 2;
         const unsigned long long off = blk.atomic_add_u64_ret(&P.ctl->lp_used, (unsigned long long)need);

@@ -159,7 +159,7 @@ int64_t encode_corpus_pipe_workspace(int64_t n_bytes, int64_t n_docs, int64_t wo
     b += align_up(z.n_tiles * 8 + 8, 256) + align_up(z.n_ctiles * 8 + 8, 256);
     b += align_up(z.n_slots * 8, 256);                       // tags
     b += align_up(z.n_slots * 32, 256);                      // res
-    b += align_up(z.n_slots * 4, 256);                       // pending
+    b += align_up(z.n_slots * 16, 256);                      // pending (4 length classes)
     b += align_up(word_cap * 4 + 64, 256);                   // refs
     b += align_up((n_docs + 1) * 8, 256);                    // doc_first_word
     b += align_up(z.odd_cap * 16, 256) + align_up(z.odd_cap * 32, 256);  // odd, odd_res
@@ -230,7 +230,7 @@ int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, 
     P.tags = (unsigned long long*)take(z.n_slots * 8);
     const int64_t zero_bytes = (base + used) - zero0;
     P.res = (ResRec*)take(z.n_slots * 32);
-    P.pending = (uint32_t*)take(z.n_slots * 4);
+    P.pending = (uint32_t*)take(z.n_slots * 16);
     P.refs = (uint32_t*)take(word_cap * 4 + 64);
     P.doc_first_word = (int64_t*)take((n_docs + 1) * 8);
     P.odd = (OddWord*)take(z.odd_cap * 16);

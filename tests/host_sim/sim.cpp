@@ -179,7 +179,7 @@ int32_t sim_encode_corpus_pipe(void* vv, int32_t spm, const uint8_t* text, int64
     PipeCtl ctl{};
     std::vector<unsigned long long> dw(n_tiles + 1, 0), dt(n_ctiles + 1, 0), tags(n_slots, 0);
     std::vector<ResRec> res(n_slots), odd_res(odd_cap);
-    std::vector<uint32_t> pending(n_slots), refs(word_cap + 16), longq(n_slots + odd_cap);
+    std::vector<uint32_t> pending(4 * n_slots), refs(word_cap + 16), longq(n_slots + odd_cap);
     std::vector<int64_t> dfw(n_docs + 1, -1);
     std::vector<OddWord> odd(odd_cap);
     std::vector<int32_t> pool(pool_cap);
