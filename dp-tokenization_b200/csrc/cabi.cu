@@ -7,6 +7,7 @@
 #include "../../include/dptok.h"
 #include "kernels.h"
 #include "vocab.h"
+#include "dpt_unicode_tables.h"
 
 namespace {
 thread_local std::string g_err;
@@ -17,7 +18,7 @@ int fail(int code, const std::string& msg) {
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct BlobLayout {
-    int64_t da, slot_id, ph_seed, ph_id, tok_bytes, tok_offs, id_rank, total;
+    int64_t da, slot_id, ph_seed, ph_id, tok_bytes, tok_offs, id_rank, uni1, uni2, total;
 };
 BlobLayout layout_of(const dpt_vocab* v) {
     BlobLayout L{};
@@ -36,6 +37,10 @@ BlobLayout layout_of(const dpt_vocab* v) {
     o = align_up(o + (int64_t)v->tok_offs.size() * 8, 256);
     L.id_rank = o;
     o = align_up(o + (int64_t)v->id_rank.size() * 4, 256);
+    L.uni1 = o;
+    o = align_up(o + DPT_UNI_STAGE1_LEN, 256);
+    L.uni2 = o;
+    o = align_up(o + DPT_UNI_STAGE2_LEN, 256);
     L.total = o;
     return L;
 }
@@ -231,6 +236,8 @@ int dpt_vocab_upload(dpt_vocab* v, int device) {
     cudaMemcpy(d + L.ph_id, v->ph_id.data(), v->ph_id.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(d + L.tok_bytes, v->tok_bytes.data(), v->tok_bytes.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(d + L.tok_offs, v->tok_offs.data(), v->tok_offs.size() * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(d + L.uni1, DPT_UNI_STAGE1, DPT_UNI_STAGE1_LEN, cudaMemcpyHostToDevice);
+    cudaMemcpy(d + L.uni2, DPT_UNI_STAGE2, DPT_UNI_STAGE2_LEN, cudaMemcpyHostToDevice);
     e = cudaMemcpy(d + L.id_rank, v->id_rank.data(), v->id_rank.size() * 4, cudaMemcpyHostToDevice);
     cudaDeviceSynchronize();
     cudaSetDevice(cur);
@@ -249,6 +256,8 @@ int dpt_vocab_upload(dpt_vocab* v, int device) {
     v->d_view.tok_bytes = (const uint8_t*)(d + L.tok_bytes);
     v->d_view.tok_offs = (const int64_t*)(d + L.tok_offs);
     v->d_view.id_rank = (const int32_t*)(d + L.id_rank);
+    v->d_view.uni1 = (const uint8_t*)(d + L.uni1);
+    v->d_view.uni2 = (const uint8_t*)(d + L.uni2);
     return DPT_OK;
 }
 
@@ -390,9 +399,9 @@ int dpt_encode_corpus(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, i
                       int64_t word_cap, int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters,
                       int64_t* d_n_out, void* d_workspace, int64_t workspace_bytes, int32_t worst_case, void* stream) {
     if (int rc = check_ready(v, "dpt_encode_corpus")) return rc;
-    if (rule != DPT_RULE_SPM_LLAMA)
-        return fail(DPT_EINVAL, "dpt_encode_corpus: rule not available on device in this build; pre-split on the host "
-                                "and call dpt_encode_words");
+    if (rule != DPT_RULE_SPM_LLAMA && rule != DPT_RULE_GPT2 && rule != DPT_RULE_LLAMA3)
+        return fail(DPT_EINVAL, "dpt_encode_corpus: rule not available on device in this build (SPM_LLAMA, GPT2, LLAMA3 "
+                                "are); pre-split on the host and call dpt_encode_words");
     std::string err;
     const int rc = dpt::encode_corpus_pipe(v, rule, d_text, n_bytes, d_doc_offs, n_docs, d_ids, ids_cap, d_word_lens,
                                            d_word_flags, word_cap, d_doc_tok_offs, d_doc_flags, d_counters, d_n_out,

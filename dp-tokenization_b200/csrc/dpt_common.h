@@ -37,6 +37,8 @@ struct DptVocabView {
     const uint8_t* tok_bytes;  // id-indexed token strings (decode / verify)
     const int64_t* tok_offs;   // tok_bytes offsets, indexed by dense id rank
     const int32_t* id_rank;    // token id -> dense rank (or -1), length id_space
+    const uint8_t* uni1;       // code-point class table of the byte-level split rules (dpt_split_rules.h)
+    const uint8_t* uni2;
     uint32_t n_slots;
     uint32_t ph_bucket_mask;
     uint32_t ph_slot_mask;

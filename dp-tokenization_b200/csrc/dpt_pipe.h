@@ -24,6 +24,7 @@
 #pragma once
 #include "dpt_common.h"
 #include "dpt_dp_core.h"
+#include "dpt_split_rules.h"
 
 #if defined(__CUDACC__)
 #define DPT_PIPE_FN __device__ __forceinline__
@@ -53,10 +54,12 @@ constexpr int PC_TILE = PC_THREADS * PC_PER;
 
 // one 32-bit ref per word: top two bits 11 = the '<s>' word in front of an SPM_LLAMA document | document index,
 // 10 = index into the odd-word list (not deduplicated), otherwise the word's table slot
+// (byte-level rules have no '<s>' word: bit 29 marks the first word of a document instead)
 constexpr uint32_t REF_BOS = 0xC0000000u;
 constexpr uint32_t REF_ODD = 0x80000000u;
 constexpr uint32_t REF_KIND = 0xC0000000u;
-constexpr uint32_t REF_INDEX = 0x3FFFFFFFu;
+constexpr uint32_t REF_DOCFIRST = 0x20000000u;
+constexpr uint32_t REF_INDEX = 0x1FFFFFFFu;
 constexpr unsigned long long PD_MASK = (1ull << 62) - 1;
 
 constexpr uint32_t RES_UNTOK = 1u << 24;      // result meta: word_len (24 bits) | flags
@@ -131,6 +134,7 @@ struct ASmem {
     uint32_t mCF[PA_NW + 2];  // character starts = CS | DS
     uint32_t mWS[PA_NW + 2];  // word starts
     uint32_t mCX[PA_NW + 2];  // positions that make their word "odd" (solved from the raw text, not deduplicated)
+    uint32_t mSY[PA_NW + 2];  // byte-level rules: synchronisation points of the split scanner
     uint32_t cnt[PA_NW + 2];
     uint16_t wlist[2 * PA_T];  // region index of every word that starts in this tile (| 0x8000: its '<s>' word)
     uint32_t pend[PA_T];       // table slots claimed by this tile
@@ -138,6 +142,8 @@ struct ASmem {
     uint32_t scan[40];
     int32_t tile, d_first, n_entries;
     uint32_t n_pend, n_pend_c[4], cur_c[4], base_c[4];
+    int32_t n_sync, s_first;
+    long long region_doc_end, first_sync_global;
     unsigned long long base_w;
 };
 
@@ -154,6 +160,13 @@ DPT_HD int pp_ctz(uint32_t x) {
     return __ffs((int)x) - 1;
 #else
     return __builtin_ctz(x);
+#endif
+}
+DPT_HD int pp_clz(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return __builtin_clz(x);
 #endif
 }
 DPT_HD int pp_popc(uint32_t x) {
@@ -282,6 +295,8 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
         for (int i = tid; i < 64; i += nt) S.text[PA_R + i] = 0;
         for (int w = tid; w < PA_NW + 2; w += nt) {
             S.mDS[w] = 0;
+            S.mSY[w] = 0;
+            if (!spm) S.mWS[w] = 0;
             if (w >= PA_NW) S.mCS[w] = S.mSP[w] = S.mM3[w] = S.mCF[w] = S.mWS[w] = S.mCX[w] = S.cnt[w] = 0;
         }
         if (tid == 0) {
@@ -307,7 +322,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
                 m3 |= (uint32_t)(t[k] == DPT_MARK0 && t[k + 1] == DPT_MARK1 && t[k + 2] == DPT_MARK2) << k;
         }
         reinterpret_cast<uint16_t*>(S.mCS)[hw] = (uint16_t)cs;
-        reinterpret_cast<uint16_t*>(S.mSP)[hw] = (uint16_t)(spm ? sp : 0u);
+        reinterpret_cast<uint16_t*>(S.mSP)[hw] = (uint16_t)sp;
         reinterpret_cast<uint16_t*>(S.mM3)[hw] = (uint16_t)(spm ? m3 : 0u);
     }
     for (int64_t k = (int64_t)S.d_first + tid; k <= P.n_docs; k += nt) {
@@ -319,42 +334,144 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
     blk.sync();
 
     // ---- boundary rule -> word starts ---------------------------------------------------------------------
-    for (int w = tid; w < PA_NW; w += nt) {
-        const uint32_t ds = S.mDS[w], dsn = S.mDS[w + 1], dsp = w ? S.mDS[w - 1] : 0u;
-        const uint32_t cs = S.mCS[w], csn = (w + 1 < PA_NW) ? S.mCS[w + 1] : ~0u, csp = w ? S.mCS[w - 1] : 0u;
-        // raw U+2581 at p: E2 96 81 inside one document, followed by a character start
-        const uint32_t m3 = S.mM3[w] & ~((ds >> 1) | (dsn << 31)) & ~((ds >> 2) | (dsn << 30)) &
-                            (((cs | ds) >> 3) | ((csn | dsn) << 29));
-        const uint32_t m3p = w ? (S.mM3[w - 1] & ~((dsp >> 1) | (ds << 31)) & ~((dsp >> 2) | (ds << 30)) &
-                                  (((csp | dsp) >> 3) | ((cs | ds) << 29)))
-                               : 0u;
-        const uint32_t sp = S.mSP[w], spp = w ? S.mSP[w - 1] : 0u;
-        const uint32_t mk = sp | m3;
-        const uint32_t pm = (sp << 1) | (spp >> 31) | (m3 << 3) | (m3p >> 29);  // previous character is a marker
-        uint32_t ws, cx, amb = 0;
-        if (spm) {
-            ws = (mk & ~pm) | ds;
-            cx = amb = mk & (pm | ds);  // a marker after a marker: word split depends on the BPE merge order
-            // malformed UTF-8: continuation bytes glued to a space (the character rule swallows them into the
-            // marker) -> solve the word from the raw text with the general character rule
-            cx |= sp & ~(((cs | ds) >> 1) | ((csn | dsn) << 31));
-        } else {
-            ws = ds;  // byte-level rules add their own word starts; documents always split
-            cx = 0;
+    if (!spm) {
+        // Byte-level rules (dpt_split_rules.h).  (1) synchronisation points: document starts and every space whose
+        // next character is a non-whitespace character of the same document.
+        const DptUniView U{P.V.uni1, P.V.uni2};
+        for (int w = tid; w < PA_NW; w += nt) {
+            const uint32_t ds = S.mDS[w];
+            uint32_t sy = ds, sp = S.mSP[w];
+            while (sp) {
+                const int r = (w << 5) + pp_ctz(sp);
+                sp &= sp - 1;
+                if (r > PA_R - 6) continue;  // next character may not be loaded completely: no sync, scanned through
+                const int dend = pp_mask_next(S.mDS, r + 1, PA_R);
+                if (dpt_is_sync_space(U, S.text, r, dend)) sy |= 1u << (r & 31);
+            }
+            S.mSY[w] = sy;
+            S.mCF[w] = S.mCS[w] | ds;
+            S.mCX[w] = 0;
         }
-        S.mCF[w] = cs | ds;
-        S.mWS[w] = ws;
-        S.mCX[w] = cx;
-        const uint32_t rm = pp_range_mask(w, own_lo, own_hi);
-        // words (and '<s>' words) that start in this tile | document starts up to here << 16
-        S.cnt[w] = (uint32_t)(pp_popc(ws & rm) + (spm ? pp_popc(ds & rm) : 0)) |
-                   ((uint32_t)pp_popc(ds & pp_range_mask(w, 0, own_hi)) << 16);
-        amb &= rm;
-        while (amb && P.doc_flags) {
-            const int r = (w << 5) + pp_ctz(amb);
-            amb &= amb - 1;
-            const int64_t d = pp_upper_bound(P.doc_offs, P.n_docs + 1, g0 + r) - 1;
-            if (d >= 0 && d < P.n_docs) P.doc_flags[d] = 1;  // DPT_DF_AMBIGUOUS
+        blk.sync();
+        // (2) the stretch that covers the first byte of the tile starts at the last sync point at or before it
+        if (tid == 0) {
+            int sf = -1;
+            for (int w = own_lo >> 5; w >= 0 && sf < 0; --w) {
+                const uint32_t m = S.mSY[w] & pp_range_mask(w, 0, own_lo + 1);
+                if (m) sf = (w << 5) + 31 - pp_clz(m);
+            }
+            S.s_first = sf;
+            // end of the document that is open at the end of the region
+            int nds = 0;
+            for (int w = 0; w < PA_NW; ++w) nds += pp_popc(S.mDS[w]);
+            const int64_t di = (int64_t)S.d_first + nds;
+            S.region_doc_end = di <= P.n_docs ? P.doc_offs[di] : n;
+            S.first_sync_global = -1;
+            if (sf < 0) {  // no sync point in the look-behind: walk back through the text (rare: a piece-free run > 32 B)
+                const int64_t d = pp_upper_bound(P.doc_offs, P.n_docs + 1, t0) - 1;
+                const int64_t dstart = P.doc_offs[d < 0 ? 0 : d];
+                const int nd = pp_mask_next(S.mDS, own_lo + 1, PA_R);
+                const int64_t dend = nd < PA_R ? g0 + nd : (int64_t)S.region_doc_end;
+                int64_t q = g0 - 1;
+                while (q > dstart && !dpt_is_sync_space(U, P.text, q, dend)) --q;
+                S.first_sync_global = q < dstart ? dstart : q;
+            }
+        }
+        blk.sync();
+        // (3) one thread per stretch between consecutive sync points: sequential regex scanner, marks piece starts
+        {
+            const int sf = S.s_first;
+            const int chunk = (PA_NW + nt - 1) / nt;
+            // stretch list = sync bits in (max(sf,-1) .. PA_R); the first stretch starts at sf (or in global memory)
+            for (int w = tid; w < PA_NW; w += nt) S.cnt[w] = (uint32_t)pp_popc(S.mSY[w] & pp_range_mask(w, sf < 0 ? 0 : sf, PA_R));
+            blk.sync();
+            const int w0 = tid * chunk, w1 = (w0 + chunk) < PA_NW ? (w0 + chunk) : PA_NW;
+            uint32_t mine = 0;
+            for (int w = w0; w < w1; ++w) mine += S.cnt[w];
+            uint32_t total;
+            uint32_t off = blk.exclusive_scan(mine, S.scan, total);
+            for (int w = w0; w < w1; ++w) {
+                uint32_t bits = S.mSY[w] & pp_range_mask(w, sf < 0 ? 0 : sf, PA_R);
+                while (bits) {
+                    S.wlist[off++] = (uint16_t)((w << 5) + pp_ctz(bits));
+                    bits &= bits - 1;
+                }
+            }
+            if (tid == 0) S.n_sync = (int32_t)total;
+            blk.sync();
+            const int ns = S.n_sync;
+            const int extra = sf < 0 ? 1 : 0;  // the stretch that starts before the region
+            for (int k = tid; k < ns + extra; k += nt) {
+                const int idx = k - extra;
+                int64_t p = idx < 0 ? (int64_t)S.first_sync_global : g0 + S.wlist[idx];
+                const int64_t limit = idx + 1 < ns ? g0 + S.wlist[idx + 1] : g0 + PA_R;
+                int64_t dend;
+                if (idx < 0) {
+                    const int nd = pp_mask_next(S.mDS, own_lo + 1, PA_R);
+                    dend = nd < PA_R ? g0 + nd : (int64_t)S.region_doc_end;
+                } else {
+                    const int nd = pp_mask_next(S.mDS, S.wlist[idx] + 1, PA_R);
+                    dend = nd < PA_R ? g0 + nd : (int64_t)S.region_doc_end;
+                }
+                const int64_t stop = limit < dend ? limit : dend;
+                while (p < stop) {
+                    const int64_t r = p - g0;
+                    if (r >= 0) blk.atomic_or(&S.mWS[r >> 5], 1u << (r & 31));
+                    p = dpt_piece_end(P.rule, U, P.text, p, dend);
+                }
+                if (p >= g0 && p < g0 + PA_R && p < n) {  // the piece start the scan landed on (next sync / tile end)
+                    const int64_t r = p - g0;
+                    blk.atomic_or(&S.mWS[r >> 5], 1u << (r & 31));
+                }
+            }
+        }
+        blk.sync();
+        for (int w = tid; w < PA_NW; w += nt) {
+            const uint32_t ds = S.mDS[w];
+            const uint32_t ws = S.mWS[w] | ds;
+            S.mWS[w] = ws;
+            S.cnt[w] = (uint32_t)pp_popc(ws & pp_range_mask(w, own_lo, own_hi)) |
+                       ((uint32_t)pp_popc(ds & pp_range_mask(w, 0, own_hi)) << 16);
+        }
+    } else
+    {
+        for (int w = tid; w < PA_NW; w += nt) {
+            const uint32_t ds = S.mDS[w], dsn = S.mDS[w + 1], dsp = w ? S.mDS[w - 1] : 0u;
+            const uint32_t cs = S.mCS[w], csn = (w + 1 < PA_NW) ? S.mCS[w + 1] : ~0u, csp = w ? S.mCS[w - 1] : 0u;
+            // raw U+2581 at p: E2 96 81 inside one document, followed by a character start
+            const uint32_t m3 = S.mM3[w] & ~((ds >> 1) | (dsn << 31)) & ~((ds >> 2) | (dsn << 30)) &
+                                (((cs | ds) >> 3) | ((csn | dsn) << 29));
+            const uint32_t m3p = w ? (S.mM3[w - 1] & ~((dsp >> 1) | (ds << 31)) & ~((dsp >> 2) | (ds << 30)) &
+                                      (((csp | dsp) >> 3) | ((cs | ds) << 29)))
+                                   : 0u;
+            const uint32_t sp = S.mSP[w], spp = w ? S.mSP[w - 1] : 0u;
+            const uint32_t mk = sp | m3;
+            const uint32_t pm = (sp << 1) | (spp >> 31) | (m3 << 3) | (m3p >> 29);  // previous character is a marker
+            uint32_t ws, cx, amb = 0;
+            if (spm) {
+                ws = (mk & ~pm) | ds;
+                cx = amb = mk & (pm | ds);  // a marker after a marker: word split depends on the BPE merge order
+                // malformed UTF-8: continuation bytes glued to a space (the character rule swallows them into the
+                // marker) -> solve the word from the raw text with the general character rule
+                cx |= sp & ~(((cs | ds) >> 1) | ((csn | dsn) << 31));
+            } else {
+                ws = ds;  // byte-level rules add their own word starts; documents always split
+                cx = 0;
+            }
+            S.mCF[w] = cs | ds;
+            S.mWS[w] = ws;
+            S.mCX[w] = cx;
+            const uint32_t rm = pp_range_mask(w, own_lo, own_hi);
+            // words (and '<s>' words) that start in this tile | document starts up to here << 16
+            S.cnt[w] = (uint32_t)(pp_popc(ws & rm) + (spm ? pp_popc(ds & rm) : 0)) |
+                       ((uint32_t)pp_popc(ds & pp_range_mask(w, 0, own_hi)) << 16);
+            amb &= rm;
+            while (amb && P.doc_flags) {
+                const int r = (w << 5) + pp_ctz(amb);
+                amb &= amb - 1;
+                const int64_t d = pp_upper_bound(P.doc_offs, P.n_docs + 1, g0 + r) - 1;
+                if (d >= 0 && d < P.n_docs) P.doc_flags[d] = 1;  // DPT_DF_AMBIGUOUS
+            }
         }
     }
     blk.sync();
@@ -466,7 +583,16 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
             }
             if (odd) {
                 const int64_t g_ws = g0 + ws;
-                const int64_t g_we = open ? (spm ? pp_spm_word_end_global(P, g_ws, ml, ds) : g_ws + 1) : g0 + we;
+                int64_t g_we = g0 + we;
+                if (open) {
+                    if (spm) {
+                        g_we = pp_spm_word_end_global(P, g_ws, ml, ds);
+                    } else {
+                        const DptUniView U{P.V.uni1, P.V.uni2};
+                        const int64_t d = pp_upper_bound(P.doc_offs, P.n_docs + 1, g_ws);
+                        g_we = dpt_piece_end(P.rule, U, P.text, g_ws, d <= P.n_docs ? P.doc_offs[d] : n);
+                    }
+                }
                 const uint32_t j = blk.atomic_add_ret(&P.ctl->n_odd, 1u);
                 if ((int64_t)j < P.odd_cap) {
                     OddWord o;
@@ -477,20 +603,31 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
                 }
                 ref = REF_ODD | (j & REF_INDEX);
             }
+            if (!spm && ds) ref |= REF_DOCFIRST;
         }
         if (staged) {
             S.stage[k] = ref;
         } else {
             const int64_t gw = (int64_t)S.base_w + k;
             if (gw < P.word_cap) P.refs[gw] = ref;
+            if (!spm && (ref & REF_DOCFIRST)) {
+                const int64_t d = pp_lower_bound(P.doc_offs, P.n_docs + 1, g0 + ws);
+                if (d < P.n_docs) P.doc_first_word[d] = gw;
+            }
         }
     }
     if (staged) blk.lookback_resolve(P.desc_w, tile, (unsigned long long)ne, &S.base_w);  // warp 0, after its probes
     blk.sync();
     const int64_t base_w = (int64_t)S.base_w;
     if (staged)
-        for (int k = tid; k < ne; k += nt)
-            if (base_w + k < P.word_cap) P.refs[base_w + k] = S.stage[k];
+        for (int k = tid; k < ne; k += nt) {
+            const uint32_t ref = S.stage[k];
+            if (base_w + k < P.word_cap) P.refs[base_w + k] = ref;
+            if (!spm && (ref & REF_DOCFIRST)) {
+                const int64_t d = pp_lower_bound(P.doc_offs, P.n_docs + 1, g0 + (int)(S.wlist[k] & 0x7FFFu));
+                if (d < P.n_docs) P.doc_first_word[d] = base_w + k;
+            }
+        }
     for (int c = tid; c < 4; c += nt)
         S.base_c[c] = S.n_pend_c[c] ? blk.atomic_add_ret(&P.ctl->n_pending[c], S.n_pend_c[c]) : 0u;
     if (tid == 0 && tile == P.n_tiles - 1) P.ctl->n_words = (unsigned long long)(base_w + ne);
@@ -717,7 +854,7 @@ DPT_PIPE_FN const ResRec* pc_record_ptr(const PipeParams& P, uint32_t ref) {
         const uint32_t j = ref & REF_INDEX;
         return (int64_t)j < P.odd_cap ? &P.odd_res[j] : nullptr;
     }
-    return &P.res[ref];
+    return &P.res[ref & REF_INDEX];
 }
 DPT_PIPE_FN uint32_t pc_meta(const PipeParams& P, uint32_t ref) {
     if ((ref & REF_KIND) == REF_BOS) return (uint32_t)P.V.bos_len | (P.V.bos_ntok ? 0u : RES_UNTOK);
@@ -788,6 +925,9 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
         const uint32_t kind = ref[k] & REF_KIND;
         if (kind == REF_BOS) {
             const int64_t d = (int64_t)(ref[k] & REF_INDEX);
+            if (d < P.n_docs) P.doc_tok_offs[d] = gt;
+        } else if (ref[k] & REF_DOCFIRST) {  // byte-level rules: first word of a document
+            const int64_t d = pp_lower_bound(P.doc_first_word, P.n_docs, w0 + k);
             if (d < P.n_docs) P.doc_tok_offs[d] = gt;
         }
         if (meta[k] & RES_UNTOK) continue;

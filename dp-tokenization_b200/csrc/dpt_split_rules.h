@@ -1,0 +1,179 @@
+// Byte-level split rules (GPT-2, Llama-3), host/device.
+//
+// The reference obtains its pieces from the tokenizer object: `pre_tokenize_str` (tokenizer_utils.py:157-159) runs
+// the tokenizer's split regex over the text; each piece is then solved by the DP on its own (:165-168).  These
+// functions restate the two regexes SURVEY.md 9.1 lists as sequential scanners with exactly the regex engine's
+// semantics (leftmost match, alternatives tried in order, greedy quantifiers with backtracking):
+//
+//   GPT-2    's|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+
+//   Llama-3  (?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+
+//
+// dpt_piece_end(rule, ...) returns where the piece that starts at p ends.  Code-point classes come from the table
+// generated out of the installed `tokenizers` itself (tools/gen_unicode_tables.py), so \p{L}, \p{N} and \s mean what
+// the reference's regex engine means by them; the case-insensitive contraction letters ('ſ' folds to 's') were
+// probed the same way.  The oracle for these rules is `tokenizers`' pre_tokenize_str (tests).
+//
+// Parallelisation (kernel A): a space followed by a non-whitespace character of the same document is ALWAYS a
+// piece start under both regexes (whitespace alternatives never consume the last whitespace character in front of
+// a non-space; only a piece that starts AT that space can take it as its optional prefix), so those positions and
+// the document starts are synchronisation points: each thread scans the stretch between two consecutive ones.
+#pragma once
+#include "dpt_common.h"
+
+#define DPT_CLS_O 0u
+#define DPT_CLS_L 1u
+#define DPT_CLS_N 2u
+#define DPT_CLS_S 3u
+
+struct DptUniView {
+    const uint8_t* stage1;  // DPT_UNI_STAGE1_LEN block indices (code point >> 8)
+    const uint8_t* stage2;  // 64-byte blocks, 2 bits per code point
+};
+
+DPT_HD uint32_t dpt_cp_class(const DptUniView& U, uint32_t cp) {
+    if (cp >= 0x110000u) return DPT_CLS_O;
+    const uint32_t blk = U.stage1[cp >> 8];
+    return (U.stage2[blk * 64u + ((cp & 255u) >> 2)] >> ((cp & 3u) * 2u)) & 3u;
+}
+
+// Decode the character that starts at text[p] (p < end).  Malformed sequences decode as a 1-byte character of
+// class "other" (the reference only ever sees valid UTF-8: Python str).
+struct DptChar {
+    uint32_t cp;
+    int32_t len;
+    uint32_t cls;
+};
+DPT_HD DptChar dpt_char_at(const DptUniView& U, const uint8_t* text, int64_t p, int64_t end) {
+    DptChar c;
+    const uint32_t b0 = text[p];
+    c.cp = b0;
+    c.len = 1;
+    if (b0 < 0x80u) {
+        // ASCII: letters, digits, the six whitespace characters
+        c.cls = ((b0 | 0x20u) - 'a' < 26u) ? DPT_CLS_L
+                : (b0 - '0' < 10u)        ? DPT_CLS_N
+                : (b0 == 0x20u || (b0 - 9u) < 5u) ? DPT_CLS_S
+                                                  : DPT_CLS_O;
+        return c;
+    }
+    int32_t need = (b0 & 0xE0u) == 0xC0u ? 2 : (b0 & 0xF0u) == 0xE0u ? 3 : (b0 & 0xF8u) == 0xF0u ? 4 : 0;
+    uint32_t cp = need == 2 ? (b0 & 0x1Fu) : need == 3 ? (b0 & 0x0Fu) : (b0 & 0x07u);
+    bool ok = need != 0 && p + need <= end;
+    for (int32_t k = 1; ok && k < need; ++k) {
+        const uint32_t bk = text[p + k];
+        ok = (bk & 0xC0u) == 0x80u;
+        cp = (cp << 6) | (bk & 0x3Fu);
+    }
+    if (!ok) {
+        c.cls = DPT_CLS_O;
+        return c;
+    }
+    c.cp = cp;
+    c.len = need;
+    c.cls = dpt_cp_class(U, cp);
+    return c;
+}
+
+// end of the maximal run of characters of class `cls` starting at p
+DPT_HD int64_t dpt_run_end(const DptUniView& U, const uint8_t* text, int64_t p, int64_t end, uint32_t cls) {
+    while (p < end) {
+        const DptChar c = dpt_char_at(U, text, p, end);
+        if (c.cls != cls) break;
+        p += c.len;
+    }
+    return p;
+}
+
+// Whitespace alternatives shared by both regexes, from a piece start p whose character is whitespace:
+//   [Llama-3 only]  \s*[\r\n]+   through the last newline of the run
+//   \s+(?!\S)       the run without its last character when a non-space follows, the whole run at the end
+//   \s+             a single whitespace character in front of a non-space
+DPT_HD int64_t dpt_ws_piece_end(const DptUniView& U, const uint8_t* text, int64_t p, int64_t end, bool newline_alt) {
+    int64_t e = p, last = p, after_nl = -1;
+    while (e < end) {
+        const DptChar c = dpt_char_at(U, text, e, end);
+        if (c.cls != DPT_CLS_S) break;
+        last = e;
+        e += c.len;
+        if (c.cp == 0x0Au || c.cp == 0x0Du) after_nl = e;
+    }
+    if (newline_alt && after_nl >= 0) return after_nl;
+    if (e >= end) return e;
+    return last > p ? last : e;
+}
+
+DPT_HD int64_t dpt_piece_end_gpt2(const DptUniView& U, const uint8_t* text, int64_t p, int64_t end) {
+    const uint32_t c0 = text[p];
+    if (c0 == '\'' && p + 1 < end) {  // 's|'t|'re|'ve|'m|'ll|'d  (case-sensitive)
+        const uint32_t c1 = text[p + 1];
+        if (c1 == 's' || c1 == 't' || c1 == 'm' || c1 == 'd') return p + 2;
+        if (p + 2 < end) {
+            const uint32_t c2 = text[p + 2];
+            if ((c1 == 'r' && c2 == 'e') || (c1 == 'v' && c2 == 'e') || (c1 == 'l' && c2 == 'l')) return p + 3;
+        }
+    }
+    int64_t q = p;
+    if (c0 == 0x20u && p + 1 < end) q = p + 1;  // the optional space of  ' ?X+'
+    const DptChar c = dpt_char_at(U, text, q, end);
+    if (c.cls != DPT_CLS_S) return dpt_run_end(U, text, q + c.len, end, c.cls);
+    return dpt_ws_piece_end(U, text, p, end, false);
+}
+
+DPT_HD bool dpt_is_newline(uint32_t b) { return b == 0x0Au || b == 0x0Du; }
+
+DPT_HD int64_t dpt_piece_end_llama3(const DptUniView& U, const uint8_t* text, int64_t p, int64_t end) {
+    const uint32_t c0 = text[p];
+    if (c0 == '\'' && p + 1 < end) {  // (?i:'s|'t|'re|'ve|'m|'ll|'d); U+017F (C5 BF) folds to 's'
+        const uint32_t c1 = text[p + 1] | 0x20u;
+        if (text[p + 1] < 0x80u && (c1 == 's' || c1 == 't' || c1 == 'm' || c1 == 'd')) return p + 2;
+        if (p + 2 < end) {
+            const uint32_t r1 = text[p + 1], r2 = text[p + 2];
+            if (r1 == 0xC5u && r2 == 0xBFu) return p + 3;
+            const uint32_t c2 = r2 | 0x20u;
+            if (r1 < 0x80u && r2 < 0x80u && (((c1 == 'r' || c1 == 'v') && c2 == 'e') || (c1 == 'l' && c2 == 'l'))) return p + 3;
+        }
+    }
+    const DptChar k0 = dpt_char_at(U, text, p, end);
+    // [^\r\n\p{L}\p{N}]?\p{L}+
+    if (k0.cls == DPT_CLS_L) return dpt_run_end(U, text, p + k0.len, end, DPT_CLS_L);
+    if (k0.cls != DPT_CLS_N && !dpt_is_newline(k0.cp) && p + k0.len < end) {
+        const DptChar k1 = dpt_char_at(U, text, p + k0.len, end);
+        if (k1.cls == DPT_CLS_L) return dpt_run_end(U, text, p + k0.len + k1.len, end, DPT_CLS_L);
+    }
+    // \p{N}{1,3}
+    if (k0.cls == DPT_CLS_N) {
+        int64_t e = p + k0.len;
+        for (int n = 1; n < 3 && e < end; ++n) {
+            const DptChar c = dpt_char_at(U, text, e, end);
+            if (c.cls != DPT_CLS_N) break;
+            e += c.len;
+        }
+        return e;
+    }
+    // ' ?[^\s\p{L}\p{N}]+[\r\n]*'
+    int64_t q = -1;
+    if (k0.cls == DPT_CLS_O) {
+        q = p;
+    } else if (c0 == 0x20u && p + 1 < end) {
+        const DptChar k1 = dpt_char_at(U, text, p + 1, end);
+        if (k1.cls == DPT_CLS_O) q = p + 1;
+    }
+    if (q >= 0) {
+        int64_t e = dpt_run_end(U, text, q, end, DPT_CLS_O);
+        while (e < end && dpt_is_newline(text[e])) ++e;
+        return e;
+    }
+    // whitespace: \s*[\r\n]+ | \s+(?!\S) | \s+
+    return dpt_ws_piece_end(U, text, p, end, true);
+}
+
+DPT_HD int64_t dpt_piece_end(int32_t rule, const DptUniView& U, const uint8_t* text, int64_t p, int64_t end) {
+    return rule == 3 /* DPT_RULE_LLAMA3 */ ? dpt_piece_end_llama3(U, text, p, end) : dpt_piece_end_gpt2(U, text, p, end);
+}
+
+// Is p (doc_start < p < end, text[p] == ' ') a synchronisation point: a space whose next character is a
+// non-whitespace character of the same document?
+DPT_HD bool dpt_is_sync_space(const DptUniView& U, const uint8_t* text, int64_t p, int64_t end) {
+    if (text[p] != 0x20u || p + 1 >= end) return false;
+    return dpt_char_at(U, text, p + 1, end).cls != DPT_CLS_S;
+}

@@ -183,8 +183,12 @@ int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, 
               "vocabulary; pre-split on the host";
         return DPT_EINVAL;
     }
-    if (n_bytes >= (1ll << 37) || word_cap >= (1ll << 30) || n_docs >= (1ll << 30)) {
-        err = "encode_corpus: batch too large (>= 128 GiB, >= 2^30 words or >= 2^30 documents); split it";
+    if (rule != DPT_RULE_SPM_LLAMA && v->unit_mode != DPT_UNIT_BYTES) {
+        err = "encode_corpus(GPT2/LLAMA3): byte-level rules need a byte-unit vocabulary (DPT_UNIT_BYTES)";
+        return DPT_EINVAL;
+    }
+    if (n_bytes >= (1ll << 37) || word_cap >= (1ll << 29) || n_docs >= (1ll << 29)) {
+        err = "encode_corpus: batch too large (>= 128 GiB, >= 2^29 words or >= 2^29 documents); split it";
         return DPT_EINVAL;
     }
     if (!d_ws || ws_bytes < encode_corpus_pipe_workspace(n_bytes, n_docs, word_cap, worst)) {

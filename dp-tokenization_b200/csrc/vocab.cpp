@@ -4,6 +4,7 @@
 #include "vocab.h"
 
 #include "dpt_dp_core.h"
+#include "dpt_unicode_tables.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -74,6 +75,8 @@ void dpt_vocab::rebuild_host_view() {
     h_view.tok_bytes = tok_bytes.data();
     h_view.tok_offs = tok_offs.data();
     h_view.id_rank = id_rank.data();
+    h_view.uni1 = DPT_UNI_STAGE1;
+    h_view.uni2 = DPT_UNI_STAGE2;
     h_view.n_slots = (uint32_t)da.size();
     h_view.ph_bucket_mask = (uint32_t)ph_seed.size() - 1;
     h_view.ph_slot_mask = (uint32_t)ph_id.size() - 1;

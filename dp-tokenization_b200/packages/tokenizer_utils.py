@@ -187,6 +187,37 @@ def _bytelevel_vocab(tokenizer, HF_CACHE_DIR) -> Dict[str, int]:
     return {token: index for index, token in enumerate(spec["model"]["vocab"])}
 
 
+_LLAMA3_SPLIT = (r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*"
+                 r"|\s*[\r\n]+|\s+(?!\S)|\s+")
+
+
+def _device_split_rule(tokenizer):
+    """DPT_RULE_* of the tokenizer's pre-tokenizer if the device implements exactly that split (GPT-2 ByteLevel regex,
+    Llama-3 Split regex + ByteLevel) and nothing rewrites the text before it; None -> pre_tokenize_str on the host."""
+    try:
+        backend = getattr(tokenizer, "backend_tokenizer", None) or tokenizer._tokenizer
+        spec = json.loads(backend.to_str())
+    except Exception:
+        return None
+    if spec.get("normalizer") is not None:
+        return None
+    pt = spec.get("pre_tokenizer") or {}
+
+    def is_bytelevel(d, use_regex):
+        return (d.get("type") == "ByteLevel" and not d.get("add_prefix_space", True) and
+                bool(d.get("use_regex", True)) == use_regex)
+
+    if is_bytelevel(pt, True):
+        return _cabi.RULE_GPT2
+    if pt.get("type") == "Sequence":
+        steps = pt.get("pretokenizers", [])
+        if (len(steps) == 2 and steps[0].get("type") == "Split" and steps[0].get("behavior") == "Isolated" and
+                not steps[0].get("invert", False) and steps[0].get("pattern", {}).get("Regex") == _LLAMA3_SPLIT and
+                is_bytelevel(steps[1], False)):
+            return _cabi.RULE_LLAMA3
+    return None
+
+
 def dp_tokenize_bloom(bloom_tokenizer, HF_CACHE_DIR, cache_dir=None, device=None):
     vocab_to_index = _BiMap(_bytelevel_vocab(bloom_tokenizer, HF_CACHE_DIR))
     engine = Engine(CompiledVocab.cached(vocab_to_index, "bytelevel", cache_dir), device)
@@ -220,7 +251,14 @@ def dp_tokenize_bloom(bloom_tokenizer, HF_CACHE_DIR, cache_dir=None, device=None
     def dp_tokenize(input_str) -> List[int]:
         return _encode_pieces(pretokenize(input_str))
 
+    device_rule = _device_split_rule(bloom_tokenizer) if bool(single.all()) else None
+
     def _batch(texts: List[str]) -> List[List[int]]:
+        if device_rule is not None and all(texts):
+            # the tokenizer's split regex runs on the GPU (kernel A of the corpus pipeline): no host pre-tokenization
+            text, offs = pack_documents([s.encode("utf-8") for s in texts])
+            res = engine.encode_corpus(torch.from_numpy(text.copy()).to(dev), torch.from_numpy(offs).to(dev), device_rule)
+            return _ids_per_doc(res, len(texts))
         per_doc = [pretokenize(s) for s in texts]
         flat = [p for doc in per_doc for p in doc]
         if not flat:
@@ -239,6 +277,7 @@ def dp_tokenize_bloom(bloom_tokenizer, HF_CACHE_DIR, cache_dir=None, device=None
 
     dp_tokenize.batch = _batch
     dp_tokenize.engine = engine
+    dp_tokenize.device_rule = device_rule
 
     def decode_dp_tokenization(encoding: List[int]):
         return bloom_tokenizer.decode(encoding)

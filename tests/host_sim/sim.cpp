@@ -146,7 +146,8 @@ int64_t sim_spm_normalise(void* vv, const uint8_t* text, int64_t n, const int64_
 // The corpus pipeline's code (dpt_pipe.h): kernel A on `nthreads` host threads emulating one CTA, kernel B as a
 // plain loop over its threads, kernel C on PC_THREADS host threads.  n_slots (power of two, 0 = default) and
 // odd_cap/pool_cap/lp_cap (0 = default) shrink the tables to exercise probe failure and capacity reporting.
-int32_t sim_encode_corpus_pipe(void* vv, int32_t spm, const uint8_t* text, int64_t n_bytes, const int64_t* doc_offs,
+// rule: 1 SPM_LLAMA, 2 GPT2, 3 LLAMA3 (include/dptok.h).
+int32_t sim_encode_corpus_pipe(void* vv, int32_t rule, const uint8_t* text, int64_t n_bytes, const int64_t* doc_offs,
                                int64_t n_docs, int32_t* ids, int64_t ids_cap, int32_t* word_lens, uint8_t* word_flags,
                                int64_t word_cap, int64_t* doc_tok_offs, uint8_t* doc_flags, int64_t* counters,
                                int64_t* n_out, int32_t nthreads, int64_t n_slots, int64_t odd_cap, int64_t pool_cap,
@@ -208,8 +209,8 @@ int32_t sim_encode_corpus_pipe(void* vv, int32_t spm, const uint8_t* text, int64
     P.slot_mask = (uint32_t)(n_slots - 1);
     P.n_tiles = (int32_t)n_tiles;
     P.n_ctiles = (int32_t)n_ctiles;
-    P.spm = spm;
-    P.rule = spm ? 1 : 0;
+    P.spm = rule == 1 ? 1 : 0;  // DPT_RULE_SPM_LLAMA
+    P.rule = rule;
     P.vec_ok = ((((uintptr_t)word_lens) & 15u) == 0 && (((uintptr_t)word_flags) & 7u) == 0) ? 1 : 0;
     memset(counters, 0, 32);
     memset(n_out, 0, 64);

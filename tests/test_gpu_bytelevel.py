@@ -1,0 +1,100 @@
+"""GPU parity of the byte-level split rules (GPT-2, Llama-3) running inside the corpus pipeline, through the C ABI:
+pieces must equal the installed `tokenizers` pre-tokenizer's (tokenizer_utils.py:157-159), ids/lengths the oracle's."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import bytelevel_table, pack, vocab_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    return 0
+
+
+def _to_dev(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a).copy()).to(dev)
+
+
+def _expected(tok, vb, docs):
+    from oracle.c_oracle import COracle
+    u2b = {c: b for b, c in bytelevel_table().items()}
+    words, first = [], []
+    for d in docs:
+        first.append(len(words))
+        for piece, _ in tok.pre_tokenizer.pre_tokenize_str(d.decode()):
+            words.append(bytes(u2b[c] for c in piece))
+    wtext, woffs = pack(words)
+    o_ids, o_lens, o_untok = COracle(vb, 0).encode_words(wtext, woffs)
+    tow = np.concatenate([[0], np.cumsum(np.where(o_untok == 0, o_lens, 0))])
+    return words, o_ids, o_lens, o_untok, tow[first + [len(words)]]
+
+
+def _engine(name, dev):
+    from dptok import assets
+    from dptok.engine import Engine
+    from dptok.vocab import CompiledVocab
+    tok = assets.load_tokenizer(name)
+    v2i = {t: k for k, t in enumerate(assets.load_spec(name)["model"]["vocab"])}
+    return tok, v2i, vocab_bytes(v2i, "bytelevel"), Engine(CompiledVocab.from_token_map(v2i, "bytelevel"), dev)
+
+
+def _check(eng, tok, vb, rule, docs, dev):
+    from dptok.engine import pack_documents
+    text, offs = pack_documents(docs)
+    res = eng.encode_corpus(_to_dev(text, dev), _to_dev(offs, dev), rule)
+    words, o_ids, o_lens, o_untok, o_dto = _expected(tok, vb, docs)
+    assert res.n_words == len(words)
+    assert np.array_equal(res.word_lens.cpu().numpy(), o_lens)
+    assert np.array_equal(res.ids.cpu().numpy(), o_ids)
+    assert np.array_equal(res.doc_tok_offs.cpu().numpy(), o_dto)
+    assert res.counters.cpu().tolist() == [sum(len(d) for d in docs), len(words), len(o_ids), int(o_untok.sum())]
+    return res
+
+
+@pytest.mark.parametrize("name,rule_name", [("gpt2_50k", "RULE_GPT2"), ("llama3_128k", "RULE_LLAMA3")])
+def test_device_split_rules_vs_tokenizers(dev, name, rule_name):
+    """configs[2]/[3]-shaped input: en/de sentence pairs (GPT-2 50k) and long mixed documents incl. Arabic with
+    diacritics (Llama-3 128k), plus a soup of contractions, digit runs, newline runs, tabs, multi-byte whitespace and
+    digits, and pieces far longer than a scan tile."""
+    from dptok import _cabi, synth
+    rule = getattr(_cabi, rule_name)
+    tok, v2i, vb, eng = _engine(name, dev)
+    text, offs = synth.gen_sentence_pairs(3_000_000, seed=0)
+    raw = text.tobytes()
+    res = _check(eng, tok, vb, rule, [raw[offs[k]:offs[k + 1]] for k in range(len(offs) - 1)], dev)
+    assert int(res.counters[3]) == 0
+    text, offs = synth.gen_documents(2_000_000, seed=2, flavour="ar", lexicon=synth.make_arabic_lexicon(20000, seed=2))
+    raw = text.tobytes()
+    _check(eng, tok, vb, rule, [raw[offs[k]:offs[k + 1]] for k in range(len(offs) - 1)], dev)
+    rng = random.Random(7)
+    soup = ["Hello", " ", "  ", "world", "'s", "'S", "'re", "'LL", "'", "''", "12345", "3", "٣٤", "é", "naïve", "日本",
+            "\n", "\n\n", "\t", "\r\n", ".", ",", "!!", "(x)", "—", "…", " ", "　", "ſ", "'ſ", "x", "İ", "ǅ",
+            "قُدَّام", "البيت", "%", "a1b2", " ", "+=", "'t", "'d", "'m", "'ve", "'VE"]
+    for trial in range(6):
+        docs = ["".join(rng.choice(soup) for _ in range(rng.randint(1, 80))).encode()
+                for _ in range(rng.choice([1, 50, 3000]))]
+        _check(eng, tok, vb, rule, docs, dev)
+    big = [("x" * 20000 + " y").encode(), ("7" * 9000 + "a").encode(), (" " * 6000 + "z\n" * 3000).encode()]
+    _check(eng, tok, vb, rule, big, dev)
+
+
+def test_bytelevel_adapter_batch_uses_device_rule(dev):
+    """`dp_tokenize_bloom(...)[0].batch` recognises the tokenizer's split regex and runs it on the GPU; the result
+    equals the per-string path that pre-tokenizes on the host like the reference (tokenizer_utils.py:161-174)."""
+    from dptok import _cabi, assets, synth
+    from packages.tokenizer_utils import dp_tokenize_bloom
+    for name, rule in (("gpt2_3k", _cabi.RULE_GPT2), ("llama3_128k", _cabi.RULE_LLAMA3), ("bloom_8k", None)):
+        tok = assets.load_hf(name)
+        enc, dec = dp_tokenize_bloom(tok, None)
+        assert enc.device_rule == rule
+        docs = synth.sample_text(60_000, seed=5) + ["it's 12345 o'clock\n\nNEW  line\there", "قُدَّام البيت ١٢٣"]
+        out = enc.batch(docs)
+        for d, ids in zip(docs[:40] + docs[-2:], out[:40] + out[-2:]):
+            assert ids == enc(d) and dec(ids) == d

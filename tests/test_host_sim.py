@@ -315,3 +315,63 @@ def test_pipeline_code_untokenizable_and_long_tokens(host_sim):
         rp = _run_fused(host_sim, h, 1, docs, nthreads=4, pool_cap=10)
         assert rp["nout"][4] > rp["nout"][5]      # words with more than 7 ids need the id pool: reported when too small
         host_sim.sim_vocab_destroy(ctypes.c_void_p(h))
+
+
+# ------------------------------------------------------------------------------------------------
+# Byte-level split rules on device (csrc/dpt_split_rules.h inside kernel A) against the installed `tokenizers`
+# pre-tokenizer (the reference's pre_tokenize_str, tokenizer_utils.py:157-159) + the C oracle's DP.
+# ------------------------------------------------------------------------------------------------
+def _bytelevel_expected(tok, vb, docs):
+    from helpers import bytelevel_table
+    from oracle.c_oracle import COracle
+    u2b = {c: b for b, c in bytelevel_table().items()}
+    words, first = [], []
+    for d in docs:
+        first.append(len(words))
+        for piece, _ in tok.pre_tokenizer.pre_tokenize_str(d.decode()):
+            words.append(bytes(u2b[c] for c in piece))
+    wtext, woffs = pack(words)
+    o_ids, o_lens, o_untok = COracle(vb, 0).encode_words(wtext, woffs)
+    tow = np.concatenate([[0], np.cumsum(np.where(o_untok == 0, o_lens, 0))])
+    return words, o_ids, o_lens, o_untok, tow[first + [len(words)]]
+
+
+def _check_bytelevel(host_sim, h, tok, vb, rule, docs, **kw):
+    r = _run_fused(host_sim, h, rule, docs, **kw)
+    words, o_ids, o_lens, o_untok, o_dto = _bytelevel_expected(tok, vb, docs)
+    assert r["nout"][1] == len(words)
+    assert np.array_equal(r["wl"], o_lens)
+    assert np.array_equal(r["ids"], o_ids)
+    assert np.array_equal(r["dto"], o_dto)
+    assert r["ctr"].tolist() == [sum(len(d) for d in docs), len(words), len(o_ids), int(o_untok.sum())]
+    return r
+
+
+def test_pipeline_code_bytelevel_rules(host_sim):
+    """GPT-2 and Llama-3 split regexes as the device scanner: English/German sentence pairs, Arabic with combining
+    marks, contractions (incl. case-insensitive and U+017F), digit groups, newline runs, tabs, ideographic space,
+    multi-byte digits, document boundaries every few bytes."""
+    from dptok import assets, synth
+    rng = random.Random(7)
+    soup = ["Hello", " ", "  ", "world", "'s", "'S", "'re", "'LL", "'", "''", "12345", "3", "٣٤", "é", "naïve", "日本",
+            "\n", "\n\n", "\t", "\r\n", ".", ",", "!!", "(x)", "—", "…", " ", "　", "ſ", "'ſ", "x", "İ", "ǅ",
+            "قُدَّام", "البيت", "%", "a1b2", " ", "+=", "'t", "'d", "'m", "'ve", "'VE"]
+    for name, rule in (("gpt2_3k", 2), ("llama3_128k", 3)):
+        tok = assets.load_tokenizer(name)
+        v2i = {t: k for k, t in enumerate(assets.load_spec(name)["model"]["vocab"])}
+        vb = vocab_bytes(v2i, "bytelevel")
+        h = make_sim_vocab(host_sim, vb, 0)
+        text, offs = synth.gen_sentence_pairs(150_000, seed=1)
+        raw = text.tobytes()
+        _check_bytelevel(host_sim, h, tok, vb, rule, [raw[offs[k]:offs[k + 1]] for k in range(len(offs) - 1)], nthreads=8)
+        text, offs = synth.gen_documents(60_000, seed=2, flavour="ar", lexicon=synth.make_arabic_lexicon(3000, seed=2))
+        raw = text.tobytes()
+        _check_bytelevel(host_sim, h, tok, vb, rule, [raw[offs[k]:offs[k + 1]] for k in range(len(offs) - 1)], nthreads=4)
+        for trial in range(25):
+            docs = ["".join(rng.choice(soup) for _ in range(rng.randint(1, 60))).encode()
+                    for _ in range(rng.choice([1, 5, 60]))]
+            _check_bytelevel(host_sim, h, tok, vb, rule, docs, nthreads=rng.choice([1, 3, 8]), n_slots=rng.choice([0, 64]))
+        # pieces far longer than a tile / its look-behind: one 20 KB letter run, 9 KB of digits, 6 KB of spaces
+        big = [("x" * 20000 + " y").encode(), ("7" * 9000 + "a").encode(), (" " * 6000 + "z\n" * 3000).encode()]
+        _check_bytelevel(host_sim, h, tok, vb, rule, big, nthreads=4)
+        host_sim.sim_vocab_destroy(ctypes.c_void_p(h))
