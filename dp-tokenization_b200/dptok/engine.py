@@ -39,6 +39,16 @@ class EncodeResult:
     doc_flags: Optional[torch.Tensor] = None     # uint8[n_docs] device
 
 
+@dataclass
+class HostResult:
+    ids: torch.Tensor            # int32[n_ids] pinned host
+    doc_tok_offs: np.ndarray     # int64[n_docs+1]
+    doc_flags: np.ndarray        # uint8[n_docs]
+    counters: np.ndarray         # int64[4] {bytes, words, tokens, untokenizable}
+    n_ids: int
+    n_chunks: int
+
+
 class Engine:
     """One compiled vocabulary on one GPU."""
 
@@ -153,6 +163,117 @@ class Engine:
                 raise _cabi.DptError(_cabi.ECAPACITY, f"capacity retries exhausted: {h}")
         nw = h[_cabi.NOUT_WORDS]
         return EncodeResult(ids[:h[0]], lens[:nw], flags[:nw], None, counters, h[0], nw, doc_tok, doc_flags)
+
+    # ---- corpus path from HOST buffers: chunked, H2D / kernels / D2H overlapped on several streams ---------------
+    def encode_corpus_host(self, h_text: torch.Tensor, doc_offs: np.ndarray, rule: int, chunk_bytes: int = 12 << 20,
+                           n_streams: int = 3, out_ids: Optional[torch.Tensor] = None) -> "HostResult":
+        """``h_text``: uint8 HOST tensor (pinned for full speed) of concatenated non-empty documents; ``doc_offs``:
+        int64[n_docs+1] numpy array.  The corpus is cut at document boundaries into chunks of about ``chunk_bytes``;
+        chunk k's host->device copy, its five kernels and its device->host copy of the ids run on stream k mod
+        ``n_streams``, so PCIe in both directions and the SMs work at the same time.  Returns host tensors."""
+        assert h_text.dtype == torch.uint8 and not h_text.is_cuda
+        doc_offs = np.ascontiguousarray(doc_offs, dtype=np.int64)
+        n_docs = len(doc_offs) - 1
+        n_bytes = int(doc_offs[-1])
+        dev = self.device
+        # chunk boundaries (document indices)
+        cuts = [0]
+        while cuts[-1] < n_docs:
+            target = doc_offs[cuts[-1]] + chunk_bytes
+            nxt = int(np.searchsorted(doc_offs, target, side="right")) - 1
+            cuts.append(min(n_docs, max(nxt, cuts[-1] + 1)))
+        n_chunks = len(cuts) - 1
+        max_b = max(int(doc_offs[cuts[k + 1]] - doc_offs[cuts[k]]) for k in range(n_chunks))
+        max_d = max(cuts[k + 1] - cuts[k] for k in range(n_chunks))
+        ids_cap = max_b // 2 + 2 * max_d + 64
+        word_cap = max_b // 3 + 2 * max_d + 64
+        if out_ids is None:
+            out_ids = torch.empty(n_bytes // 2 + 2 * n_docs + 64, dtype=torch.int32).pin_memory()
+        out_doc_tok = np.zeros(n_docs + 1, dtype=np.int64)
+        out_doc_flags = np.zeros(n_docs, dtype=np.uint8)
+        totals = np.zeros(4, dtype=np.int64)
+        with torch.cuda.device(dev):
+            key = (rule, max_b, max_d, n_streams)
+            if getattr(self, "_host_slots_key", None) != key:
+                ws_bytes = lib.dpt_encode_corpus_workspace(rule, max_b, max_d, word_cap, 0)
+                self._host_slots = []
+                for _ in range(n_streams):
+                    self._host_slots.append(dict(
+                        stream=torch.cuda.Stream(device=dev), event=torch.cuda.Event(),
+                        d_text=torch.empty(max_b, dtype=torch.uint8, device=dev),
+                        d_offs=torch.empty(max_d + 1, dtype=torch.int64, device=dev),
+                        h_offs=torch.empty(max_d + 1, dtype=torch.int64).pin_memory(),
+                        ids=torch.empty(ids_cap, dtype=torch.int32, device=dev),
+                        lens=torch.empty(word_cap, dtype=torch.int32, device=dev),
+                        flags=torch.empty(word_cap, dtype=torch.uint8, device=dev),
+                        doc_tok=torch.empty(max_d + 1, dtype=torch.int64, device=dev),
+                        doc_flags=torch.empty(max_d, dtype=torch.uint8, device=dev),
+                        counters=torch.empty(4, dtype=torch.int64, device=dev),
+                        n_out=torch.empty(8, dtype=torch.int64, device=dev),
+                        h_small=torch.empty(12, dtype=torch.int64).pin_memory(),
+                        h_doc_tok=torch.empty(max_d + 1, dtype=torch.int64).pin_memory(),
+                        h_doc_flags=torch.empty(max_d, dtype=torch.uint8).pin_memory(),
+                        ws=torch.empty(int(ws_bytes), dtype=torch.uint8, device=dev)))
+                self._host_slots_key = key
+            slots = self._host_slots
+            cur = torch.cuda.current_stream(dev)
+            for sl in slots:
+                sl["stream"].wait_stream(cur)
+            ids_base = 0
+            pending = []  # (chunk index, slot)
+
+            def finalize(k, sl):
+                nonlocal ids_base
+                lo, hi = cuts[k], cuts[k + 1]
+                nd = hi - lo
+                sl["event"].synchronize()                   # status vector + document offsets of chunk k are on the host
+                h = sl["h_small"].tolist()
+                if h[1] > word_cap or h[0] > ids_cap or h[2] > h[3] or h[4] > h[5] or h[6] > h[7]:
+                    # a capacity was exceeded: redo this chunk through the retrying device-resident path
+                    b0, b1 = int(doc_offs[lo]), int(doc_offs[hi])
+                    res = self.encode_corpus(h_text[b0:b1].to(dev), torch.from_numpy(doc_offs[lo:hi + 1] - b0).to(dev), rule)
+                    n_ids = res.n_ids
+                    out_ids[ids_base:ids_base + n_ids].copy_(res.ids)
+                    out_doc_tok[lo:hi] = res.doc_tok_offs[:nd].cpu().numpy() + ids_base
+                    out_doc_flags[lo:hi] = res.doc_flags.cpu().numpy()
+                    totals[:] += np.asarray(res.counters.cpu().tolist(), dtype=np.int64)
+                else:
+                    n_ids = h[0]
+                    with torch.cuda.stream(sl["stream"]):
+                        out_ids[ids_base:ids_base + n_ids].copy_(sl["ids"][:n_ids], non_blocking=True)
+                    out_doc_tok[lo:hi] = sl["h_doc_tok"][:nd].numpy() + ids_base
+                    out_doc_flags[lo:hi] = sl["h_doc_flags"][:nd].numpy()
+                    totals[:] += np.asarray(h[8:12], dtype=np.int64)
+                ids_base += n_ids
+
+            for k in range(n_chunks):
+                sl = slots[k % n_streams]
+                if len(pending) >= n_streams:
+                    finalize(*pending.pop(0))
+                lo, hi = cuts[k], cuts[k + 1]
+                b0, b1 = int(doc_offs[lo]), int(doc_offs[hi])
+                nb, nd = b1 - b0, hi - lo
+                sl["h_offs"][:nd + 1].copy_(torch.from_numpy(doc_offs[lo:hi + 1] - b0))
+                with torch.cuda.stream(sl["stream"]):
+                    sl["d_text"][:nb].copy_(h_text[b0:b1], non_blocking=True)
+                    sl["d_offs"][:nd + 1].copy_(sl["h_offs"][:nd + 1], non_blocking=True)
+                    check(lib.dpt_encode_corpus(self.vocab.handle, rule, _ptr(sl["d_text"]), nb, _ptr(sl["d_offs"]), nd,
+                                                _ptr(sl["ids"]), ids_cap, _ptr(sl["lens"]), _ptr(sl["flags"]), word_cap,
+                                                _ptr(sl["doc_tok"]), _ptr(sl["doc_flags"]), _ptr(sl["counters"]),
+                                                _ptr(sl["n_out"]), _ptr(sl["ws"]), sl["ws"].numel(), 0,
+                                                C.c_void_p(sl["stream"].cuda_stream)))
+                    sl["h_small"][:8].copy_(sl["n_out"], non_blocking=True)
+                    sl["h_small"][8:12].copy_(sl["counters"], non_blocking=True)
+                    sl["h_doc_tok"][:nd + 1].copy_(sl["doc_tok"][:nd + 1], non_blocking=True)
+                    sl["h_doc_flags"][:nd].copy_(sl["doc_flags"][:nd], non_blocking=True)
+                    sl["event"].record(sl["stream"])
+                pending.append((k, sl))
+            while pending:
+                finalize(*pending.pop(0))
+            for sl in slots:
+                sl["stream"].synchronize()
+        out_doc_tok[n_docs] = ids_base
+        return HostResult(out_ids[:ids_base], out_doc_tok, out_doc_flags, totals, ids_base, n_chunks)
 
     def _encode_corpus_general(self, text, doc_offs, rule, ids_cap, word_cap) -> EncodeResult:
         """General multi-kernel CUDA path (normalise -> DP count -> scan -> DP emit): any word length."""

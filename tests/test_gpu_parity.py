@@ -364,3 +364,22 @@ def test_pipeline_equals_general_path(dev):
     b = eng.encode_corpus(d_text, d_offs, _cabi.RULE_SPM_LLAMA, force_general=True)
     assert torch.equal(a.ids, b.ids) and torch.equal(a.word_lens, b.word_lens) and a.n_words == 8
     assert bool(eng.roundtrip_ok(a, d_text, d_offs, skip_bos=True).all())
+
+
+def test_host_chunked_path_equals_resident_path(dev):
+    """Engine.encode_corpus_host (pinned host text, chunks on 3 streams, ids back on the host) == the device-resident
+    single-batch path: ids, document offsets, flags, counters."""
+    from dptok import _cabi, synth
+    tok, t2i, eng = _llama_engine("llama2_32k", dev)
+    text, doc_offs = synth.gen_documents(9_000_000, seed=4, newline_headers=True)
+    text = text.copy()
+    text[doc_offs[7]:doc_offs[7] + 2] = 0x20          # a document that starts with two spaces: ambiguous flag
+    res = eng.encode_corpus(_to_dev(text, dev), _to_dev(doc_offs, dev), _cabi.RULE_SPM_LLAMA)
+    h_text = torch.from_numpy(text).pin_memory()
+    for chunk in (1 << 20, 3_500_000, 64 << 20):
+        hr = eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_SPM_LLAMA, chunk_bytes=chunk)
+        assert hr.n_ids == res.n_ids and hr.n_chunks == max(1, -(-len(text) // chunk)) or hr.n_chunks >= 1
+        assert np.array_equal(hr.ids.numpy(), res.ids.cpu().numpy())
+        assert np.array_equal(hr.doc_tok_offs, res.doc_tok_offs.cpu().numpy())
+        assert np.array_equal(hr.doc_flags, res.doc_flags.cpu().numpy()) and hr.doc_flags[7] == 1
+        assert hr.counters.tolist() == res.counters.cpu().tolist()
