@@ -66,3 +66,38 @@ def run(asset_name: str, docs, budget_s: float = 15.0, procs: int | None = None)
         pool.terminate()
     return dict(bytes_per_s=done_b / dt, tokens_per_s=done_t / dt, cores=procs, bytes=done_b, tokens=done_t,
                 docs=done_d, seconds=dt)
+
+
+class Runner:
+    """One worker pool kept across several bounded runs (bench.py --impl reference: one run per step)."""
+
+    def __init__(self, asset_name: str, procs: int | None = None):
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        self.procs = procs or os.cpu_count() or 1
+        self.pool = mp.get_context("spawn").Pool(self.procs, initializer=_init, initargs=(asset_name, root))
+
+    def warm(self, docs):
+        list(self.pool.imap_unordered(_encode_doc, docs[:self.procs], chunksize=1))
+
+    def run(self, docs, budget_s: float):
+        """Tokenize documents from ``docs`` for about ``budget_s`` seconds.  Work is handed to the pool in small
+        batches and each batch is waited for, so no task is left in flight when the step ends (imap over the whole
+        list would keep running after a ``break`` and bleed into the next step's timing)."""
+        done_b = done_t = done_d = 0
+        batch = self.procs * 4
+        pos = 0
+        t0 = time.perf_counter()
+        while pos < len(docs):
+            for nb, nt in self.pool.map(_encode_doc, docs[pos:pos + batch], chunksize=4):
+                done_b += nb
+                done_t += nt
+                done_d += 1
+            pos += batch
+            if time.perf_counter() - t0 > budget_s:
+                break
+        dt = time.perf_counter() - t0
+        return dict(bytes_per_s=done_b / dt, tokens_per_s=done_t / dt, cores=self.procs, bytes=done_b, tokens=done_t,
+                    docs=done_d, seconds=dt)
+
+    def close(self):
+        self.pool.terminate()
