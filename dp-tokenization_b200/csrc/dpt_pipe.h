@@ -230,6 +230,34 @@ DPT_HD uint32_t pp_load4(const uint8_t* base4, int64_t off) {
     return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
 #endif
 }
+// the first min(len,16) bytes at byte offset `off` of a 4-byte-aligned buffer as four little-endian words,
+// zero-padded: five aligned loads + four funnel shifts, no loop
+DPT_HD void pp_load16(const uint8_t* base4, int64_t off, int len, uint32_t v[4]) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(base4 + (off & ~(int64_t)3));
+    const uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3], a4 = w[4];
+    const uint32_t sh = (uint32_t)(off & 3) * 8u;
+#if defined(__CUDA_ARCH__)
+    v[0] = __funnelshift_r(a0, a1, sh);
+    v[1] = __funnelshift_r(a1, a2, sh);
+    v[2] = __funnelshift_r(a2, a3, sh);
+    v[3] = __funnelshift_r(a3, a4, sh);
+#else
+    v[0] = sh ? (a0 >> sh) | (a1 << (32u - sh)) : a0;
+    v[1] = sh ? (a1 >> sh) | (a2 << (32u - sh)) : a1;
+    v[2] = sh ? (a2 >> sh) | (a3 << (32u - sh)) : a2;
+    v[3] = sh ? (a3 >> sh) | (a4 << (32u - sh)) : a3;
+#endif
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int rem = len - 4 * k;
+        v[k] &= rem >= 4 ? ~0u : rem <= 0 ? 0u : ((1u << (8 * rem)) - 1u);
+    }
+}
+DPT_HD uint32_t pp_hash_step(uint32_t h, uint32_t v) {
+    h = (h ^ v) * 0x9E3779B1u;
+    return h ^ (h >> 15);
+}
+
 // 4-bit mask of the bytes of x equal to the bytes of c4 (exact SWAR zero-byte test)
 DPT_HD uint32_t pp_eq4(uint32_t x, uint32_t c4) {
     const uint32_t z = x ^ c4;
@@ -533,13 +561,13 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
             bool odd = open || len > PA_MAXLEN || len < 0 || pp_any_in_range(S.mCX, ws, we);
             ref = 0;
             if (!odd) {
-                // hash the body 4 bytes at a time (tail zero-padded)
+                // hash the body: the first 16 bytes straight-line (four zero-padded words, no loop: 19 of 20 words
+                // end here with every lane active), longer bodies 4 more bytes per step
+                uint32_t wv[4];
+                pp_load16(S.text, b, len, wv);
                 uint32_t h = 0x811C9DC5u ^ (uint32_t)len;
-                for (int q = 0; q < len; q += 4) {
-                    const uint32_t v = pp_load4(S.text, b + q) & pp_tail_mask(len - q);
-                    h = (h ^ v) * 0x9E3779B1u;
-                    h ^= h >> 15;
-                }
+                h = pp_hash_step(pp_hash_step(pp_hash_step(pp_hash_step(h, wv[0]), wv[1]), wv[2]), wv[3]);
+                for (int q = 16; q < len; q += 4) h = pp_hash_step(h, pp_load4(S.text, b + q) & pp_tail_mask(len - q));
                 h *= 0x2C1B3C6Du;
                 h ^= h >> 13;
                 const int64_t g_b = g0 + b;
@@ -562,15 +590,17 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
                     }
                     if ((t >> 38) == (mine >> 38)) {  // same hash bits and length: verify against the corpus text
                         const int64_t rp = pp_tag_pos(t);
-                        bool same = true;
-                        if (rp + len + 8 <= n) {  // 4 bytes at a time off the 4-byte-aligned corpus base
+                        bool same;
+                        if (rp + len + 24 <= n) {  // words straight off the 4-byte-aligned corpus base
                             const uint8_t* base4 = P.text - ((uintptr_t)P.text & 3u);
                             const int64_t ro = rp + (int64_t)((uintptr_t)P.text & 3u);
-                            for (int q = 0; q < len && same; q += 4) {
-                                const uint32_t m = pp_tail_mask(len - q);
-                                same = ((pp_load4(base4, ro + q) ^ pp_load4(S.text, b + q)) & m) == 0;
-                            }
+                            uint32_t rv[4];
+                            pp_load16(base4, ro, len, rv);
+                            same = ((rv[0] ^ wv[0]) | (rv[1] ^ wv[1]) | (rv[2] ^ wv[2]) | (rv[3] ^ wv[3])) == 0;
+                            for (int q = 16; q < len && same; q += 4)
+                                same = ((pp_load4(base4, ro + q) ^ pp_load4(S.text, b + q)) & pp_tail_mask(len - q)) == 0;
                         } else {
+                            same = true;
                             for (int q = 0; q < len && same; ++q) same = P.text[rp + q] == S.text[b + q];
                         }
                         if (same) {

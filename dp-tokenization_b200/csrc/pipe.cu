@@ -81,23 +81,38 @@ struct DevBlk {
         const int lane = threadIdx.x;
         unsigned long long excl = 0;
         if (tile > 0) {
+            // every lane inspects 4 consecutive predecessors per round (128 per warp round): a tile typically has a
+            // few hundred predecessors in flight, and each round costs an L2 round trip
             int base = tile - 1;
             for (;;) {
-                const int idx = base - lane;
-                unsigned long long v = 2ull << 62;  // in front of tile 0: inclusive prefix 0
-                if (idx >= 0) {
-                    do {
-                        v = ld_relaxed_gpu(&desc[idx]);
-                    } while ((v >> 62) == 0);
+                unsigned long long v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {  // four independent loads in flight
+                    const int idx = base - (lane * 4 + j);
+                    v[j] = idx >= 0 ? ld_relaxed_gpu(&desc[idx]) : (2ull << 62);  // in front of tile 0: inclusive prefix 0
                 }
-                const unsigned incl = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {  // older tiles publish earlier, so every one of these becomes non-zero
+                    const int idx = base - (lane * 4 + j);
+                    while ((v[j] >> 62) == 0) v[j] = ld_relaxed_gpu(&desc[idx]);
+                }
+                unsigned long long c = 0;
+                bool found = false;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (!found) {
+                        c += v[j] & PD_MASK;
+                        found = (v[j] >> 62) == 2;
+                    }
+                }
+                const unsigned incl = __ballot_sync(0xffffffffu, found);
                 const int first = incl ? __ffs((int)incl) - 1 : 31;
-                unsigned long long c = lane <= first ? (v & PD_MASK) : 0ull;
+                if (lane > first) c = 0;
 #pragma unroll
                 for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
                 excl += c;
                 if (incl) break;
-                base -= 32;
+                base -= 128;
             }
             if (lane == 0) st_relaxed_gpu(&desc[tile], (2ull << 62) | (excl + agg));
         }
