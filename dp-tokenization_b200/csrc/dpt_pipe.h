@@ -49,7 +49,7 @@ constexpr int PB_THREADS = 128;
 constexpr int PB_LOCAL = 72;                  // normalised bytes solved with per-thread local state in kernel B
 constexpr int PC_THREADS = 256;
 constexpr int PC_PER = 8;                     // words per thread in kernel C
-constexpr int PA_STAGE = 1024;                // refs staged in shared memory per tile (more -> direct writes)
+constexpr int PA_WIN = 1024;                  // words of a tile handled per pass (a 4 KB tile holds ~520; more -> more passes)
 constexpr int PC_TILE = PC_THREADS * PC_PER;
 
 // one 32-bit ref per word: top two bits 11 = the '<s>' word in front of an SPM_LLAMA document | document index,
@@ -125,7 +125,11 @@ struct PipeParams {
     int32_t vec_ok;  // word_lens / word_flags are aligned for 16- / 8-byte stores
 };
 
-struct ASmem {
+template <bool kSpm>
+struct ASmemT {
+    // list capacity: SPM needs one window of entries; byte-level rules also list their synchronisation points
+    // (up to one per byte of the region)
+    static constexpr int WL_CAP = kSpm ? PA_WIN : PA_R + 32;
     alignas(16) uint8_t text[PA_R + 64];
     uint32_t mDS[PA_NW + 2];  // document starts (and the end-of-text sentinel)
     uint32_t mCS[PA_NW + 2];  // code-point start bytes
@@ -136,9 +140,9 @@ struct ASmem {
     uint32_t mCX[PA_NW + 2];  // positions that make their word "odd" (solved from the raw text, not deduplicated)
     uint32_t mSY[PA_NW + 2];  // byte-level rules: synchronisation points of the split scanner
     uint32_t cnt[PA_NW + 2];
-    uint16_t wlist[2 * PA_T];  // region index of every word that starts in this tile (| 0x8000: its '<s>' word)
-    uint32_t pend[PA_T];       // table slots claimed by this tile
-    uint32_t stage[PA_STAGE];  // refs of this tile, written out coalesced once the word offset is known
+    uint16_t wlist[WL_CAP];   // region index of the words of the current window (| 0x8000: a document's '<s>' word)
+    uint32_t pend[PA_WIN];    // table slots claimed in the current window
+    uint32_t stage[PA_WIN];   // refs of the current window, written out coalesced once the word offset is known
     uint32_t scan[40];
     int32_t tile, d_first, n_entries;
     uint32_t n_pend, n_pend_c[4], cur_c[4], base_c[4];
@@ -296,15 +300,15 @@ DPT_PIPE_FN int64_t pp_spm_word_end_global(const PipeParams& P, int64_t g_ws, in
 // =========================================================================================================
 // Kernel A: scan + dedup
 // =========================================================================================================
-template <class Blk>
-DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int tile) {
+template <class Blk, bool kSpm>
+DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, const int tile) {
     const int tid = blk.tid(), nt = blk.nthreads();
     const int64_t t0 = (int64_t)tile * PA_T;
     const int64_t g0 = t0 - PA_HALO;  // global offset of region index 0
     const int64_t n = P.n_bytes;
     const int tvalid = (int)((n - t0) < PA_T ? (n - t0) : PA_T);
     const int own_lo = PA_HALO, own_hi = PA_HALO + tvalid;
-    const bool spm = P.spm != 0;
+    constexpr bool spm = kSpm;
 
     // ---- load: coalesced 16-byte loads of the region ------------------------------------------------------
     {
@@ -504,174 +508,185 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmem& S, const int 
     }
     blk.sync();
 
-    // ---- word list (corpus order) ---------------------------------------------------------------------------
+    // ---- entries (words and '<s>' words) that start in this tile, in corpus order ---------------------------------
+    const int chunk = (PA_NW + nt - 1) / nt;
+    const int w0 = tid * chunk, w1 = (w0 + chunk) < PA_NW ? (w0 + chunk) : PA_NW;
+    uint32_t my_off, my_dord;
+    int ne;
     {
-        const int chunk = (PA_NW + nt - 1) / nt;
-        const int w0 = tid * chunk, w1 = (w0 + chunk) < PA_NW ? (w0 + chunk) : PA_NW;
         uint32_t mine = 0;
         for (int w = w0; w < w1; ++w) mine += S.cnt[w];
         uint32_t total;
         const uint32_t ex = blk.exclusive_scan(mine, S.scan, total);
-        uint32_t off = ex & 0xFFFFu;
-        uint32_t dord = ex >> 16;  // document starts in the region before this chunk
-        const bool staged_all = (total & 0xFFFFu) <= (uint32_t)PA_STAGE;
-        for (int w = w0; w < w1; ++w) {
-            uint32_t bits = S.mWS[w] & pp_range_mask(w, own_lo, own_hi);
-            uint32_t dsw = S.mDS[w] & pp_range_mask(w, 0, own_hi);
-            while (bits) {
-                const int r = (w << 5) + pp_ctz(bits);
-                bits &= bits - 1;
-                if (spm && pp_bit(S.mDS, r)) {
-                    // index of this document = first document of the region + document starts before r
-                    const uint32_t before = dord + (uint32_t)pp_popc(dsw & ((1u << (r & 31)) - 1u));
-                    if (staged_all) S.stage[off] = REF_BOS | (((uint32_t)S.d_first + before) & REF_INDEX);
-                    S.wlist[off++] = (uint16_t)(r | 0x8000);
-                }
-                S.wlist[off++] = (uint16_t)r;
-            }
-            dord += (uint32_t)pp_popc(dsw);
-        }
-        if (tid == 0) S.n_entries = (int32_t)(total & 0xFFFFu);
+        my_off = ex & 0xFFFFu;
+        my_dord = ex >> 16;  // document starts in the region before this thread's chunk
+        ne = (int)(total & 0xFFFFu);
     }
-    blk.sync();
-    const int ne = S.n_entries;
-    // publish this tile's word count at once (successors never wait long); resolve the prefix as late as possible
+    // publish this tile's word count at once (successors never wait long); resolve the prefix as late as possible:
+    // after the probes when the tile fits one window (the normal case)
     blk.lookback_publish(P.desc_w, tile, (unsigned long long)ne);
-    const bool staged = ne <= PA_STAGE;
-    if (!staged) {
+    const bool single = ne <= PA_WIN;
+    if (!single) {
         blk.lookback_resolve(P.desc_w, tile, (unsigned long long)ne, &S.base_w);
         blk.sync();
     }
+    int lo = 0;
+    do {
+        const int hi = (lo + PA_WIN) < ne ? (lo + PA_WIN) : ne;
+        const int nwin = hi - lo;
+        // ---- list of this window ------------------------------------------------------------------------------
+        {
+            uint32_t off = my_off, dord = my_dord;
+            for (int w = w0; w < w1; ++w) {
+                uint32_t bits = S.mWS[w] & pp_range_mask(w, own_lo, own_hi);
+                const uint32_t dsw = S.mDS[w] & pp_range_mask(w, 0, own_hi);
+                while (bits) {
+                    const int r = (w << 5) + pp_ctz(bits);
+                    bits &= bits - 1;
+                    if (spm && pp_bit(S.mDS, r)) {
+                        if ((int)off >= lo && (int)off < hi) {
+                            // index of this document = first document of the region + document starts before r
+                            const uint32_t before = dord + (uint32_t)pp_popc(dsw & ((1u << (r & 31)) - 1u));
+                            S.stage[off - lo] = REF_BOS | (((uint32_t)S.d_first + before) & REF_INDEX);
+                            S.wlist[off - lo] = (uint16_t)(r | 0x8000);
+                        }
+                        ++off;
+                    }
+                    if ((int)off >= lo && (int)off < hi) S.wlist[off - lo] = (uint16_t)r;
+                    ++off;
+                }
+                dord += (uint32_t)pp_popc(dsw);
+            }
+        }
+        blk.sync();
 
-    // ---- one table probe per word ------------------------------------------------------------------------------
-    for (int k = tid; k < ne; k += nt) {
-        const uint32_t e = S.wlist[k];
-        const int ws = (int)(e & 0x7FFFu);
-        uint32_t ref;
-        if (e & 0x8000u) {
-            if (staged) continue;  // staged with its document index by the list build
-            const int64_t d = pp_lower_bound(P.doc_offs, P.n_docs + 1, g0 + ws);
-            ref = REF_BOS | (uint32_t)(d & REF_INDEX);
-        } else {
-            const bool ds = pp_bit(S.mDS, ws);
-            const int we = pp_mask_next(S.mWS, ws + 1, PA_R);
-            const int ml = !spm ? 0 : ds ? 0 : (S.text[ws] == 0x20u ? 1 : 3);
-            const int b = ws + ml, len = we - b;
-            const bool open = we >= PA_R;
-            bool odd = open || len > PA_MAXLEN || len < 0 || pp_any_in_range(S.mCX, ws, we);
-            ref = 0;
-            if (!odd) {
-                // hash the body: the first 16 bytes straight-line (four zero-padded words, no loop: 19 of 20 words
-                // end here with every lane active), longer bodies 4 more bytes per step
-                uint32_t wv[4];
-                pp_load16(S.text, b, len, wv);
-                uint32_t h = 0x811C9DC5u ^ (uint32_t)len;
-                h = pp_hash_step(pp_hash_step(pp_hash_step(pp_hash_step(h, wv[0]), wv[1]), wv[2]), wv[3]);
-                for (int q = 16; q < len; q += 4) h = pp_hash_step(h, pp_load4(S.text, b + q) & pp_tail_mask(len - q));
-                h *= 0x2C1B3C6Du;
-                h ^= h >> 13;
-                const int64_t g_b = g0 + b;
-                const unsigned long long mine = pp_tag(h >> 12, len, g_b);
-                uint32_t slot = h & P.slot_mask;
-                bool done = false;
-                for (int probe = 0; probe < PA_PROBES && !done; ++probe, slot = (slot + 1) & P.slot_mask) {
-                    unsigned long long t = blk.load_relaxed(&P.tags[slot]);
-                    if (t == 0) {
-                        t = blk.cas_u64(&P.tags[slot], 0ull, mine);
-                        if (t == 0) {  // first occurrence of this word: claim the slot, queue the DP
-                            const uint32_t li = blk.atomic_add_ret(&S.n_pend, 1u);
-                            const uint32_t cls = (uint32_t)pp_len_class(len);
-                            S.pend[li] = slot | (cls << 30);
-                            blk.atomic_add(&S.n_pend_c[cls], 1u);
-                            ref = slot;
-                            done = true;
-                            break;
+        // ---- one table probe per word ----------------------------------------------------------------------------
+            for (int k = tid; k < nwin; k += nt) {
+            const uint32_t e = S.wlist[k];
+            const int ws = (int)(e & 0x7FFFu);
+            uint32_t ref;
+            if (e & 0x8000u) {
+                continue;  // staged with its document index by the list build
+            } else {
+                const bool ds = pp_bit(S.mDS, ws);
+                const int we = pp_mask_next(S.mWS, ws + 1, PA_R);
+                const int ml = !spm ? 0 : ds ? 0 : (S.text[ws] == 0x20u ? 1 : 3);
+                const int b = ws + ml, len = we - b;
+                const bool open = we >= PA_R;
+                bool odd = open || len > PA_MAXLEN || len < 0 || pp_any_in_range(S.mCX, ws, we);
+                ref = 0;
+                if (!odd) {
+                    // hash the body: the first 16 bytes straight-line (four zero-padded words, no loop: 19 of 20 words
+                    // end here with every lane active), longer bodies 4 more bytes per step
+                    uint32_t wv[4];
+                    pp_load16(S.text, b, len, wv);
+                    uint32_t h = 0x811C9DC5u ^ (uint32_t)len;
+                    h = pp_hash_step(pp_hash_step(pp_hash_step(pp_hash_step(h, wv[0]), wv[1]), wv[2]), wv[3]);
+                    for (int q = 16; q < len; q += 4) h = pp_hash_step(h, pp_load4(S.text, b + q) & pp_tail_mask(len - q));
+                    h *= 0x2C1B3C6Du;
+                    h ^= h >> 13;
+                    const int64_t g_b = g0 + b;
+                    const unsigned long long mine = pp_tag(h >> 12, len, g_b);
+                    uint32_t slot = h & P.slot_mask;
+                    bool done = false;
+                    for (int probe = 0; probe < PA_PROBES && !done; ++probe, slot = (slot + 1) & P.slot_mask) {
+                        unsigned long long t = blk.load_relaxed(&P.tags[slot]);
+                        if (t == 0) {
+                            t = blk.cas_u64(&P.tags[slot], 0ull, mine);
+                            if (t == 0) {  // first occurrence of this word: claim the slot, queue the DP
+                                const uint32_t li = blk.atomic_add_ret(&S.n_pend, 1u);
+                                const uint32_t cls = (uint32_t)pp_len_class(len);
+                                S.pend[li] = slot | (cls << 30);
+                                blk.atomic_add(&S.n_pend_c[cls], 1u);
+                                ref = slot;
+                                done = true;
+                                break;
+                            }
+                        }
+                        if ((t >> 38) == (mine >> 38)) {  // same hash bits and length: verify against the corpus text
+                            const int64_t rp = pp_tag_pos(t);
+                            bool same;
+                            if (rp + len + 24 <= n) {  // words straight off the 4-byte-aligned corpus base
+                                const uint8_t* base4 = P.text - ((uintptr_t)P.text & 3u);
+                                const int64_t ro = rp + (int64_t)((uintptr_t)P.text & 3u);
+                                uint32_t rv[4];
+                                pp_load16(base4, ro, len, rv);
+                                same = ((rv[0] ^ wv[0]) | (rv[1] ^ wv[1]) | (rv[2] ^ wv[2]) | (rv[3] ^ wv[3])) == 0;
+                                for (int q = 16; q < len && same; q += 4)
+                                    same = ((pp_load4(base4, ro + q) ^ pp_load4(S.text, b + q)) & pp_tail_mask(len - q)) == 0;
+                            } else {
+                                same = true;
+                                for (int q = 0; q < len && same; ++q) same = P.text[rp + q] == S.text[b + q];
+                            }
+                            if (same) {
+                                ref = slot;
+                                done = true;
+                            }
                         }
                     }
-                    if ((t >> 38) == (mine >> 38)) {  // same hash bits and length: verify against the corpus text
-                        const int64_t rp = pp_tag_pos(t);
-                        bool same;
-                        if (rp + len + 24 <= n) {  // words straight off the 4-byte-aligned corpus base
-                            const uint8_t* base4 = P.text - ((uintptr_t)P.text & 3u);
-                            const int64_t ro = rp + (int64_t)((uintptr_t)P.text & 3u);
-                            uint32_t rv[4];
-                            pp_load16(base4, ro, len, rv);
-                            same = ((rv[0] ^ wv[0]) | (rv[1] ^ wv[1]) | (rv[2] ^ wv[2]) | (rv[3] ^ wv[3])) == 0;
-                            for (int q = 16; q < len && same; q += 4)
-                                same = ((pp_load4(base4, ro + q) ^ pp_load4(S.text, b + q)) & pp_tail_mask(len - q)) == 0;
+                    odd = !done;  // neighbourhood full: solve this occurrence on its own
+                }
+                if (odd) {
+                    const int64_t g_ws = g0 + ws;
+                    int64_t g_we = g0 + we;
+                    if (open) {
+                        if (spm) {
+                            g_we = pp_spm_word_end_global(P, g_ws, ml, ds);
                         } else {
-                            same = true;
-                            for (int q = 0; q < len && same; ++q) same = P.text[rp + q] == S.text[b + q];
-                        }
-                        if (same) {
-                            ref = slot;
-                            done = true;
+                            const DptUniView U{P.V.uni1, P.V.uni2};
+                            const int64_t d = pp_upper_bound(P.doc_offs, P.n_docs + 1, g_ws);
+                            g_we = dpt_piece_end(P.rule, U, P.text, g_ws, d <= P.n_docs ? P.doc_offs[d] : n);
                         }
                     }
-                }
-                odd = !done;  // neighbourhood full: solve this occurrence on its own
-            }
-            if (odd) {
-                const int64_t g_ws = g0 + ws;
-                int64_t g_we = g0 + we;
-                if (open) {
-                    if (spm) {
-                        g_we = pp_spm_word_end_global(P, g_ws, ml, ds);
-                    } else {
-                        const DptUniView U{P.V.uni1, P.V.uni2};
-                        const int64_t d = pp_upper_bound(P.doc_offs, P.n_docs + 1, g_ws);
-                        g_we = dpt_piece_end(P.rule, U, P.text, g_ws, d <= P.n_docs ? P.doc_offs[d] : n);
+                    const uint32_t j = blk.atomic_add_ret(&P.ctl->n_odd, 1u);
+                    if ((int64_t)j < P.odd_cap) {
+                        OddWord o;
+                        o.pos = g_ws;
+                        o.len = (int32_t)(g_we - g_ws);
+                        o.virt = (spm && ds) ? 1 : 0;
+                        P.odd[j] = o;
                     }
+                    ref = REF_ODD | (j & REF_INDEX);
                 }
-                const uint32_t j = blk.atomic_add_ret(&P.ctl->n_odd, 1u);
-                if ((int64_t)j < P.odd_cap) {
-                    OddWord o;
-                    o.pos = g_ws;
-                    o.len = (int32_t)(g_we - g_ws);
-                    o.virt = (spm && ds) ? 1 : 0;
-                    P.odd[j] = o;
-                }
-                ref = REF_ODD | (j & REF_INDEX);
+                if (!spm && ds) ref |= REF_DOCFIRST;
             }
-            if (!spm && ds) ref |= REF_DOCFIRST;
-        }
-        if (staged) {
             S.stage[k] = ref;
-        } else {
-            const int64_t gw = (int64_t)S.base_w + k;
-            if (gw < P.word_cap) P.refs[gw] = ref;
-            if (!spm && (ref & REF_DOCFIRST)) {
-                const int64_t d = pp_lower_bound(P.doc_offs, P.n_docs + 1, g0 + ws);
-                if (d < P.n_docs) P.doc_first_word[d] = gw;
-            }
         }
-    }
-    if (staged) blk.lookback_resolve(P.desc_w, tile, (unsigned long long)ne, &S.base_w);  // warp 0, after its probes
-    blk.sync();
-    const int64_t base_w = (int64_t)S.base_w;
-    if (staged)
-        for (int k = tid; k < ne; k += nt) {
+        if (single) blk.lookback_resolve(P.desc_w, tile, (unsigned long long)ne, &S.base_w);  // warp 0, after its probes
+        blk.sync();
+        const int64_t base = (int64_t)S.base_w + lo;
+        for (int k = tid; k < nwin; k += nt) {
             const uint32_t ref = S.stage[k];
-            if (base_w + k < P.word_cap) P.refs[base_w + k] = ref;
+            if (base + k < P.word_cap) P.refs[base + k] = ref;
             if (!spm && (ref & REF_DOCFIRST)) {
                 const int64_t d = pp_lower_bound(P.doc_offs, P.n_docs + 1, g0 + (int)(S.wlist[k] & 0x7FFFu));
-                if (d < P.n_docs) P.doc_first_word[d] = base_w + k;
+                if (d < P.n_docs) P.doc_first_word[d] = base + k;
             }
         }
-    for (int c = tid; c < 4; c += nt)
-        S.base_c[c] = S.n_pend_c[c] ? blk.atomic_add_ret(&P.ctl->n_pending[c], S.n_pend_c[c]) : 0u;
-    if (tid == 0 && tile == P.n_tiles - 1) P.ctl->n_words = (unsigned long long)(base_w + ne);
-    blk.sync();
-    for (uint32_t i = tid; i < S.n_pend; i += nt) {
-        const uint32_t v = S.pend[i], cls = v >> 30;
-        const uint32_t r = blk.atomic_add_ret(&S.cur_c[cls], 1u);
-        P.pending[(size_t)cls * ((size_t)P.slot_mask + 1) + S.base_c[cls] + r] = v & REF_INDEX;
-    }
+        // ---- distinct words claimed in this window -> the DP queues (by length class) -------------------------------
+        for (int c = tid; c < 4; c += nt)
+            S.base_c[c] = S.n_pend_c[c] ? blk.atomic_add_ret(&P.ctl->n_pending[c], S.n_pend_c[c]) : 0u;
+        blk.sync();
+        const uint32_t npend = S.n_pend;
+        for (uint32_t i = tid; i < npend; i += nt) {
+            const uint32_t v = S.pend[i], cls = v >> 30;
+            const uint32_t r = blk.atomic_add_ret(&S.cur_c[cls], 1u);
+            P.pending[(size_t)cls * ((size_t)P.slot_mask + 1) + S.base_c[cls] + r] = v & REF_INDEX;
+        }
+        blk.sync();
+        if (tid == 0) {
+            S.n_pend = 0;
+            for (int c = 0; c < 4; ++c) S.n_pend_c[c] = S.cur_c[c] = 0;
+        }
+        lo += PA_WIN;
+        if (lo < ne) blk.sync();
+    } while (lo < ne);
+    if (tid == 0 && tile == P.n_tiles - 1) P.ctl->n_words = (unsigned long long)((int64_t)S.base_w + ne);
     blk.sync();
 }
 
-template <class Blk>
-DPT_PIPE_FN void pa_kernel(Blk& blk, const PipeParams& P, ASmem& S) {
+template <class Blk, bool kSpm>
+DPT_PIPE_FN void pa_kernel(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S) {
     // tiles are handed out in corpus order by an atomic ticket, so the look-back only ever waits for tiles held
     // by CTAs that are already running
     for (;;) {
@@ -679,7 +694,7 @@ DPT_PIPE_FN void pa_kernel(Blk& blk, const PipeParams& P, ASmem& S) {
         blk.sync();
         const int tile = S.tile;
         if (tile >= P.n_tiles) break;
-        pa_run_tile(blk, P, S, tile);
+        pa_run_tile<Blk, kSpm>(blk, P, S, tile);
         if (!blk.persistent()) break;
     }
 }

@@ -120,10 +120,17 @@ struct DevBlk {
     }
 };
 
-__global__ void __launch_bounds__(PA_THREADS) k_scan_dedup(const __grid_constant__ PipeParams P) {
-    __shared__ ASmem S;
+// SPM_LLAMA rule: 21 KB of shared memory and <= 40 registers -> 6 CTAs (48 warps) per SM
+__global__ void __launch_bounds__(PA_THREADS, 6) k_scan_dedup(const __grid_constant__ PipeParams P) {
+    __shared__ ASmemT<true> S;
     DevBlk blk;
-    pa_kernel(blk, P, S);
+    pa_kernel<DevBlk, true>(blk, P, S);
+}
+// byte-level rules (GPT-2, Llama-3): the split scanner needs more registers and the sync-point list more memory
+__global__ void __launch_bounds__(PA_THREADS) k_scan_dedup_bl(const __grid_constant__ PipeParams P) {
+    __shared__ ASmemT<false> S;
+    DevBlk blk;
+    pa_kernel<DevBlk, false>(blk, P, S);
 }
 
 __global__ void __launch_bounds__(PB_THREADS) k_dp_distinct(const __grid_constant__ PipeParams P) {
@@ -273,8 +280,11 @@ int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, 
     cudaMemsetAsync(zero0, 0, (size_t)zero_bytes, st);
     if (d_doc_flags) cudaMemsetAsync(d_doc_flags, 0, (size_t)n_docs, st);
     {
-        ProfScope prof("k_scan_dedup", st);
-        k_scan_dedup<<<(unsigned)z.n_tiles, PA_THREADS, 0, st>>>(P);
+        ProfScope prof(P.spm ? "k_scan_dedup" : "k_scan_dedup_bl", st);
+        if (P.spm)
+            k_scan_dedup<<<(unsigned)z.n_tiles, PA_THREADS, 0, st>>>(P);
+        else
+            k_scan_dedup_bl<<<(unsigned)z.n_tiles, PA_THREADS, 0, st>>>(P);
         ++g_launches;
     }
     {

@@ -7,6 +7,7 @@
 #include <memory>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "dpt_dp_core.h"
@@ -216,15 +217,24 @@ int32_t sim_encode_corpus_pipe(void* vv, int32_t rule, const uint8_t* text, int6
     memset(n_out, 0, 64);
     if (doc_flags) memset(doc_flags, 0, (size_t)n_docs);
     {   // kernel A
-        auto S = std::make_unique<ASmem>();
-        HostShared sh(nthreads);
-        std::vector<std::thread> th;
-        for (int t = 0; t < nthreads; ++t)
-            th.emplace_back([&, t] {
-                HostBlk blk{t, nthreads, &sh};
-                pa_kernel(blk, P, *S);
-            });
-        for (auto& x : th) x.join();
+        auto run = [&](auto* S) {
+            constexpr bool kSpm = std::is_same_v<std::remove_pointer_t<decltype(S)>, ASmemT<true>>;
+            HostShared sh(nthreads);
+            std::vector<std::thread> th;
+            for (int t = 0; t < nthreads; ++t)
+                th.emplace_back([&, t] {
+                    HostBlk blk{t, nthreads, &sh};
+                    pa_kernel<HostBlk, kSpm>(blk, P, *S);
+                });
+            for (auto& x : th) x.join();
+        };
+        if (P.spm) {
+            auto S = std::make_unique<ASmemT<true>>();
+            run(S.get());
+        } else {
+            auto S = std::make_unique<ASmemT<false>>();
+            run(S.get());
+        }
     }
     {   // kernels B (no block-level cooperation: run the threads one after the other)
         HostBlk blk{0, 1, nullptr};
