@@ -190,7 +190,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.cuda.current_device()
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner to STDOUT when the communicator is created; the contract is ONE JSON line on
+        # stdout, so create the communicator (init + one collective) with fd 1 pointing at stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     # ---- workload: this rank's shard (documents are independent; each rank generates its own) ----
     n_bytes_target = int(args.size_mb * 1e6)
@@ -276,7 +288,7 @@ def main():
                 pass
 
     # ---- end to end through the public API with HOST buffers -------------------------------------
-    # Engine.encode_corpus_host: pinned host text -> chunked H2D / kernels / D2H on 3 streams -> pinned host ids,
+    # Engine.encode_corpus_host: pinned host text -> chunked H2D / kernels / D2H on 4 streams -> pinned host ids,
     # document offsets and counters.  Both copies are inside the timed region.
     e2e = None
     if not args.no_e2e:
@@ -304,7 +316,7 @@ def main():
                "d2h_bytes_per_step": int(4 * r.n_ids + 9 * n_docs + 104 * r.n_chunks),
                "tokens_per_sec": g_tokens * args.steps / float(tt.item()),
                "ms_per_step": 1e3 * float(tt.item()) / args.steps, "chunks": r.n_chunks,
-               "how": "Engine.encode_corpus_host: 12 MB chunks at document boundaries, 3 streams, wall clock"}
+               "how": "Engine.encode_corpus_host: 16 MB chunks at document boundaries, 4 streams, wall clock"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------
     cpu = None
