@@ -51,6 +51,7 @@ constexpr int PC_THREADS = 256;
 constexpr int PC_PER = 8;                     // words per thread in kernel C
 constexpr int PA_WIN = 1024;                  // words of a tile handled per pass (a 4 KB tile holds ~520; more -> more passes)
 constexpr int PC_TILE = PC_THREADS * PC_PER;
+constexpr int PC_STAGE = 6144;                // ids of one kernel-C tile staged in shared memory (more -> direct writes)
 
 // one 32-bit ref per word: top two bits 11 = the '<s>' word in front of an SPM_LLAMA document | document index,
 // 10 = index into the odd-word list (not deduplicated), otherwise the word's table slot
@@ -83,6 +84,7 @@ struct PipeCtl {  // device-side counters, zeroed by the launcher
     unsigned int n_pending[4];  // distinct words queued for the DP, by length class (keeps a warp's lanes alike)
     unsigned int n_odd, n_long;
     unsigned long long pool_used, lp_used, n_words, n_untok, n_too_long;
+    unsigned long long b_cursor;  // next unclaimed item of kernel B's work list
 };
 
 struct PipeParams {
@@ -152,6 +154,7 @@ struct ASmemT {
 };
 
 struct CSmem {
+    int32_t ids[PC_STAGE];
     uint32_t scan[40];
     int32_t tile;
     uint32_t tile_tot, n_untok;
@@ -771,25 +774,30 @@ struct PbItem {
     bool marker;
     ResRec* out;
 };
-DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint64_t i, const uint32_t* npc) {
+// Work list order: odd words, then the length classes from longest to shortest, so the expensive words are
+// claimed first and the kernel's tail is made of the cheapest ones.
+DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint64_t i, const uint32_t* npc, uint32_t n_odd) {
     PbItem it;
-    const uint64_t p1 = npc[0], p2 = p1 + npc[1], p3 = p2 + npc[2], p4 = p3 + npc[3];
-    if (i < p4) {
-        const uint32_t cls = i < p1 ? 0u : i < p2 ? 1u : i < p3 ? 2u : 3u;
-        const uint64_t idx = i - (cls == 0 ? 0 : cls == 1 ? p1 : cls == 2 ? p2 : p3);
-        const uint32_t slot = P.pending[(size_t)cls * ((size_t)P.slot_mask + 1) + idx];
-        const unsigned long long t = P.tags[slot];
-        it.pos = pp_tag_pos(t);
-        it.end = it.pos + pp_tag_len(t);
-        it.marker = P.spm != 0;
-        it.out = &P.res[slot];
-    } else {
-        const OddWord o = P.odd[i - p4];
+    if (i < n_odd) {
+        const OddWord o = P.odd[i];
         it.pos = o.pos;
         it.end = o.pos + o.len;
         it.marker = o.virt != 0;
-        it.out = &P.odd_res[i - p4];
+        it.out = &P.odd_res[i];
+        return it;
     }
+    i -= n_odd;
+    uint32_t cls = 3;
+    while (cls > 0 && i >= npc[cls]) {
+        i -= npc[cls];
+        --cls;
+    }
+    const uint32_t slot = P.pending[(size_t)cls * ((size_t)P.slot_mask + 1) + i];
+    const unsigned long long t = P.tags[slot];
+    it.pos = pp_tag_pos(t);
+    it.end = it.pos + pp_tag_len(t);
+    it.marker = P.spm != 0;
+    it.out = &P.res[slot];
     return it;
 }
 
@@ -797,20 +805,21 @@ DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint64_t i, const uint32_t* npc)
 // go through the same sequence of single loops (normalise, forward state machine, backward chase) and reconverge
 // between them.
 template <class Blk>
-DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P, int64_t gtid, int64_t gthreads) {
+DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
     const uint32_t npc[4] = {P.ctl->n_pending[0], P.ctl->n_pending[1], P.ctl->n_pending[2], P.ctl->n_pending[3]};
     const uint32_t n_odd = P.ctl->n_odd < (uint32_t)P.odd_cap ? P.ctl->n_odd : (uint32_t)P.odd_cap;
     const uint64_t total = (uint64_t)npc[0] + npc[1] + npc[2] + npc[3] + n_odd;
-    const uint64_t rounds = (total + (uint64_t)gthreads - 1) / (uint64_t)gthreads;
-    for (uint64_t r = 0; r < rounds; ++r) {
-        const uint64_t i = r * (uint64_t)gthreads + (uint64_t)gtid;
+    for (;;) {
+        // every warp claims the next 32 items (dynamic: a warp stuck on long words does not hold the others back)
+        const uint64_t i = blk.warp_take(&P.ctl->b_cursor);
+        if (!blk.warp_any(i < total)) break;
         const bool valid = i < total;
         PbItem it;
         it.out = nullptr;
         uint8_t norm[PB_LOCAL + 8];
         int32_t nlen = 0;
         if (valid) {
-            it = pb_item(P, i, npc);
+            it = pb_item(P, i, npc, n_odd);
             nlen = pb_normalise(P, it.pos, it.end, it.marker, norm, PB_LOCAL);
             if (nlen < 0) {
                 const uint32_t q = blk.atomic_add_ret(&P.ctl->n_long, 1u);
@@ -856,9 +865,10 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P, int64_t gtid, int64_t 
 template <class Blk>
 DPT_PIPE_FN void pb_long_thread(Blk& blk, const PipeParams& P, int64_t gtid, int64_t gthreads) {
     const uint32_t npc[4] = {P.ctl->n_pending[0], P.ctl->n_pending[1], P.ctl->n_pending[2], P.ctl->n_pending[3]};
+    const uint32_t n_odd = P.ctl->n_odd < (uint32_t)P.odd_cap ? P.ctl->n_odd : (uint32_t)P.odd_cap;
     const uint32_t n_long = P.ctl->n_long;
     for (uint64_t k = (uint64_t)gtid; k < n_long; k += (uint64_t)gthreads) {
-        const PbItem it = pb_item(P, (uint64_t)P.longq[k], npc);
+        const PbItem it = pb_item(P, (uint64_t)P.longq[k], npc, n_odd);
         const int64_t raw = it.end - it.pos;
         const int64_t need = (P.spm ? 6 * raw + 3 : raw) + 2;
         const unsigned long long off = blk.atomic_add_u64_ret(&P.ctl->lp_used, (unsigned long long)need);
@@ -961,47 +971,73 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
                 P.word_flags[w0 + k] = (uint8_t)(((meta[k] & RES_UNTOK) ? 1u : 0u) | ((meta[k] & RES_LONG) ? 4u : 0u));
             }
     }
-    blk.lookback_resolve(P.desc_t, tile, (unsigned long long)total, &S.base_t);
-    blk.sync();
-    int64_t gt = (int64_t)S.base_t + off;
+    // ids: staged in shared memory at their tile-local offsets (every thread copies its words' ids out of the
+    // records), then written to their final place by the whole CTA with fully coalesced stores.  The look-back is
+    // resolved in between, as late as possible.
+    const bool staged = total <= (uint32_t)PC_STAGE;
+    if (!staged) {
+        blk.lookback_resolve(P.desc_t, tile, (unsigned long long)total, &S.base_t);
+        blk.sync();
+    }
+    {
+        int64_t gt = staged ? (int64_t)off : (int64_t)S.base_t + off;  // tile-local when staged
+        int32_t* dst = staged ? S.ids : P.ids;
+        const int64_t cap = staged ? (int64_t)PC_STAGE : P.ids_cap;
 #pragma unroll
-    for (int k = 0; k < PC_PER; ++k) {
-        if (w0 + k >= n_words) break;
-        const uint32_t kind = ref[k] & REF_KIND;
-        if (kind == REF_BOS) {
-            const int64_t d = (int64_t)(ref[k] & REF_INDEX);
-            if (d < P.n_docs) P.doc_tok_offs[d] = gt;
-        } else if (ref[k] & REF_DOCFIRST) {  // byte-level rules: first word of a document
-            const int64_t d = pp_lower_bound(P.doc_first_word, P.n_docs, w0 + k);
-            if (d < P.n_docs) P.doc_tok_offs[d] = gt;
-        }
-        if (meta[k] & RES_UNTOK) continue;
-        const uint32_t nk = meta[k] & 0xFFFFFFu;
-        if (nk == 0) continue;
-        if (kind == REF_BOS) {
-            for (uint32_t q = 0; q < nk && q < 3; ++q)
-                if (gt + q < P.ids_cap) P.ids[gt + q] = P.V.bos_ids[q];
-        } else {
-            const ResRec* r = pc_record_ptr(P, ref[k]);
-            if (meta[k] & RES_POOLED) {
-                const int64_t po = (int64_t)(uint32_t)r->ids[0] | ((int64_t)(uint32_t)r->ids[1] << 32);
-                for (uint32_t q = 0; q < nk; ++q)
-                    if (gt + q < P.ids_cap && po + q < P.pool_cap) P.ids[gt + q] = P.pool[po + q];
+        for (int k = 0; k < PC_PER; ++k) {
+            if (w0 + k >= n_words) break;
+            const uint32_t kind = ref[k] & REF_KIND;
+            if (meta[k] & RES_UNTOK) continue;
+            const uint32_t nk = meta[k] & 0xFFFFFFu;
+            if (nk == 0) continue;
+            if (kind == REF_BOS) {
+                for (uint32_t q = 0; q < nk && q < 3; ++q)
+                    if (gt + q < cap) dst[gt + q] = P.V.bos_ids[q];
             } else {
-                const uint4 a = *reinterpret_cast<const uint4*>(r);             // meta, ids[0..2]
-                if (gt < P.ids_cap) P.ids[gt] = (int32_t)a.y;
-                if (nk > 1 && gt + 1 < P.ids_cap) P.ids[gt + 1] = (int32_t)a.z;
-                if (nk > 2 && gt + 2 < P.ids_cap) P.ids[gt + 2] = (int32_t)a.w;
-                if (nk > 3) {
-                    const uint4 c = *(reinterpret_cast<const uint4*>(r) + 1);   // ids[3..6]
-                    if (gt + 3 < P.ids_cap) P.ids[gt + 3] = (int32_t)c.x;
-                    if (nk > 4 && gt + 4 < P.ids_cap) P.ids[gt + 4] = (int32_t)c.y;
-                    if (nk > 5 && gt + 5 < P.ids_cap) P.ids[gt + 5] = (int32_t)c.z;
-                    if (nk > 6 && gt + 6 < P.ids_cap) P.ids[gt + 6] = (int32_t)c.w;
+                const ResRec* r = pc_record_ptr(P, ref[k]);
+                if (meta[k] & RES_POOLED) {
+                    const int64_t po = (int64_t)(uint32_t)r->ids[0] | ((int64_t)(uint32_t)r->ids[1] << 32);
+                    for (uint32_t q = 0; q < nk; ++q)
+                        if (gt + q < cap && po + q < P.pool_cap) dst[gt + q] = P.pool[po + q];
+                } else {
+                    const uint4 a = *reinterpret_cast<const uint4*>(r);             // meta, ids[0..2]
+                    if (gt < cap) dst[gt] = (int32_t)a.y;
+                    if (nk > 1 && gt + 1 < cap) dst[gt + 1] = (int32_t)a.z;
+                    if (nk > 2 && gt + 2 < cap) dst[gt + 2] = (int32_t)a.w;
+                    if (nk > 3) {
+                        const uint4 c = *(reinterpret_cast<const uint4*>(r) + 1);   // ids[3..6]
+                        if (gt + 3 < cap) dst[gt + 3] = (int32_t)c.x;
+                        if (nk > 4 && gt + 4 < cap) dst[gt + 4] = (int32_t)c.y;
+                        if (nk > 5 && gt + 5 < cap) dst[gt + 5] = (int32_t)c.z;
+                        if (nk > 6 && gt + 6 < cap) dst[gt + 6] = (int32_t)c.w;
+                    }
                 }
             }
+            gt += nk;
         }
-        gt += nk;
+    }
+    if (staged) blk.lookback_resolve(P.desc_t, tile, (unsigned long long)total, &S.base_t);
+    blk.sync();
+    {
+        const int64_t base_t = (int64_t)S.base_t;
+        if (staged)
+            for (uint32_t q = (uint32_t)tid; q < total; q += (uint32_t)blk.nthreads())
+                if (base_t + q < P.ids_cap) P.ids[base_t + q] = S.ids[q];
+        // document token offsets
+        int64_t gt = base_t + off;
+#pragma unroll
+        for (int k = 0; k < PC_PER; ++k) {
+            if (w0 + k >= n_words) break;
+            const uint32_t kind = ref[k] & REF_KIND;
+            if (kind == REF_BOS) {
+                const int64_t d = (int64_t)(ref[k] & REF_INDEX);
+                if (d < P.n_docs) P.doc_tok_offs[d] = gt;
+            } else if (ref[k] & REF_DOCFIRST) {  // byte-level rules: first word of a document
+                const int64_t d = pp_lower_bound(P.doc_first_word, P.n_docs, w0 + k);
+                if (d < P.n_docs) P.doc_tok_offs[d] = gt;
+            }
+            if (!(meta[k] & RES_UNTOK)) gt += meta[k] & 0xFFFFFFu;
+        }
     }
     if (tid == 0) {
         if (S.n_untok) blk.atomic_add_u64_ret(&P.ctl->n_untok, (unsigned long long)S.n_untok);

@@ -67,6 +67,14 @@ struct DevBlk {
     }
 
     __device__ __forceinline__ void reconverge() const { __syncwarp(); }
+    // kernel B: lane 0 claims 32 consecutive work items for its warp; returns this lane's item index
+    __device__ __forceinline__ unsigned long long warp_take(unsigned long long* cursor) const {
+        unsigned long long base = 0;
+        if ((threadIdx.x & 31) == 0) base = atomicAdd(cursor, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        return base + (threadIdx.x & 31);
+    }
+    __device__ __forceinline__ bool warp_any(bool p) const { return __any_sync(0xffffffffu, p); }
 
     // decoupled look-back, split in two so a tile can publish early and resolve late.  descriptor = status << 62 |
     // value (1 = this tile's aggregate, 2 = inclusive prefix).  publish: thread 0.  resolve: warp 0 sums the
@@ -135,7 +143,7 @@ __global__ void __launch_bounds__(PA_THREADS) k_scan_dedup_bl(const __grid_const
 
 __global__ void __launch_bounds__(PB_THREADS) k_dp_distinct(const __grid_constant__ PipeParams P) {
     DevBlk blk;
-    pb_thread(blk, P, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+    pb_thread(blk, P);
 }
 
 __global__ void __launch_bounds__(PB_THREADS) k_dp_distinct_long(const __grid_constant__ PipeParams P) {
@@ -289,7 +297,7 @@ int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, 
     }
     {
         ProfScope prof("k_dp_distinct", st);
-        k_dp_distinct<<<(unsigned)(sm_count * 16), PB_THREADS, 0, st>>>(P);
+        k_dp_distinct<<<(unsigned)(sm_count * 12), PB_THREADS, 0, st>>>(P);
         ++g_launches;
     }
     {

@@ -53,6 +53,8 @@ struct HostBlk {
         return ex;
     }
     void reconverge() const {}
+    unsigned long long warp_take(unsigned long long* cursor) const { return __atomic_fetch_add(cursor, 1ull, __ATOMIC_RELAXED); }
+    bool warp_any(bool p) const { return p; }
     // tiles are processed in order by the one emulated CTA: the predecessor's inclusive prefix is always there
     void lookback_publish(unsigned long long* desc, int tile, unsigned long long agg) const {
         if (tid_ == 0) desc[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | agg;
@@ -239,7 +241,7 @@ int32_t sim_encode_corpus_pipe(void* vv, int32_t rule, const uint8_t* text, int6
     {   // kernels B (no block-level cooperation: run the threads one after the other)
         HostBlk blk{0, 1, nullptr};
         const int64_t g = 37;
-        for (int64_t t = 0; t < g; ++t) pb_thread(blk, P, t, g);
+        pb_thread(blk, P);
         for (int64_t t = 0; t < g; ++t) pb_long_thread(blk, P, t, g);
     }
     {   // kernel C
