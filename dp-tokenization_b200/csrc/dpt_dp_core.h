@@ -305,3 +305,96 @@ DPT_HD bool dpt_backward_flat32(const DptVocabView& V, int32_t n, const uint32_t
     }
     return true;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Shared-memory variant for words of at most DPT_FLAT16_MAX normalised bytes (19 of 20 distinct words): the word's
+// bytes and the per-position keys - the two arrays on the loop's critical path - live in shared memory, interleaved
+// by thread (element p of thread t at [p * stride + t]); key in 16 bits  len << 7 | notreach << 6 | (63 - M).
+// Back-pointers and winning slots are write-only in the forward pass and stay in local memory.
+// ---------------------------------------------------------------------------------------------------------
+#define DPT_FLAT16_MAX 32
+#define DPT_K16_NONE 0xFFFFu
+DPT_HD uint32_t dpt_k16_extend(uint32_t kj, uint32_t cl) {
+    const uint32_t lowj = kj & 0x3Fu, lowe = 63u - cl;
+    return (kj & 0xFFC0u) + 0x80u + (lowj < lowe ? lowj : lowe);
+}
+
+DPT_HD void dpt_forward_flat16(const DptVocabView& V, const uint8_t* s, uint16_t* best, int32_t stride, int32_t n, uint8_t* A,
+                               uint8_t* B, uint32_t* As, uint32_t* Bs) {
+    const bool cp_mode = V.unit_mode != 0;
+    uint32_t u = 0;
+    for (int32_t p = 0; p <= n; ++p) {
+        const bool b = (p == 0 || p == n || !cp_mode) ? true : dpt_is_cp_start(s[p * stride]);
+        best[p * stride] = (uint16_t)(b ? ((u << 7) | 0x7Fu) : DPT_K16_NONE);  // phantom: len = unit index, not reachable
+        if (b) ++u;
+        A[p] = 0;
+        B[p] = 0;
+    }
+    if (n > 0) best[0] = 63u;  // origin: len 0, reachable, longest 0
+    const uint32_t* __restrict__ da = V.da;
+    int32_t j = -1, i = 0;
+    uint32_t entry = 0, cl = 0, kj = 0;
+    bool walking = false;
+    for (;;) {
+        if (!walking) {
+            if (++j >= n) break;
+            kj = best[j * stride];
+            entry = DPT_DA_ROOT_ENTRY;
+            i = j;
+            cl = 0;
+            walking = kj != DPT_K16_NONE;
+            if (!walking) continue;
+        }
+        const uint32_t base = entry >> DPT_DA_BASE_SHIFT;
+        const uint32_t c = i < n ? (uint32_t)s[i * stride] : 0x100u;
+        const uint32_t slot = base + (c & 0xFFu);
+        uint32_t e = 0;
+        if (base != 0 && c < 0x100u) {
+#if defined(__CUDA_ARCH__)
+            e = __ldg(da + slot);
+#else
+            e = da[slot];
+#endif
+        }
+        if ((e & DPT_DA_MATCH_MASK) != (DPT_DA_OCCUPIED | c)) {
+            walking = false;
+            continue;
+        }
+        entry = e;
+        ++i;
+        cl += (!cp_mode || dpt_is_cp_start(c)) ? 1u : 0u;
+        if (e & DPT_DA_TERMINAL) {
+            const uint32_t bi = best[i * stride];
+            if (bi != DPT_K16_NONE) {
+                const uint32_t k = dpt_k16_extend(kj, cl);
+                const uint32_t packed = slot | (cl << 22);
+                if ((k >> 6) <= (bi >> 6)) {
+                    A[i] = (uint8_t)(i - j);
+                    As[i] = packed;
+                }
+                if (k <= bi) {
+                    best[i * stride] = (uint16_t)k;
+                    B[i] = (uint8_t)(i - j);
+                    Bs[i] = packed;
+                }
+            }
+        }
+    }
+}
+
+// Backward chase shared by the compact variants: word_len ids into out_ids[0..word_len) in text order.
+DPT_HD void dpt_backward_chase(const DptVocabView& V, int32_t n, uint32_t word_len, uint32_t target, const uint8_t* A,
+                               const uint8_t* B, const uint32_t* As, const uint32_t* Bs, int32_t* out_ids, int64_t out_cap) {
+    int64_t slot_out = (int64_t)word_len - 1;
+    bool got = false;
+    int32_t i = n;
+    while (i > 0 && slot_out >= 0) {
+        const int32_t d = got ? A[i] : B[i];
+        if (d <= 0 || d > i) break;  // cannot happen on a reachable path; never spin on corrupt state
+        const uint32_t ts = got ? As[i] : Bs[i];
+        if (!got && (ts >> 22) == target) got = true;
+        if (slot_out < out_cap) out_ids[slot_out] = V.slot_id[ts & 0x3FFFFFu];
+        --slot_out;
+        i -= d;
+    }
+}

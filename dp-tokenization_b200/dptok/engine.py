@@ -169,8 +169,9 @@ class Engine:
                            n_streams: int = 4, out_ids: Optional[torch.Tensor] = None) -> "HostResult":
         """``h_text``: uint8 HOST tensor (pinned for full speed) of concatenated non-empty documents; ``doc_offs``:
         int64[n_docs+1] numpy array.  The corpus is cut at document boundaries into chunks of about ``chunk_bytes``;
-        chunk k's host->device copy, its five kernels and its device->host copy of the ids run on stream k mod
-        ``n_streams``, so PCIe in both directions and the SMs work at the same time.  Returns host tensors."""
+        host->device copies, kernels and device->host copies run on three dedicated streams over a ring of
+        ``n_streams`` buffer slots, so PCIe in both directions and the SMs work at the same time.  Returns host
+        tensors."""
         assert h_text.dtype == torch.uint8 and not h_text.is_cuda
         doc_offs = np.ascontiguousarray(doc_offs, dtype=np.int64)
         n_docs = len(doc_offs) - 1
@@ -196,10 +197,11 @@ class Engine:
             key = (rule, max_b, max_d, n_streams)
             if getattr(self, "_host_slots_key", None) != key:
                 ws_bytes = lib.dpt_encode_corpus_workspace(rule, max_b, max_d, word_cap, 0)
+                self._host_streams = [torch.cuda.Stream(device=dev) for _ in range(3)]  # copy-in, compute, copy-out
                 self._host_slots = []
                 for _ in range(n_streams):
                     self._host_slots.append(dict(
-                        stream=torch.cuda.Stream(device=dev), event=torch.cuda.Event(),
+                        ev_in=torch.cuda.Event(), ev_comp=torch.cuda.Event(), ev_out=torch.cuda.Event(),
                         d_text=torch.empty(max_b, dtype=torch.uint8, device=dev),
                         d_offs=torch.empty(max_d + 1, dtype=torch.int64, device=dev),
                         h_offs=torch.empty(max_d + 1, dtype=torch.int64).pin_memory(),
@@ -216,17 +218,26 @@ class Engine:
                         ws=torch.empty(int(ws_bytes), dtype=torch.uint8, device=dev)))
                 self._host_slots_key = key
             slots = self._host_slots
+            s_in, s_comp, s_out = self._host_streams
             cur = torch.cuda.current_stream(dev)
-            for sl in slots:
-                sl["stream"].wait_stream(cur)
+            for st in (s_in, s_comp, s_out):
+                st.wait_stream(cur)
             ids_base = 0
-            pending = []  # (chunk index, slot)
+            pending = []  # (chunk index, slot), in order
+            trace = getattr(self, "_trace", None)
+
+            def mark(name, k, stream):
+                if trace is not None:
+                    import time as _t
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record(stream)
+                    trace.append((name, k, ev, _t.perf_counter()))
 
             def finalize(k, sl):
                 nonlocal ids_base
                 lo, hi = cuts[k], cuts[k + 1]
                 nd = hi - lo
-                sl["event"].synchronize()                   # status vector + document offsets of chunk k are on the host
+                sl["ev_comp"].synchronize()                 # status vector + document offsets of chunk k are on the host
                 h = sl["h_small"].tolist()
                 if h[1] > word_cap or h[0] > ids_cap or h[2] > h[3] or h[4] > h[5] or h[6] > h[7]:
                     # a capacity was exceeded: redo this chunk through the retrying device-resident path
@@ -237,10 +248,14 @@ class Engine:
                     out_doc_tok[lo:hi] = res.doc_tok_offs[:nd].cpu().numpy() + ids_base
                     out_doc_flags[lo:hi] = res.doc_flags.cpu().numpy()
                     totals[:] += np.asarray(res.counters.cpu().tolist(), dtype=np.int64)
+                    sl["ev_out"].record(s_out)
                 else:
                     n_ids = h[0]
-                    with torch.cuda.stream(sl["stream"]):
+                    with torch.cuda.stream(s_out):          # the host has seen ev_comp: the ids are complete
+                        mark("d2h-begin", k, s_out)
                         out_ids[ids_base:ids_base + n_ids].copy_(sl["ids"][:n_ids], non_blocking=True)
+                        sl["ev_out"].record(s_out)
+                        mark("d2h-end", k, s_out)
                     out_doc_tok[lo:hi] = sl["h_doc_tok"][:nd].numpy() + ids_base
                     out_doc_flags[lo:hi] = sl["h_doc_flags"][:nd].numpy()
                     totals[:] += np.asarray(h[8:12], dtype=np.int64)
@@ -248,30 +263,38 @@ class Engine:
 
             for k in range(n_chunks):
                 sl = slots[k % n_streams]
-                if len(pending) >= n_streams:
+                if len(pending) >= n_streams:               # the slot's previous chunk must have left the GPU
                     finalize(*pending.pop(0))
                 lo, hi = cuts[k], cuts[k + 1]
                 b0, b1 = int(doc_offs[lo]), int(doc_offs[hi])
                 nb, nd = b1 - b0, hi - lo
                 sl["h_offs"][:nd + 1].copy_(torch.from_numpy(doc_offs[lo:hi + 1] - b0))
-                with torch.cuda.stream(sl["stream"]):
+                with torch.cuda.stream(s_in):               # copy-in engine: chunk after chunk, never behind a copy-out
+                    s_in.wait_event(sl["ev_comp"])          # the slot's text is no longer being read
+                    mark("h2d-begin", k, s_in)
                     sl["d_text"][:nb].copy_(h_text[b0:b1], non_blocking=True)
                     sl["d_offs"][:nd + 1].copy_(sl["h_offs"][:nd + 1], non_blocking=True)
+                    sl["ev_in"].record(s_in)
+                    mark("h2d-end", k, s_in)
+                with torch.cuda.stream(s_comp):
+                    s_comp.wait_event(sl["ev_in"])
+                    s_comp.wait_event(sl["ev_out"])         # the slot's ids have been copied out
+                    mark("comp-begin", k, s_comp)
                     check(lib.dpt_encode_corpus(self.vocab.handle, rule, _ptr(sl["d_text"]), nb, _ptr(sl["d_offs"]), nd,
                                                 _ptr(sl["ids"]), ids_cap, _ptr(sl["lens"]), _ptr(sl["flags"]), word_cap,
                                                 _ptr(sl["doc_tok"]), _ptr(sl["doc_flags"]), _ptr(sl["counters"]),
                                                 _ptr(sl["n_out"]), _ptr(sl["ws"]), sl["ws"].numel(), 0,
-                                                C.c_void_p(sl["stream"].cuda_stream)))
+                                                C.c_void_p(s_comp.cuda_stream)))
                     sl["h_small"][:8].copy_(sl["n_out"], non_blocking=True)
                     sl["h_small"][8:12].copy_(sl["counters"], non_blocking=True)
                     sl["h_doc_tok"][:nd + 1].copy_(sl["doc_tok"][:nd + 1], non_blocking=True)
                     sl["h_doc_flags"][:nd].copy_(sl["doc_flags"][:nd], non_blocking=True)
-                    sl["event"].record(sl["stream"])
+                    sl["ev_comp"].record(s_comp)
+                    mark("comp-end", k, s_comp)
                 pending.append((k, sl))
             while pending:
                 finalize(*pending.pop(0))
-            for sl in slots:
-                sl["stream"].synchronize()
+            s_out.synchronize()
         out_doc_tok[n_docs] = ids_base
         return HostResult(out_ids[:ids_base], out_doc_tok, out_doc_flags, totals, ids_base, n_chunks)
 
