@@ -223,6 +223,18 @@ DPT_HD uint32_t dpt_k32_len(uint32_t k) { return k >> 17; }
 DPT_HD bool dpt_k32_reach(uint32_t k) { return (k & 0x10000u) == 0; }
 DPT_HD uint32_t dpt_k32_longest(uint32_t k) { return 0xFFFFu - (k & 0xFFFFu); }
 
+// trie slot load: read-only path, L1 evict_last (the DP state streaming through L1 as local memory must not push the
+// trie out: the trie lookup is the loop-carried dependency of the forward pass)
+DPT_HD uint32_t dpt_da_load(const uint32_t* da, uint32_t slot) {
+#if defined(__CUDA_ARCH__)
+    uint32_t e;
+    asm volatile("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(e) : "l"(da + slot));
+    return e;
+#else
+    return da[slot];
+#endif
+}
+
 DPT_HD void dpt_forward_flat32(const DptVocabView& V, const uint8_t* s, int32_t n, uint32_t* best, uint8_t* A, uint8_t* B,
                                uint32_t* As, uint32_t* Bs) {
     const bool cp_mode = V.unit_mode != 0;
@@ -253,13 +265,7 @@ DPT_HD void dpt_forward_flat32(const DptVocabView& V, const uint8_t* s, int32_t 
         const uint32_t c = i < n ? (uint32_t)s[i] : 0x100u;
         const uint32_t slot = base + (c & 0xFFu);
         uint32_t e = 0;
-        if (base != 0 && c < 0x100u) {
-#if defined(__CUDA_ARCH__)
-            e = __ldg(da + slot);
-#else
-            e = da[slot];
-#endif
-        }
+        if (base != 0 && c < 0x100u) e = dpt_da_load(da, slot);
         if ((e & DPT_DA_MATCH_MASK) != (DPT_DA_OCCUPIED | c)) {
             walking = false;
             continue;
@@ -304,82 +310,6 @@ DPT_HD bool dpt_backward_flat32(const DptVocabView& V, int32_t n, const uint32_t
         i -= d;
     }
     return true;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Shared-memory variant for words of at most DPT_FLAT16_MAX normalised bytes (19 of 20 distinct words): the word's
-// bytes and the per-position keys - the two arrays on the loop's critical path - live in shared memory, interleaved
-// by thread (element p of thread t at [p * stride + t]); key in 16 bits  len << 7 | notreach << 6 | (63 - M).
-// Back-pointers and winning slots are write-only in the forward pass and stay in local memory.
-// ---------------------------------------------------------------------------------------------------------
-#define DPT_FLAT16_MAX 32
-#define DPT_K16_NONE 0xFFFFu
-DPT_HD uint32_t dpt_k16_extend(uint32_t kj, uint32_t cl) {
-    const uint32_t lowj = kj & 0x3Fu, lowe = 63u - cl;
-    return (kj & 0xFFC0u) + 0x80u + (lowj < lowe ? lowj : lowe);
-}
-
-DPT_HD void dpt_forward_flat16(const DptVocabView& V, const uint8_t* s, uint16_t* best, int32_t stride, int32_t n, uint8_t* A,
-                               uint8_t* B, uint32_t* As, uint32_t* Bs) {
-    const bool cp_mode = V.unit_mode != 0;
-    uint32_t u = 0;
-    for (int32_t p = 0; p <= n; ++p) {
-        const bool b = (p == 0 || p == n || !cp_mode) ? true : dpt_is_cp_start(s[p * stride]);
-        best[p * stride] = (uint16_t)(b ? ((u << 7) | 0x7Fu) : DPT_K16_NONE);  // phantom: len = unit index, not reachable
-        if (b) ++u;
-        A[p] = 0;
-        B[p] = 0;
-    }
-    if (n > 0) best[0] = 63u;  // origin: len 0, reachable, longest 0
-    const uint32_t* __restrict__ da = V.da;
-    int32_t j = -1, i = 0;
-    uint32_t entry = 0, cl = 0, kj = 0;
-    bool walking = false;
-    for (;;) {
-        if (!walking) {
-            if (++j >= n) break;
-            kj = best[j * stride];
-            entry = DPT_DA_ROOT_ENTRY;
-            i = j;
-            cl = 0;
-            walking = kj != DPT_K16_NONE;
-            if (!walking) continue;
-        }
-        const uint32_t base = entry >> DPT_DA_BASE_SHIFT;
-        const uint32_t c = i < n ? (uint32_t)s[i * stride] : 0x100u;
-        const uint32_t slot = base + (c & 0xFFu);
-        uint32_t e = 0;
-        if (base != 0 && c < 0x100u) {
-#if defined(__CUDA_ARCH__)
-            e = __ldg(da + slot);
-#else
-            e = da[slot];
-#endif
-        }
-        if ((e & DPT_DA_MATCH_MASK) != (DPT_DA_OCCUPIED | c)) {
-            walking = false;
-            continue;
-        }
-        entry = e;
-        ++i;
-        cl += (!cp_mode || dpt_is_cp_start(c)) ? 1u : 0u;
-        if (e & DPT_DA_TERMINAL) {
-            const uint32_t bi = best[i * stride];
-            if (bi != DPT_K16_NONE) {
-                const uint32_t k = dpt_k16_extend(kj, cl);
-                const uint32_t packed = slot | (cl << 22);
-                if ((k >> 6) <= (bi >> 6)) {
-                    A[i] = (uint8_t)(i - j);
-                    As[i] = packed;
-                }
-                if (k <= bi) {
-                    best[i * stride] = (uint16_t)k;
-                    B[i] = (uint8_t)(i - j);
-                    Bs[i] = packed;
-                }
-            }
-        }
-    }
 }
 
 // Backward chase shared by the compact variants: word_len ids into out_ids[0..word_len) in text order.

@@ -804,10 +804,8 @@ DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint64_t i, const uint32_t* npc,
 // one thread per distinct word, DP state in local memory.  The loop body is written so that the lanes of a warp
 // go through the same sequence of single loops (normalise, forward state machine, backward chase) and reconverge
 // between them.
-// sm_norm / sm_best: shared memory of the block, DPT_FLAT16_MAX (+1) elements per thread interleaved by thread
-// (element p of this thread at [p * stride]; the pointers are already offset by the thread index).
 template <class Blk>
-DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P, uint8_t* sm_norm, uint16_t* sm_best, int32_t stride) {
+DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
     const uint32_t npc[4] = {P.ctl->n_pending[0], P.ctl->n_pending[1], P.ctl->n_pending[2], P.ctl->n_pending[3]};
     const uint32_t n_odd = P.ctl->n_odd < (uint32_t)P.odd_cap ? P.ctl->n_odd : (uint32_t)P.odd_cap;
     const uint64_t total = (uint64_t)npc[0] + npc[1] + npc[2] + npc[3] + n_odd;
@@ -830,18 +828,10 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P, uint8_t* sm_norm, uint
         }
         blk.reconverge();
         const int32_t n = nlen > 0 ? nlen : 0;
-        // short words (19 of 20): bytes + keys in shared memory; the rest: everything in local memory.  Every lane
-        // runs both loops (with n = 0 for the one that is not its own) so the warp stays converged.
-        const bool small = n <= DPT_FLAT16_MAX;
+        uint32_t best[PB_LOCAL + 1];
         uint8_t A[PB_LOCAL + 1], B[PB_LOCAL + 1];
         uint32_t As[PB_LOCAL + 1], Bs[PB_LOCAL + 1];
-        uint32_t best[PB_LOCAL + 1];
-        if (small)
-            for (int32_t p = 0; p < n; ++p) sm_norm[p * stride] = norm[p];
-        blk.reconverge();
-        dpt_forward_flat16(P.V, sm_norm, sm_best, stride, small ? n : 0, A, B, As, Bs);
-        blk.reconverge();
-        dpt_forward_flat32(P.V, norm, small ? 0 : n, best, A, B, As, Bs);
+        dpt_forward_flat32(P.V, norm, n, best, A, B, As, Bs);
         blk.reconverge();
         if (!valid || nlen < 0) continue;
         ResRec rec;
@@ -851,30 +841,20 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P, uint8_t* sm_norm, uint
             *it.out = rec;
             continue;
         }
-        uint32_t word_len, target;
-        bool reach;
-        if (small) {
-            const uint32_t kn = sm_best[n * stride];
-            word_len = kn >> 7;
-            reach = (kn & 0x40u) == 0;
-            target = 63u - (kn & 0x3Fu);
-        } else {
-            const uint32_t kn = best[n];
-            word_len = dpt_k32_len(kn);
-            reach = dpt_k32_reach(kn);
-            target = dpt_k32_longest(kn);
-        }
+        const uint32_t kn = best[n];
+        const uint32_t word_len = dpt_k32_len(kn);
+        const bool reach = dpt_k32_reach(kn);
         rec.meta = (word_len & 0xFFFFFFu) | (reach ? 0u : RES_UNTOK);
         if (reach) {
             if (word_len <= (uint32_t)RES_INLINE) {
-                dpt_backward_chase(P.V, n, word_len, target, A, B, As, Bs, rec.ids, RES_INLINE);
+                dpt_backward_flat32(P.V, n, best, A, B, As, Bs, rec.ids, RES_INLINE);
             } else {
                 const unsigned long long off = blk.atomic_add_u64_ret(&P.ctl->pool_used, (unsigned long long)word_len);
                 rec.meta |= RES_POOLED;
                 rec.ids[0] = (int32_t)(uint32_t)(off & 0xFFFFFFFFull);
                 rec.ids[1] = (int32_t)(uint32_t)(off >> 32);
                 if ((int64_t)(off + word_len) <= P.pool_cap)
-                    dpt_backward_chase(P.V, n, word_len, target, A, B, As, Bs, P.pool + off, (int64_t)word_len);
+                    dpt_backward_flat32(P.V, n, best, A, B, As, Bs, P.pool + off, (int64_t)word_len);
             }
         }
         *it.out = rec;

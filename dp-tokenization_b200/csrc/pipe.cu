@@ -142,11 +142,8 @@ __global__ void __launch_bounds__(PA_THREADS) k_scan_dedup_bl(const __grid_const
 }
 
 __global__ void __launch_bounds__(PB_THREADS) k_dp_distinct(const __grid_constant__ PipeParams P) {
-    // bytes and keys of the short words: shared memory, interleaved by thread (12.5 KB per CTA)
-    __shared__ uint16_t sm_best[(DPT_FLAT16_MAX + 1) * PB_THREADS];
-    __shared__ uint8_t sm_norm[DPT_FLAT16_MAX * PB_THREADS];
     DevBlk blk;
-    pb_thread(blk, P, sm_norm + threadIdx.x, sm_best + threadIdx.x, PB_THREADS);
+    pb_thread(blk, P);
 }
 
 __global__ void __launch_bounds__(PB_THREADS) k_dp_distinct_long(const __grid_constant__ PipeParams P) {

@@ -165,8 +165,8 @@ class Engine:
         return EncodeResult(ids[:h[0]], lens[:nw], flags[:nw], None, counters, h[0], nw, doc_tok, doc_flags)
 
     # ---- corpus path from HOST buffers: chunked, H2D / kernels / D2H overlapped on several streams ---------------
-    def encode_corpus_host(self, h_text: torch.Tensor, doc_offs: np.ndarray, rule: int, chunk_bytes: int = 16 << 20,
-                           n_streams: int = 4, out_ids: Optional[torch.Tensor] = None) -> "HostResult":
+    def encode_corpus_host(self, h_text: torch.Tensor, doc_offs: np.ndarray, rule: int, chunk_bytes: int = 25 << 20,
+                           n_streams: int = 3, out_ids: Optional[torch.Tensor] = None) -> "HostResult":
         """``h_text``: uint8 HOST tensor (pinned for full speed) of concatenated non-empty documents; ``doc_offs``:
         int64[n_docs+1] numpy array.  The corpus is cut at document boundaries into chunks of about ``chunk_bytes``;
         host->device copies, kernels and device->host copies run on three dedicated streams over a ring of

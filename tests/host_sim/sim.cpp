@@ -241,9 +241,7 @@ int32_t sim_encode_corpus_pipe(void* vv, int32_t rule, const uint8_t* text, int6
     {   // kernels B (no block-level cooperation: run the threads one after the other)
         HostBlk blk{0, 1, nullptr};
         const int64_t g = 37;
-        uint8_t sm_norm[DPT_FLAT16_MAX];
-        uint16_t sm_best[DPT_FLAT16_MAX + 1];
-        pb_thread(blk, P, sm_norm, sm_best, 1);
+        pb_thread(blk, P);
         for (int64_t t = 0; t < g; ++t) pb_long_thread(blk, P, t, g);
     }
     {   // kernel C
