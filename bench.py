@@ -316,7 +316,7 @@ def main():
                "d2h_bytes_per_step": int(4 * r.n_ids + 9 * n_docs + 104 * r.n_chunks),
                "tokens_per_sec": g_tokens * args.steps / float(tt.item()),
                "ms_per_step": 1e3 * float(tt.item()) / args.steps, "chunks": r.n_chunks,
-               "how": "Engine.encode_corpus_host: 25 MB chunks at document boundaries, copy-in / compute / copy-out streams over 3 buffer slots, wall clock"}
+               "how": "Engine.encode_corpus_host: 16 MB ranges at document boundaries, copy-in / compute / copy-out streams, one word table for the whole corpus, wall clock"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------
     cpu = None

@@ -409,6 +409,34 @@ int dpt_encode_corpus(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, i
     return rc ? fail(rc, err) : DPT_OK;
 }
 
+// ---- chunked calls: one word table for all ranges of a corpus that is resident (or arriving) in one buffer ----------
+int64_t dpt_corpus_table_workspace(int64_t n_bytes_total, int64_t word_cap_total, int32_t worst_case) {
+    return dpt::corpus_table_workspace(n_bytes_total, word_cap_total, worst_case);
+}
+int64_t dpt_encode_corpus_range_workspace(int32_t rule, int64_t range_bytes, int64_t range_docs, int64_t word_cap,
+                                          int32_t worst_case) {
+    (void)rule;
+    return dpt::corpus_range_workspace(range_bytes, range_docs, word_cap, worst_case);
+}
+int dpt_encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, int64_t n_bytes_total,
+                            const int64_t* d_doc_offs, int64_t n_docs_total, int64_t byte_begin, int64_t byte_end,
+                            int64_t doc_begin, int64_t doc_end, int32_t reset_table, int64_t table_word_cap, int32_t* d_ids,
+                            int64_t ids_cap, int32_t* d_word_lens, uint8_t* d_word_flags, int64_t word_cap,
+                            int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters, int64_t* d_n_out,
+                            void* d_table_workspace, int64_t table_workspace_bytes, void* d_workspace,
+                            int64_t workspace_bytes, int32_t worst_case, void* stream) {
+    if (int rc = check_ready(v, "dpt_encode_corpus_range")) return rc;
+    if (rule != DPT_RULE_SPM_LLAMA && rule != DPT_RULE_GPT2 && rule != DPT_RULE_LLAMA3)
+        return fail(DPT_EINVAL, "dpt_encode_corpus_range: rule not available on device in this build");
+    std::string err;
+    const int rc = dpt::encode_corpus_range(v, rule, d_text, n_bytes_total, d_doc_offs, n_docs_total, byte_begin, byte_end,
+                                            doc_begin, doc_end, reset_table, n_bytes_total, table_word_cap, d_ids, ids_cap,
+                                            d_word_lens, d_word_flags, word_cap, d_doc_tok_offs, d_doc_flags, d_counters,
+                                            d_n_out, d_table_workspace, table_workspace_bytes, d_workspace, workspace_bytes,
+                                            worst_case, (cudaStream_t)stream, err);
+    return rc ? fail(rc, err) : DPT_OK;
+}
+
 int dpt_lattice_word(const dpt_vocab* v, const uint8_t* d_text, int32_t n_bytes, const uint8_t* d_unit_starts,
                      int32_t* d_len_dp, int32_t* d_pred_offs, int32_t* d_pred, int32_t pred_cap, int32_t* d_n_out,
                      int32_t* d_scratch, void* stream) {

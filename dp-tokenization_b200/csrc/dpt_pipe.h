@@ -83,16 +83,25 @@ struct PipeCtl {  // device-side counters, zeroed by the launcher
     unsigned int ticket_a, ticket_c;
     unsigned int n_pending[4];  // distinct words queued for the DP, by length class (keeps a warp's lanes alike)
     unsigned int n_odd, n_long;
-    unsigned long long pool_used, lp_used, n_words, n_untok, n_too_long;
+    unsigned long long lp_used, n_words, n_untok, n_too_long;
     unsigned long long b_cursor;  // next unclaimed item of kernel B's work list
+};
+
+struct PipePersist {  // survives the launches of one chunked call (same lifetime as the word table)
+    unsigned long long pool_used;
 };
 
 struct PipeParams {
     DptVocabView V;
-    const uint8_t* text;
+    const uint8_t* text;      // the WHOLE corpus buffer; this launch tokenizes [byte_begin, byte_end)
     int64_t n_bytes;
-    const int64_t* doc_offs;  // n_docs + 1, doc_offs[0] == 0, doc_offs[n_docs] == n_bytes
+    const int64_t* doc_offs;  // n_docs + 1, doc_offs[0] == 0, doc_offs[n_docs] == n_bytes (global offsets)
     int64_t n_docs;
+    // the range of this launch: documents [doc_begin, doc_begin + n_docs_local) = bytes [byte_begin, byte_end).
+    // Outputs are range-local (ids from 0, doc_tok_offs[d - doc_begin]); table tags hold corpus-global offsets, so a
+    // chunked call can keep its word table across launches.
+    int64_t byte_begin, byte_end, doc_begin, n_docs_local;
+    PipePersist* persist;
     int32_t* ids;
     int64_t ids_cap;
     int32_t* word_lens;
@@ -110,7 +119,7 @@ struct PipeParams {
     uint32_t* pending;            // 4 length classes x n_slots
     OddWord* odd;                 // odd_cap
     ResRec* odd_res;              // odd_cap
-    int32_t* pool;                // pool_cap ids of words with more than 3 tokens
+    int32_t* pool;                // pool_cap ids of words with more than 7 tokens (persistent, like the table)
     uint32_t* longq;              // n_slots + odd_cap
     uint8_t* lp_norm;             // long-word scratch: lp_cap positions
     uint64_t* lp_best;
@@ -122,6 +131,7 @@ struct PipeParams {
     int64_t odd_cap, pool_cap, lp_cap;
     uint32_t slot_mask;           // n_slots - 1 (power of two, <= 2^30)
     int32_t n_tiles, n_ctiles;
+    int32_t tile_first;           // global index (byte offset / PA_T) of this launch's first tile
     int32_t spm;  // 1: SPM_LLAMA rule; 0: byte-level rules
     int32_t rule;
     int32_t vec_ok;  // word_lens / word_flags are aligned for 16- / 8-byte stores
@@ -306,11 +316,11 @@ DPT_PIPE_FN int64_t pp_spm_word_end_global(const PipeParams& P, int64_t g_ws, in
 template <class Blk, bool kSpm>
 DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, const int tile) {
     const int tid = blk.tid(), nt = blk.nthreads();
-    const int64_t t0 = (int64_t)tile * PA_T;
+    const int64_t t0 = ((int64_t)P.tile_first + tile) * PA_T;
     const int64_t g0 = t0 - PA_HALO;  // global offset of region index 0
-    const int64_t n = P.n_bytes;
+    const int64_t n = P.byte_end;  // nothing at or beyond the end of the range is looked at (it may not be there yet)
     const int tvalid = (int)((n - t0) < PA_T ? (n - t0) : PA_T);
-    const int own_lo = PA_HALO, own_hi = PA_HALO + tvalid;
+    const int own_lo = PA_HALO + (int)(P.byte_begin > t0 ? P.byte_begin - t0 : 0), own_hi = PA_HALO + tvalid;
     constexpr bool spm = kSpm;
 
     // ---- load: coalesced 16-byte loads of the region ------------------------------------------------------
@@ -505,7 +515,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                 const int r = (w << 5) + pp_ctz(amb);
                 amb &= amb - 1;
                 const int64_t d = pp_upper_bound(P.doc_offs, P.n_docs + 1, g0 + r) - 1;
-                if (d >= 0 && d < P.n_docs) P.doc_flags[d] = 1;  // DPT_DF_AMBIGUOUS
+                if (d >= P.doc_begin && d < P.doc_begin + P.n_docs_local) P.doc_flags[d - P.doc_begin] = 1;  // DPT_DF_AMBIGUOUS
             }
         }
     }
@@ -550,7 +560,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                         if ((int)off >= lo && (int)off < hi) {
                             // index of this document = first document of the region + document starts before r
                             const uint32_t before = dord + (uint32_t)pp_popc(dsw & ((1u << (r & 31)) - 1u));
-                            S.stage[off - lo] = REF_BOS | (((uint32_t)S.d_first + before) & REF_INDEX);
+                            S.stage[off - lo] = REF_BOS | ((uint32_t)((int64_t)S.d_first + before - P.doc_begin) & REF_INDEX);
                             S.wlist[off - lo] = (uint16_t)(r | 0x8000);
                         }
                         ++off;
@@ -663,7 +673,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
             if (base + k < P.word_cap) P.refs[base + k] = ref;
             if (!spm && (ref & REF_DOCFIRST)) {
                 const int64_t d = pp_lower_bound(P.doc_offs, P.n_docs + 1, g0 + (int)(S.wlist[k] & 0x7FFFu));
-                if (d < P.n_docs) P.doc_first_word[d] = base + k;
+                if (d >= P.doc_begin && d < P.doc_begin + P.n_docs_local) P.doc_first_word[d - P.doc_begin] = base + k;
             }
         }
         // ---- distinct words claimed in this window -> the DP queues (by length class) -------------------------------
@@ -849,7 +859,7 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
             if (word_len <= (uint32_t)RES_INLINE) {
                 dpt_backward_flat32(P.V, n, best, A, B, As, Bs, rec.ids, RES_INLINE);
             } else {
-                const unsigned long long off = blk.atomic_add_u64_ret(&P.ctl->pool_used, (unsigned long long)word_len);
+                const unsigned long long off = blk.atomic_add_u64_ret(&P.persist->pool_used, (unsigned long long)word_len);
                 rec.meta |= RES_POOLED;
                 rec.ids[0] = (int32_t)(uint32_t)(off & 0xFFFFFFFFull);
                 rec.ids[1] = (int32_t)(uint32_t)(off >> 32);
@@ -891,7 +901,7 @@ DPT_PIPE_FN void pb_long_thread(Blk& blk, const PipeParams& P, int64_t gtid, int
         const bool reach = dpt_key_reach(kn);
         rec.meta = (word_len & 0xFFFFFFu) | (reach ? 0u : RES_UNTOK) | RES_LONG;
         if (reach) {
-            const unsigned long long po = blk.atomic_add_u64_ret(&P.ctl->pool_used, (unsigned long long)word_len);
+            const unsigned long long po = blk.atomic_add_u64_ret(&P.persist->pool_used, (unsigned long long)word_len);
             rec.meta |= RES_POOLED;
             rec.ids[0] = (int32_t)(uint32_t)(po & 0xFFFFFFFFull);
             rec.ids[1] = (int32_t)(uint32_t)(po >> 32);
@@ -1031,10 +1041,10 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
             const uint32_t kind = ref[k] & REF_KIND;
             if (kind == REF_BOS) {
                 const int64_t d = (int64_t)(ref[k] & REF_INDEX);
-                if (d < P.n_docs) P.doc_tok_offs[d] = gt;
+                if (d < P.n_docs_local) P.doc_tok_offs[d] = gt;
             } else if (ref[k] & REF_DOCFIRST) {  // byte-level rules: first word of a document
-                const int64_t d = pp_lower_bound(P.doc_first_word, P.n_docs, w0 + k);
-                if (d < P.n_docs) P.doc_tok_offs[d] = gt;
+                const int64_t d = pp_lower_bound(P.doc_first_word, P.n_docs_local, w0 + k);
+                if (d < P.n_docs_local) P.doc_tok_offs[d] = gt;
             }
             if (!(meta[k] & RES_UNTOK)) gt += meta[k] & 0xFFFFFFu;
         }
@@ -1064,7 +1074,7 @@ DPT_PIPE_FN void pd_finish(const PipeParams& P) {
     const int64_t n_words = n_words_true < P.word_cap ? n_words_true : P.word_cap;
     const int64_t n_ctiles = (n_words + PC_TILE - 1) / PC_TILE;
     const unsigned long long tot = n_ctiles > 0 ? (P.desc_t[n_ctiles - 1] & PD_MASK) : 0ull;
-    P.counters[0] = (unsigned long long)P.n_bytes;
+    P.counters[0] = (unsigned long long)(P.byte_end - P.byte_begin);
     P.counters[1] = (unsigned long long)n_words_true;
     P.counters[2] = tot;
     P.counters[3] = P.ctl->n_untok;
@@ -1072,11 +1082,11 @@ DPT_PIPE_FN void pd_finish(const PipeParams& P) {
     P.n_out[1] = n_words_true;             // DPT_NOUT_WORDS
     P.n_out[2] = (int64_t)P.ctl->lp_used;  // DPT_NOUT_POOL_REQ  (long-word scratch positions)
     P.n_out[3] = P.lp_cap;                 // DPT_NOUT_POOL_CAP
-    P.n_out[4] = (int64_t)P.ctl->pool_used;  // ids pool required
+    P.n_out[4] = (int64_t)P.persist->pool_used;  // ids pool required
     P.n_out[5] = P.pool_cap;
     P.n_out[6] = (int64_t)P.ctl->n_odd;    // odd words required
     P.n_out[7] = P.odd_cap;
-    P.doc_tok_offs[P.n_docs] = (int64_t)tot;
+    P.doc_tok_offs[P.n_docs_local] = (int64_t)tot;
 }
 
 }  // namespace dpt

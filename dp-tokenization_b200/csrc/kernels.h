@@ -25,6 +25,17 @@ struct ProfScope {
 
 // corpus pipeline (pipe.cu / dpt_pipe.h): scan+dedup -> DP per distinct word -> scan+emit; asynchronous
 int64_t encode_corpus_pipe_workspace(int64_t n_bytes, int64_t n_docs, int64_t word_cap, int32_t worst);
+int64_t corpus_table_workspace(int64_t n_bytes_total, int64_t word_cap_total, int32_t worst);
+int64_t corpus_range_workspace(int64_t range_bytes, int64_t range_docs, int64_t word_cap, int32_t worst);
+// one range [byte_begin, byte_end) = documents [doc_begin, doc_end) of a corpus resident in d_text; the word table in
+// d_table_ws is kept from the previous range of the same call unless reset_table
+int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, int64_t n_bytes_total,
+                        const int64_t* d_doc_offs, int64_t n_docs_total, int64_t byte_begin, int64_t byte_end,
+                        int64_t doc_begin, int64_t doc_end, int32_t reset_table, int64_t table_bytes_total,
+                        int64_t table_word_cap, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens, uint8_t* d_word_flags,
+                        int64_t word_cap, int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters,
+                        int64_t* d_n_out, void* d_table_ws, int64_t table_ws_bytes, void* d_ws, int64_t ws_bytes,
+                        int32_t worst, cudaStream_t st, std::string& err);
 int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, int64_t n_bytes, const int64_t* d_doc_offs,
                        int64_t n_docs, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens, uint8_t* d_word_flags,
                        int64_t word_cap, int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters,

@@ -163,48 +163,73 @@ __global__ void k_pipe_finish(const __grid_constant__ PipeParams P) {
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
-struct PipeSizes {
-    int64_t n_tiles, n_ctiles, n_slots, odd_cap, pool_cap, lp_cap;
+// Workspace = a TABLE part (word table, result records, id pool, DP queues: lives as long as the table, i.e. one
+// call or the chunks of one chunked call) + a RANGE part (everything private to one launch sequence).
+struct TableSizes {
+    int64_t n_slots, pool_cap;
+};
+struct RangeSizes {
+    int64_t n_tiles, n_ctiles, odd_cap, lp_cap;
 };
 
-static PipeSizes pipe_sizes(int64_t n_bytes, int64_t word_cap, int worst) {
-    PipeSizes z;
-    z.n_tiles = (n_bytes + PA_T - 1) / PA_T;
-    z.n_ctiles = (word_cap + PC_TILE - 1) / PC_TILE;
-    int64_t want = worst ? word_cap : n_bytes / 48;
+static TableSizes table_sizes(int64_t n_bytes_total, int64_t word_cap_total, int worst) {
+    TableSizes z;
+    int64_t want = worst ? word_cap_total : n_bytes_total / 48;
     if (want < 4096) want = 4096;
     int64_t s = 4096;
     while (s < want) s <<= 1;
     z.n_slots = s;
-    z.odd_cap = worst ? word_cap + 16 : n_bytes / 64 + 4096;
-    z.pool_cap = worst ? 6 * n_bytes + 3 * word_cap + 64 : n_bytes / 4 + 65536;
-    z.lp_cap = worst ? 6 * n_bytes + 8 * word_cap + 64 : n_bytes / 4 + 262144;
+    z.pool_cap = worst ? 6 * n_bytes_total + 3 * word_cap_total + 64 : n_bytes_total / 4 + 65536;
+    return z;
+}
+static RangeSizes range_sizes(int64_t range_bytes, int64_t word_cap, int worst) {
+    RangeSizes z;
+    z.n_tiles = (range_bytes + PA_T - 1) / PA_T + 1;  // +1: a range need not start on a tile boundary
+    z.n_ctiles = (word_cap + PC_TILE - 1) / PC_TILE;
+    z.odd_cap = worst ? word_cap + 16 : range_bytes / 64 + 4096;
+    z.lp_cap = worst ? 6 * range_bytes + 8 * word_cap + 64 : range_bytes / 4 + 262144;
     return z;
 }
 
-int64_t encode_corpus_pipe_workspace(int64_t n_bytes, int64_t n_docs, int64_t word_cap, int32_t worst) {
-    const PipeSizes z = pipe_sizes(n_bytes, word_cap, worst);
+int64_t corpus_table_workspace(int64_t n_bytes_total, int64_t word_cap_total, int32_t worst) {
+    const TableSizes z = table_sizes(n_bytes_total, word_cap_total, worst);
+    int64_t b = 0;
+    b += align_up(sizeof(PipePersist), 256);
+    b += align_up(z.n_slots * 8, 256);    // tags
+    b += align_up(z.n_slots * 32, 256);   // res
+    b += align_up(z.n_slots * 16, 256);   // pending (4 length classes)
+    b += align_up(z.pool_cap * 4, 256);   // pool
+    return b + 1024;
+}
+
+int64_t corpus_range_workspace(int64_t range_bytes, int64_t range_docs, int64_t word_cap, int32_t worst) {
+    const RangeSizes z = range_sizes(range_bytes, word_cap, worst);
     int64_t b = 0;
     b += align_up(sizeof(PipeCtl), 256);
     b += align_up(z.n_tiles * 8 + 8, 256) + align_up(z.n_ctiles * 8 + 8, 256);
-    b += align_up(z.n_slots * 8, 256);                       // tags
-    b += align_up(z.n_slots * 32, 256);                      // res
-    b += align_up(z.n_slots * 16, 256);                      // pending (4 length classes)
     b += align_up(word_cap * 4 + 64, 256);                   // refs
-    b += align_up((n_docs + 1) * 8, 256);                    // doc_first_word
+    b += align_up((range_docs + 1) * 8, 256);                // doc_first_word
     b += align_up(z.odd_cap * 16, 256) + align_up(z.odd_cap * 32, 256);  // odd, odd_res
-    b += align_up(z.pool_cap * 4, 256);                      // pool
-    b += align_up((z.n_slots + z.odd_cap) * 4, 256);         // longq
+    b += align_up((word_cap + z.odd_cap) * 4, 256);          // longq
     b += align_up(z.lp_cap, 256) + align_up(z.lp_cap * 8, 256) + 2 * align_up(z.lp_cap * 2, 256);
     return b + 4096;
 }
 
-int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, int64_t n_bytes, const int64_t* d_doc_offs,
-                       int64_t n_docs, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens, uint8_t* d_word_flags,
-                       int64_t word_cap, int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters,
-                       int64_t* d_n_out, void* d_ws, int64_t ws_bytes, int32_t worst, cudaStream_t st, std::string& err) {
-    if (n_bytes <= 0 || n_docs <= 0 || word_cap <= 0 || !d_text || !d_doc_offs || !d_doc_tok_offs || !d_counters ||
-        !d_n_out || !d_ids || !d_word_lens || !d_word_flags) {
+int64_t encode_corpus_pipe_workspace(int64_t n_bytes, int64_t n_docs, int64_t word_cap, int32_t worst) {
+    return corpus_table_workspace(n_bytes, word_cap, worst) + corpus_range_workspace(n_bytes, n_docs, word_cap, worst);
+}
+
+int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, int64_t n_bytes_total,
+                        const int64_t* d_doc_offs, int64_t n_docs_total, int64_t byte_begin, int64_t byte_end,
+                        int64_t doc_begin, int64_t doc_end, int32_t reset_table, int64_t table_bytes_total,
+                        int64_t table_word_cap, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens, uint8_t* d_word_flags,
+                        int64_t word_cap, int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters,
+                        int64_t* d_n_out, void* d_table_ws, int64_t table_ws_bytes, void* d_ws, int64_t ws_bytes,
+                        int32_t worst, cudaStream_t st, std::string& err) {
+    const int64_t range_bytes = byte_end - byte_begin, range_docs = doc_end - doc_begin;
+    if (n_bytes_total <= 0 || n_docs_total <= 0 || word_cap <= 0 || range_bytes <= 0 || range_docs <= 0 || byte_begin < 0 ||
+        byte_end > n_bytes_total || doc_begin < 0 || doc_end > n_docs_total || !d_text || !d_doc_offs || !d_doc_tok_offs ||
+        !d_counters || !d_n_out || !d_ids || !d_word_lens || !d_word_flags) {
         err = "encode_corpus: bad argument";
         return DPT_EINVAL;
     }
@@ -217,15 +242,21 @@ int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, 
         err = "encode_corpus(GPT2/LLAMA3): byte-level rules need a byte-unit vocabulary (DPT_UNIT_BYTES)";
         return DPT_EINVAL;
     }
-    if (n_bytes >= (1ll << 37) || word_cap >= (1ll << 29) || n_docs >= (1ll << 29)) {
+    if (n_bytes_total >= (1ll << 37) || word_cap >= (1ll << 29) || range_docs >= (1ll << 29)) {
         err = "encode_corpus: batch too large (>= 128 GiB, >= 2^29 words or >= 2^29 documents); split it";
         return DPT_EINVAL;
     }
-    if (!d_ws || ws_bytes < encode_corpus_pipe_workspace(n_bytes, n_docs, word_cap, worst)) {
-        err = "encode_corpus: workspace too small (see dpt_encode_corpus_workspace)";
+    if (!d_ws || !d_table_ws || ws_bytes < corpus_range_workspace(range_bytes, range_docs, word_cap, worst) ||
+        table_ws_bytes < corpus_table_workspace(table_bytes_total, table_word_cap, worst)) {
+        err = "encode_corpus: workspace too small (see dpt_encode_corpus_workspace / dpt_corpus_table_workspace)";
         return DPT_ECAPACITY;
     }
-    const PipeSizes z = pipe_sizes(n_bytes, word_cap, worst);
+    const TableSizes tz = table_sizes(table_bytes_total, table_word_cap, worst);
+    const RangeSizes z = range_sizes(range_bytes, word_cap, worst);
+    if (tz.n_slots > (1ll << 29)) {
+        err = "encode_corpus: word table too large; split the batch";
+        return DPT_EINVAL;
+    }
     static int sm_count = 0;
     if (!sm_count) {
         int dev = 0;
@@ -233,20 +264,16 @@ int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, 
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
         if (sm_count <= 0) sm_count = 148;
     }
-    char* base = (char*)d_ws;
-    int64_t used = 0;
-    auto take = [&](int64_t bytes) {
-        used = align_up(used, 256);
-        char* p = base + used;
-        used += bytes;
-        return p;
-    };
     PipeParams P{};
     P.V = v->d_view;
     P.text = d_text;
-    P.n_bytes = n_bytes;
+    P.n_bytes = n_bytes_total;
     P.doc_offs = d_doc_offs;
-    P.n_docs = n_docs;
+    P.n_docs = n_docs_total;
+    P.byte_begin = byte_begin;
+    P.byte_end = byte_end;
+    P.doc_begin = doc_begin;
+    P.n_docs_local = range_docs;
     P.ids = d_ids;
     P.ids_cap = ids_cap;
     P.word_lens = d_word_lens;
@@ -256,43 +283,64 @@ int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, 
     P.doc_flags = d_doc_flags;
     P.counters = (unsigned long long*)d_counters;
     P.n_out = d_n_out;
-    // everything that must start zeroed is contiguous: one memset
-    char* zero0 = take(0);
-    P.ctl = (PipeCtl*)take(sizeof(PipeCtl));
-    P.desc_w = (unsigned long long*)take(z.n_tiles * 8 + 8);
-    P.desc_t = (unsigned long long*)take(z.n_ctiles * 8 + 8);
-    P.tags = (unsigned long long*)take(z.n_slots * 8);
-    const int64_t zero_bytes = (base + used) - zero0;
-    P.res = (ResRec*)take(z.n_slots * 32);
-    P.pending = (uint32_t*)take(z.n_slots * 16);
-    P.refs = (uint32_t*)take(word_cap * 4 + 64);
-    P.doc_first_word = (int64_t*)take((n_docs + 1) * 8);
-    P.odd = (OddWord*)take(z.odd_cap * 16);
-    P.odd_res = (ResRec*)take(z.odd_cap * 32);
-    P.pool = (int32_t*)take(z.pool_cap * 4);
-    P.longq = (uint32_t*)take((z.n_slots + z.odd_cap) * 4);
-    P.lp_norm = (uint8_t*)take(z.lp_cap);
-    P.lp_best = (uint64_t*)take(z.lp_cap * 8);
-    P.lp_a = (uint16_t*)take(z.lp_cap * 2);
-    P.lp_b = (uint16_t*)take(z.lp_cap * 2);
-    P.odd_cap = z.odd_cap;
-    P.pool_cap = z.pool_cap;
-    P.lp_cap = z.lp_cap;
-    P.slot_mask = (uint32_t)(z.n_slots - 1);
-    P.n_tiles = (int32_t)z.n_tiles;
+    {   // table part: PipePersist + tags first, so a reset is one memset
+        char* base = (char*)d_table_ws;
+        int64_t used = 0;
+        auto take = [&](int64_t bytes) {
+            used = align_up(used, 256);
+            char* p = base + used;
+            used += bytes;
+            return p;
+        };
+        P.persist = (PipePersist*)take(sizeof(PipePersist));
+        P.tags = (unsigned long long*)take(tz.n_slots * 8);
+        const int64_t zero_bytes = used;
+        P.res = (ResRec*)take(tz.n_slots * 32);
+        P.pending = (uint32_t*)take(tz.n_slots * 16);
+        P.pool = (int32_t*)take(tz.pool_cap * 4);
+        P.pool_cap = tz.pool_cap;
+        P.slot_mask = (uint32_t)(tz.n_slots - 1);
+        if (reset_table) cudaMemsetAsync(base, 0, (size_t)zero_bytes, st);
+    }
+    {   // range part: everything that must start zeroed is contiguous
+        char* base = (char*)d_ws;
+        int64_t used = 0;
+        auto take = [&](int64_t bytes) {
+            used = align_up(used, 256);
+            char* p = base + used;
+            used += bytes;
+            return p;
+        };
+        P.ctl = (PipeCtl*)take(sizeof(PipeCtl));
+        P.desc_w = (unsigned long long*)take(z.n_tiles * 8 + 8);
+        P.desc_t = (unsigned long long*)take(z.n_ctiles * 8 + 8);
+        const int64_t zero_bytes = used;
+        P.refs = (uint32_t*)take(word_cap * 4 + 64);
+        P.doc_first_word = (int64_t*)take((range_docs + 1) * 8);
+        P.odd = (OddWord*)take(z.odd_cap * 16);
+        P.odd_res = (ResRec*)take(z.odd_cap * 32);
+        P.longq = (uint32_t*)take((word_cap + z.odd_cap) * 4);
+        P.lp_norm = (uint8_t*)take(z.lp_cap);
+        P.lp_best = (uint64_t*)take(z.lp_cap * 8);
+        P.lp_a = (uint16_t*)take(z.lp_cap * 2);
+        P.lp_b = (uint16_t*)take(z.lp_cap * 2);
+        P.odd_cap = z.odd_cap;
+        P.lp_cap = z.lp_cap;
+        cudaMemsetAsync(base, 0, (size_t)zero_bytes, st);
+    }
+    P.tile_first = (int32_t)(byte_begin / PA_T);
+    P.n_tiles = (int32_t)((byte_end + PA_T - 1) / PA_T - byte_begin / PA_T);
     P.n_ctiles = (int32_t)z.n_ctiles;
     P.spm = rule == DPT_RULE_SPM_LLAMA ? 1 : 0;
     P.rule = rule;
     P.vec_ok = ((((uintptr_t)d_word_lens) & 15u) == 0 && (((uintptr_t)d_word_flags) & 7u) == 0) ? 1 : 0;
-
-    cudaMemsetAsync(zero0, 0, (size_t)zero_bytes, st);
-    if (d_doc_flags) cudaMemsetAsync(d_doc_flags, 0, (size_t)n_docs, st);
+    if (d_doc_flags) cudaMemsetAsync(d_doc_flags, 0, (size_t)range_docs, st);
     {
         ProfScope prof(P.spm ? "k_scan_dedup" : "k_scan_dedup_bl", st);
         if (P.spm)
-            k_scan_dedup<<<(unsigned)z.n_tiles, PA_THREADS, 0, st>>>(P);
+            k_scan_dedup<<<(unsigned)P.n_tiles, PA_THREADS, 0, st>>>(P);
         else
-            k_scan_dedup_bl<<<(unsigned)z.n_tiles, PA_THREADS, 0, st>>>(P);
+            k_scan_dedup_bl<<<(unsigned)P.n_tiles, PA_THREADS, 0, st>>>(P);
         ++g_launches;
     }
     {
@@ -321,6 +369,25 @@ int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, 
         return DPT_ECUDA;
     }
     return DPT_OK;
+}
+
+int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, int64_t n_bytes, const int64_t* d_doc_offs,
+                       int64_t n_docs, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens, uint8_t* d_word_flags,
+                       int64_t word_cap, int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters,
+                       int64_t* d_n_out, void* d_ws, int64_t ws_bytes, int32_t worst, cudaStream_t st, std::string& err) {
+    if (n_bytes <= 0 || n_docs <= 0 || word_cap <= 0 || !d_ws) {
+        err = "encode_corpus: bad argument";
+        return DPT_EINVAL;
+    }
+    const int64_t tb = corpus_table_workspace(n_bytes, word_cap, worst);
+    if (ws_bytes < tb + corpus_range_workspace(n_bytes, n_docs, word_cap, worst)) {
+        err = "encode_corpus: workspace too small (see dpt_encode_corpus_workspace)";
+        return DPT_ECAPACITY;
+    }
+    const int64_t tb_al = align_up(tb, 256);
+    return encode_corpus_range(v, rule, d_text, n_bytes, d_doc_offs, n_docs, 0, n_bytes, 0, n_docs, 1, n_bytes, word_cap, d_ids,
+                               ids_cap, d_word_lens, d_word_flags, word_cap, d_doc_tok_offs, d_doc_flags, d_counters, d_n_out,
+                               d_ws, tb_al, (char*)d_ws + tb_al, ws_bytes - tb_al, worst, st, err);
 }
 
 }  // namespace dpt

@@ -164,20 +164,20 @@ class Engine:
         nw = h[_cabi.NOUT_WORDS]
         return EncodeResult(ids[:h[0]], lens[:nw], flags[:nw], None, counters, h[0], nw, doc_tok, doc_flags)
 
-    # ---- corpus path from HOST buffers: chunked, H2D / kernels / D2H overlapped on several streams ---------------
-    def encode_corpus_host(self, h_text: torch.Tensor, doc_offs: np.ndarray, rule: int, chunk_bytes: int = 25 << 20,
+    # ---- corpus path from HOST buffers: chunked, H2D / kernels / D2H overlapped ---------------------------------------
+    def encode_corpus_host(self, h_text: torch.Tensor, doc_offs: np.ndarray, rule: int, chunk_bytes: int = 16 << 20,
                            n_streams: int = 3, out_ids: Optional[torch.Tensor] = None) -> "HostResult":
         """``h_text``: uint8 HOST tensor (pinned for full speed) of concatenated non-empty documents; ``doc_offs``:
-        int64[n_docs+1] numpy array.  The corpus is cut at document boundaries into chunks of about ``chunk_bytes``;
-        host->device copies, kernels and device->host copies run on three dedicated streams over a ring of
-        ``n_streams`` buffer slots, so PCIe in both directions and the SMs work at the same time.  Returns host
-        tensors."""
+        int64[n_docs+1] numpy array.  The corpus is cut at document boundaries into ranges of about ``chunk_bytes``.
+        Range k is copied into its place in ONE device text buffer on the copy-in stream, tokenized by
+        ``dpt_encode_corpus_range`` on the compute stream (the word table is shared by all ranges of the call, so a
+        word is still solved once per corpus) and its ids are copied out on the copy-out stream over a ring of
+        ``n_streams`` output slots: PCIe in both directions and the SMs work at the same time.  Returns host tensors."""
         assert h_text.dtype == torch.uint8 and not h_text.is_cuda
         doc_offs = np.ascontiguousarray(doc_offs, dtype=np.int64)
         n_docs = len(doc_offs) - 1
         n_bytes = int(doc_offs[-1])
         dev = self.device
-        # chunk boundaries (document indices)
         cuts = [0]
         while cuts[-1] < n_docs:
             target = doc_offs[cuts[-1]] + chunk_bytes
@@ -188,41 +188,48 @@ class Engine:
         max_d = max(cuts[k + 1] - cuts[k] for k in range(n_chunks))
         ids_cap = max_b // 2 + 2 * max_d + 64
         word_cap = max_b // 3 + 2 * max_d + 64
+        word_cap_total = n_bytes // 3 + 2 * n_docs + 64
         if out_ids is None:
             out_ids = torch.empty(n_bytes // 2 + 2 * n_docs + 64, dtype=torch.int32).pin_memory()
         out_doc_tok = np.zeros(n_docs + 1, dtype=np.int64)
         out_doc_flags = np.zeros(n_docs, dtype=np.uint8)
         totals = np.zeros(4, dtype=np.int64)
         with torch.cuda.device(dev):
-            key = (rule, max_b, max_d, n_streams)
-            if getattr(self, "_host_slots_key", None) != key:
-                ws_bytes = lib.dpt_encode_corpus_workspace(rule, max_b, max_d, word_cap, 0)
-                self._host_streams = [torch.cuda.Stream(device=dev) for _ in range(3)]  # copy-in, compute, copy-out
-                self._host_slots = []
-                for _ in range(n_streams):
-                    self._host_slots.append(dict(
-                        ev_in=torch.cuda.Event(), ev_comp=torch.cuda.Event(), ev_out=torch.cuda.Event(),
-                        d_text=torch.empty(max_b, dtype=torch.uint8, device=dev),
-                        d_offs=torch.empty(max_d + 1, dtype=torch.int64, device=dev),
-                        h_offs=torch.empty(max_d + 1, dtype=torch.int64).pin_memory(),
-                        ids=torch.empty(ids_cap, dtype=torch.int32, device=dev),
-                        lens=torch.empty(word_cap, dtype=torch.int32, device=dev),
-                        flags=torch.empty(word_cap, dtype=torch.uint8, device=dev),
-                        doc_tok=torch.empty(max_d + 1, dtype=torch.int64, device=dev),
-                        doc_flags=torch.empty(max_d, dtype=torch.uint8, device=dev),
-                        counters=torch.empty(4, dtype=torch.int64, device=dev),
-                        n_out=torch.empty(8, dtype=torch.int64, device=dev),
-                        h_small=torch.empty(12, dtype=torch.int64).pin_memory(),
-                        h_doc_tok=torch.empty(max_d + 1, dtype=torch.int64).pin_memory(),
-                        h_doc_flags=torch.empty(max_d, dtype=torch.uint8).pin_memory(),
-                        ws=torch.empty(int(ws_bytes), dtype=torch.uint8, device=dev)))
-                self._host_slots_key = key
-            slots = self._host_slots
-            s_in, s_comp, s_out = self._host_streams
+            key = (rule, n_bytes, n_docs, max_b, max_d, n_streams)
+            if getattr(self, "_host_key", None) != key:
+                self._host = None
+                ws_bytes = lib.dpt_encode_corpus_range_workspace(rule, max_b, max_d, word_cap, 0)
+                tws_bytes = lib.dpt_corpus_table_workspace(n_bytes, word_cap_total, 0)
+                self._host = dict(
+                    streams=[torch.cuda.Stream(device=dev) for _ in range(3)],  # copy-in, compute, copy-out
+                    d_text=torch.empty(n_bytes, dtype=torch.uint8, device=dev),
+                    d_offs=torch.empty(n_docs + 1, dtype=torch.int64, device=dev),
+                    h_offs=torch.empty(n_docs + 1, dtype=torch.int64).pin_memory(),
+                    table_ws=torch.empty(int(tws_bytes), dtype=torch.uint8, device=dev),
+                    slots=[dict(ev_in=torch.cuda.Event(), ev_comp=torch.cuda.Event(), ev_out=torch.cuda.Event(),
+                                ids=torch.empty(ids_cap, dtype=torch.int32, device=dev),
+                                lens=torch.empty(word_cap, dtype=torch.int32, device=dev),
+                                flags=torch.empty(word_cap, dtype=torch.uint8, device=dev),
+                                doc_tok=torch.empty(max_d + 1, dtype=torch.int64, device=dev),
+                                doc_flags=torch.empty(max_d, dtype=torch.uint8, device=dev),
+                                counters=torch.empty(4, dtype=torch.int64, device=dev),
+                                n_out=torch.empty(8, dtype=torch.int64, device=dev),
+                                h_small=torch.empty(12, dtype=torch.int64).pin_memory(),
+                                h_doc_tok=torch.empty(max_d + 1, dtype=torch.int64).pin_memory(),
+                                h_doc_flags=torch.empty(max_d, dtype=torch.uint8).pin_memory(),
+                                ws=torch.empty(int(ws_bytes), dtype=torch.uint8, device=dev)) for _ in range(n_streams)])
+                self._host_key = key
+            H = self._host
+            slots = H["slots"]
+            s_in, s_comp, s_out = H["streams"]
             cur = torch.cuda.current_stream(dev)
             for st in (s_in, s_comp, s_out):
                 st.wait_stream(cur)
+            H["h_offs"].copy_(torch.from_numpy(doc_offs))
+            with torch.cuda.stream(s_in):
+                H["d_offs"].copy_(H["h_offs"], non_blocking=True)
             ids_base = 0
+            overflow = False
             pending = []  # (chunk index, slot), in order
             trace = getattr(self, "_trace", None)
 
@@ -234,67 +241,69 @@ class Engine:
                     trace.append((name, k, ev, _t.perf_counter()))
 
             def finalize(k, sl):
-                nonlocal ids_base
+                nonlocal ids_base, overflow
                 lo, hi = cuts[k], cuts[k + 1]
                 nd = hi - lo
-                sl["ev_comp"].synchronize()                 # status vector + document offsets of chunk k are on the host
+                sl["ev_comp"].synchronize()                 # status vector + document offsets of range k are on the host
                 h = sl["h_small"].tolist()
                 if h[1] > word_cap or h[0] > ids_cap or h[2] > h[3] or h[4] > h[5] or h[6] > h[7]:
-                    # a capacity was exceeded: redo this chunk through the retrying device-resident path
-                    b0, b1 = int(doc_offs[lo]), int(doc_offs[hi])
-                    res = self.encode_corpus(h_text[b0:b1].to(dev), torch.from_numpy(doc_offs[lo:hi + 1] - b0).to(dev), rule)
-                    n_ids = res.n_ids
-                    out_ids[ids_base:ids_base + n_ids].copy_(res.ids)
-                    out_doc_tok[lo:hi] = res.doc_tok_offs[:nd].cpu().numpy() + ids_base
-                    out_doc_flags[lo:hi] = res.doc_flags.cpu().numpy()
-                    totals[:] += np.asarray(res.counters.cpu().tolist(), dtype=np.int64)
+                    overflow = True                         # a capacity was exceeded: the whole corpus is redone below
                     sl["ev_out"].record(s_out)
-                else:
-                    n_ids = h[0]
-                    with torch.cuda.stream(s_out):          # the host has seen ev_comp: the ids are complete
-                        mark("d2h-begin", k, s_out)
-                        out_ids[ids_base:ids_base + n_ids].copy_(sl["ids"][:n_ids], non_blocking=True)
-                        sl["ev_out"].record(s_out)
-                        mark("d2h-end", k, s_out)
-                    out_doc_tok[lo:hi] = sl["h_doc_tok"][:nd].numpy() + ids_base
-                    out_doc_flags[lo:hi] = sl["h_doc_flags"][:nd].numpy()
-                    totals[:] += np.asarray(h[8:12], dtype=np.int64)
+                    return
+                n_ids = h[0]
+                with torch.cuda.stream(s_out):              # the host has seen ev_comp: the ids are complete
+                    mark("d2h-begin", k, s_out)
+                    out_ids[ids_base:ids_base + n_ids].copy_(sl["ids"][:n_ids], non_blocking=True)
+                    sl["ev_out"].record(s_out)
+                    mark("d2h-end", k, s_out)
+                out_doc_tok[lo:hi] = sl["h_doc_tok"][:nd].numpy() + ids_base
+                out_doc_flags[lo:hi] = sl["h_doc_flags"][:nd].numpy()
+                totals[:] += np.asarray(h[8:12], dtype=np.int64)
                 ids_base += n_ids
 
             for k in range(n_chunks):
                 sl = slots[k % n_streams]
-                if len(pending) >= n_streams:               # the slot's previous chunk must have left the GPU
+                if len(pending) >= n_streams:               # the slot's previous range must have left the GPU
                     finalize(*pending.pop(0))
                 lo, hi = cuts[k], cuts[k + 1]
                 b0, b1 = int(doc_offs[lo]), int(doc_offs[hi])
-                nb, nd = b1 - b0, hi - lo
-                sl["h_offs"][:nd + 1].copy_(torch.from_numpy(doc_offs[lo:hi + 1] - b0))
-                with torch.cuda.stream(s_in):               # copy-in engine: chunk after chunk, never behind a copy-out
-                    s_in.wait_event(sl["ev_comp"])          # the slot's text is no longer being read
+                with torch.cuda.stream(s_in):               # copy-in engine: range after range
                     mark("h2d-begin", k, s_in)
-                    sl["d_text"][:nb].copy_(h_text[b0:b1], non_blocking=True)
-                    sl["d_offs"][:nd + 1].copy_(sl["h_offs"][:nd + 1], non_blocking=True)
+                    H["d_text"][b0:b1].copy_(h_text[b0:b1], non_blocking=True)
                     sl["ev_in"].record(s_in)
                     mark("h2d-end", k, s_in)
                 with torch.cuda.stream(s_comp):
                     s_comp.wait_event(sl["ev_in"])
-                    s_comp.wait_event(sl["ev_out"])         # the slot's ids have been copied out
+                    s_comp.wait_event(sl["ev_out"])         # the slot's previous ids have been copied out
                     mark("comp-begin", k, s_comp)
-                    check(lib.dpt_encode_corpus(self.vocab.handle, rule, _ptr(sl["d_text"]), nb, _ptr(sl["d_offs"]), nd,
-                                                _ptr(sl["ids"]), ids_cap, _ptr(sl["lens"]), _ptr(sl["flags"]), word_cap,
-                                                _ptr(sl["doc_tok"]), _ptr(sl["doc_flags"]), _ptr(sl["counters"]),
-                                                _ptr(sl["n_out"]), _ptr(sl["ws"]), sl["ws"].numel(), 0,
-                                                C.c_void_p(s_comp.cuda_stream)))
+                    check(lib.dpt_encode_corpus_range(
+                        self.vocab.handle, rule, _ptr(H["d_text"]), n_bytes, _ptr(H["d_offs"]), n_docs, b0, b1, lo, hi,
+                        1 if k == 0 else 0, word_cap_total, _ptr(sl["ids"]), ids_cap, _ptr(sl["lens"]), _ptr(sl["flags"]),
+                        word_cap, _ptr(sl["doc_tok"]), _ptr(sl["doc_flags"]), _ptr(sl["counters"]), _ptr(sl["n_out"]),
+                        _ptr(H["table_ws"]), H["table_ws"].numel(), _ptr(sl["ws"]), sl["ws"].numel(), 0,
+                        C.c_void_p(s_comp.cuda_stream)))
                     sl["h_small"][:8].copy_(sl["n_out"], non_blocking=True)
                     sl["h_small"][8:12].copy_(sl["counters"], non_blocking=True)
-                    sl["h_doc_tok"][:nd + 1].copy_(sl["doc_tok"][:nd + 1], non_blocking=True)
-                    sl["h_doc_flags"][:nd].copy_(sl["doc_flags"][:nd], non_blocking=True)
+                    sl["h_doc_tok"][:hi - lo + 1].copy_(sl["doc_tok"][:hi - lo + 1], non_blocking=True)
+                    sl["h_doc_flags"][:hi - lo].copy_(sl["doc_flags"][:hi - lo], non_blocking=True)
                     sl["ev_comp"].record(s_comp)
                     mark("comp-end", k, s_comp)
                 pending.append((k, sl))
             while pending:
                 finalize(*pending.pop(0))
             s_out.synchronize()
+            if overflow:
+                # rare: a range exceeded a capacity.  The text is resident: redo the corpus through the retrying
+                # device-resident call and copy the result out.
+                s_comp.synchronize()
+                res = self.encode_corpus(H["d_text"], H["d_offs"], rule)
+                ids_base = res.n_ids
+                if out_ids.numel() < ids_base:
+                    out_ids = torch.empty(ids_base, dtype=torch.int32).pin_memory()
+                out_ids[:ids_base].copy_(res.ids)
+                out_doc_tok[:] = res.doc_tok_offs.cpu().numpy()
+                out_doc_flags[:] = res.doc_flags.cpu().numpy()
+                totals[:] = np.asarray(res.counters.cpu().tolist(), dtype=np.int64)
         out_doc_tok[n_docs] = ids_base
         return HostResult(out_ids[:ids_base], out_doc_tok, out_doc_flags, totals, ids_base, n_chunks)
 

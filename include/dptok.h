@@ -203,6 +203,29 @@ int dpt_encode_corpus(const dpt_vocab* v, int32_t rule,
                       int64_t* d_counters, int64_t* d_n_out,
                       void* d_workspace, int64_t workspace_bytes, int32_t worst_case, void* stream);
 
+/* ---- chunked corpus calls (Engine.encode_corpus_host): the corpus arrives in d_text range by range (ranges cut at
+ *      document boundaries, processed in order on one stream); each call tokenizes documents
+ *      [doc_begin, doc_end) = bytes [byte_begin, byte_end) and may look at bytes BEFORE byte_begin only.  The word
+ *      table lives in d_table_workspace (dpt_corpus_table_workspace, sized for the WHOLE corpus) and is kept from
+ *      the previous range unless reset_table != 0 (pass 1 for the first range): a word is still solved once per
+ *      corpus, not once per chunk.  d_doc_offs holds corpus-global offsets; outputs are range-local exactly as
+ *      dpt_encode_corpus would produce them for the range alone (ids from 0, d_doc_tok_offs[doc_end-doc_begin+1],
+ *      d_doc_flags[doc_end-doc_begin]).  d_workspace: dpt_encode_corpus_range_workspace (per range). */
+int64_t dpt_corpus_table_workspace(int64_t n_bytes_total, int64_t word_cap_total, int32_t worst_case);
+int64_t dpt_encode_corpus_range_workspace(int32_t rule, int64_t range_bytes, int64_t range_docs, int64_t word_cap,
+                                          int32_t worst_case);
+int dpt_encode_corpus_range(const dpt_vocab* v, int32_t rule,
+                            const uint8_t* d_text, int64_t n_bytes_total,
+                            const int64_t* d_doc_offs, int64_t n_docs_total,
+                            int64_t byte_begin, int64_t byte_end, int64_t doc_begin, int64_t doc_end,
+                            int32_t reset_table, int64_t table_word_cap,
+                            int32_t* d_ids, int64_t ids_cap,
+                            int32_t* d_word_lens, uint8_t* d_word_flags, int64_t word_cap,
+                            int64_t* d_doc_tok_offs, uint8_t* d_doc_flags,
+                            int64_t* d_counters, int64_t* d_n_out,
+                            void* d_table_workspace, int64_t table_workspace_bytes,
+                            void* d_workspace, int64_t workspace_bytes, int32_t worst_case, void* stream);
+
 /* ---- the same contract WITHOUT deduplication: normalise -> DP count per word -> scan -> DP emit per word
  *      (what dpt_pretokenize + dpt_encode_words compose to); synchronises the stream once.  Kept as
  *      the independent cross-check of the pipeline above (tests) and for callers who want the

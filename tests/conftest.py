@@ -63,5 +63,5 @@ def host_sim():
     lib.sim_encode_corpus_pipe.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                            C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64,
-                                           C.c_int64, C.c_int64]
+                                           C.c_int64, C.c_int64, C.c_int32]
     return lib

@@ -149,30 +149,15 @@ int64_t sim_spm_normalise(void* vv, const uint8_t* text, int64_t n, const int64_
 // The corpus pipeline's code (dpt_pipe.h): kernel A on `nthreads` host threads emulating one CTA, kernel B as a
 // plain loop over its threads, kernel C on PC_THREADS host threads.  n_slots (power of two, 0 = default) and
 // odd_cap/pool_cap/lp_cap (0 = default) shrink the tables to exercise probe failure and capacity reporting.
-// rule: 1 SPM_LLAMA, 2 GPT2, 3 LLAMA3 (include/dptok.h).
+// rule: 1 SPM_LLAMA, 2 GPT2, 3 LLAMA3 (include/dptok.h).  n_ranges > 1: the corpus is processed as that many
+// consecutive document ranges that share ONE word table (dpt_encode_corpus_range semantics); outputs are stitched.
 int32_t sim_encode_corpus_pipe(void* vv, int32_t rule, const uint8_t* text, int64_t n_bytes, const int64_t* doc_offs,
                                int64_t n_docs, int32_t* ids, int64_t ids_cap, int32_t* word_lens, uint8_t* word_flags,
                                int64_t word_cap, int64_t* doc_tok_offs, uint8_t* doc_flags, int64_t* counters,
                                int64_t* n_out, int32_t nthreads, int64_t n_slots, int64_t odd_cap, int64_t pool_cap,
-                               int64_t lp_cap) {
+                               int64_t lp_cap, int32_t n_ranges) {
     using namespace dpt;
     dpt_vocab* v = (dpt_vocab*)vv;
-    PipeParams P{};
-    P.V = v->h_view;
-    P.text = text;
-    P.n_bytes = n_bytes;
-    P.doc_offs = doc_offs;
-    P.n_docs = n_docs;
-    P.ids = ids;
-    P.ids_cap = ids_cap;
-    P.word_lens = word_lens;
-    P.word_flags = word_flags;
-    P.word_cap = word_cap;
-    P.doc_tok_offs = doc_tok_offs;
-    P.doc_flags = doc_flags;
-    P.counters = (unsigned long long*)counters;
-    P.n_out = n_out;
-    const int64_t n_tiles = (n_bytes + PA_T - 1) / PA_T, n_ctiles = (word_cap + PC_TILE - 1) / PC_TILE;
     if (n_slots <= 0) {
         n_slots = 4096;
         while (n_slots < n_bytes / 48) n_slots <<= 1;
@@ -180,82 +165,143 @@ int32_t sim_encode_corpus_pipe(void* vv, int32_t rule, const uint8_t* text, int6
     if (odd_cap <= 0) odd_cap = word_cap + 16;
     if (pool_cap <= 0) pool_cap = 6 * n_bytes + 3 * word_cap + 64;
     if (lp_cap <= 0) lp_cap = 6 * n_bytes + 8 * word_cap + 64;
-    PipeCtl ctl{};
-    std::vector<unsigned long long> dw(n_tiles + 1, 0), dt(n_ctiles + 1, 0), tags(n_slots, 0);
-    std::vector<ResRec> res(n_slots), odd_res(odd_cap);
-    std::vector<uint32_t> pending(4 * n_slots), refs(word_cap + 16), longq(n_slots + odd_cap);
-    std::vector<int64_t> dfw(n_docs + 1, -1);
-    std::vector<OddWord> odd(odd_cap);
+    if (n_ranges < 1) n_ranges = 1;
+    if (n_ranges > n_docs) n_ranges = (int32_t)n_docs;
+    // table part: shared by all ranges
+    PipePersist persist{};
+    std::vector<unsigned long long> tags(n_slots, 0);
+    std::vector<ResRec> res(n_slots);
+    std::vector<uint32_t> pending(4 * n_slots);
     std::vector<int32_t> pool(pool_cap);
-    std::vector<uint8_t> lpn(lp_cap);
-    std::vector<uint64_t> lpb(lp_cap);
-    std::vector<uint16_t> lpa(lp_cap), lpbb(lp_cap);
-    P.ctl = &ctl;
-    P.desc_w = dw.data();
-    P.desc_t = dt.data();
-    P.tags = tags.data();
-    P.res = res.data();
-    P.pending = pending.data();
-    P.refs = refs.data();
-    P.doc_first_word = dfw.data();
-    P.odd = odd.data();
-    P.odd_res = odd_res.data();
-    P.pool = pool.data();
-    P.longq = longq.data();
-    P.lp_norm = lpn.data();
-    P.lp_best = lpb.data();
-    P.lp_a = lpa.data();
-    P.lp_b = lpbb.data();
-    P.odd_cap = odd_cap;
-    P.pool_cap = pool_cap;
-    P.lp_cap = lp_cap;
-    P.slot_mask = (uint32_t)(n_slots - 1);
-    P.n_tiles = (int32_t)n_tiles;
-    P.n_ctiles = (int32_t)n_ctiles;
-    P.spm = rule == 1 ? 1 : 0;  // DPT_RULE_SPM_LLAMA
-    P.rule = rule;
-    P.vec_ok = ((((uintptr_t)word_lens) & 15u) == 0 && (((uintptr_t)word_flags) & 7u) == 0) ? 1 : 0;
     memset(counters, 0, 32);
     memset(n_out, 0, 64);
-    if (doc_flags) memset(doc_flags, 0, (size_t)n_docs);
-    {   // kernel A
-        auto run = [&](auto* S) {
-            constexpr bool kSpm = std::is_same_v<std::remove_pointer_t<decltype(S)>, ASmemT<true>>;
-            HostShared sh(nthreads);
+    int64_t ids_base = 0, words_base = 0;
+    for (int32_t rg = 0; rg < n_ranges; ++rg) {
+        const int64_t d0 = n_docs * rg / n_ranges, d1 = n_docs * (rg + 1) / n_ranges;
+        const int64_t b0 = doc_offs[d0], b1 = doc_offs[d1], nd = d1 - d0;
+        PipeParams P{};
+        P.V = v->h_view;
+        P.text = text;
+        P.n_bytes = n_bytes;
+        P.doc_offs = doc_offs;
+        P.n_docs = n_docs;
+        P.byte_begin = b0;
+        P.byte_end = b1;
+        P.doc_begin = d0;
+        P.n_docs_local = nd;
+        P.persist = &persist;
+        // range-local outputs
+        const int64_t r_ids_cap = ids_cap > ids_base ? ids_cap - ids_base : 0, r_word_cap = word_cap - words_base;
+        std::vector<int32_t> r_ids(r_ids_cap + 1), r_lens(r_word_cap + 8);
+        std::vector<uint8_t> r_flags(r_word_cap + 8), r_dflags(nd + 1);
+        std::vector<int64_t> r_dto(nd + 1, -7);
+        int64_t r_ctr[4] = {0, 0, 0, 0}, r_nout[8] = {0};
+        P.ids = r_ids.data();
+        P.ids_cap = r_ids_cap;
+        P.word_lens = r_lens.data();
+        P.word_flags = r_flags.data();
+        P.word_cap = r_word_cap;
+        P.doc_tok_offs = r_dto.data();
+        P.doc_flags = doc_flags ? r_dflags.data() : nullptr;
+        P.counters = (unsigned long long*)r_ctr;
+        P.n_out = r_nout;
+        const int64_t n_tiles = (b1 + PA_T - 1) / PA_T - b0 / PA_T, n_ctiles = (r_word_cap + PC_TILE - 1) / PC_TILE;
+        PipeCtl ctl{};
+        std::vector<unsigned long long> dw(n_tiles + 1, 0), dt(n_ctiles + 1, 0);
+        std::vector<ResRec> odd_res(odd_cap);
+        std::vector<uint32_t> refs(r_word_cap + 16), longq(r_word_cap + odd_cap + 16);
+        std::vector<int64_t> dfw(nd + 1, -1);
+        std::vector<OddWord> odd(odd_cap);
+        std::vector<uint8_t> lpn(lp_cap);
+        std::vector<uint64_t> lpb(lp_cap);
+        std::vector<uint16_t> lpa(lp_cap), lpbb(lp_cap);
+        P.ctl = &ctl;
+        P.desc_w = dw.data();
+        P.desc_t = dt.data();
+        P.tags = tags.data();
+        P.res = res.data();
+        P.pending = pending.data();
+        P.refs = refs.data();
+        P.doc_first_word = dfw.data();
+        P.odd = odd.data();
+        P.odd_res = odd_res.data();
+        P.pool = pool.data();
+        P.longq = longq.data();
+        P.lp_norm = lpn.data();
+        P.lp_best = lpb.data();
+        P.lp_a = lpa.data();
+        P.lp_b = lpbb.data();
+        P.odd_cap = odd_cap;
+        P.pool_cap = pool_cap;
+        P.lp_cap = lp_cap;
+        P.slot_mask = (uint32_t)(n_slots - 1);
+        P.tile_first = (int32_t)(b0 / PA_T);
+        P.n_tiles = (int32_t)n_tiles;
+        P.n_ctiles = (int32_t)n_ctiles;
+        P.spm = rule == 1 ? 1 : 0;  // DPT_RULE_SPM_LLAMA
+        P.rule = rule;
+        P.vec_ok = ((((uintptr_t)P.word_lens) & 15u) == 0 && (((uintptr_t)P.word_flags) & 7u) == 0) ? 1 : 0;
+        {   // kernel A
+            auto run = [&](auto* S) {
+                constexpr bool kSpm = std::is_same_v<std::remove_pointer_t<decltype(S)>, ASmemT<true>>;
+                HostShared sh(nthreads);
+                std::vector<std::thread> th;
+                for (int t = 0; t < nthreads; ++t)
+                    th.emplace_back([&, t] {
+                        HostBlk blk{t, nthreads, &sh};
+                        pa_kernel<HostBlk, kSpm>(blk, P, *S);
+                    });
+                for (auto& x : th) x.join();
+            };
+            if (P.spm) {
+                auto S = std::make_unique<ASmemT<true>>();
+                run(S.get());
+            } else {
+                auto S = std::make_unique<ASmemT<false>>();
+                run(S.get());
+            }
+        }
+        {   // kernels B (no block-level cooperation: run the threads one after the other)
+            HostBlk blk{0, 1, nullptr};
+            const int64_t g = 37;
+            pb_thread(blk, P);
+            for (int64_t t = 0; t < g; ++t) pb_long_thread(blk, P, t, g);
+        }
+        {   // kernel C
+            auto S = std::make_unique<CSmem>();
+            HostShared sh(PC_THREADS);
             std::vector<std::thread> th;
-            for (int t = 0; t < nthreads; ++t)
+            for (int t = 0; t < PC_THREADS; ++t)
                 th.emplace_back([&, t] {
-                    HostBlk blk{t, nthreads, &sh};
-                    pa_kernel<HostBlk, kSpm>(blk, P, *S);
+                    HostBlk blk{t, PC_THREADS, &sh};
+                    pc_kernel(blk, P, *S);
                 });
             for (auto& x : th) x.join();
-        };
-        if (P.spm) {
-            auto S = std::make_unique<ASmemT<true>>();
-            run(S.get());
-        } else {
-            auto S = std::make_unique<ASmemT<false>>();
-            run(S.get());
         }
+        pd_finish(P);
+        // stitch
+        const int64_t nid = r_nout[0] < r_ids_cap ? r_nout[0] : r_ids_cap, nw = r_nout[1] < r_word_cap ? r_nout[1] : r_word_cap;
+        for (int64_t k = 0; k < nid; ++k) ids[ids_base + k] = r_ids[k];
+        for (int64_t k = 0; k < nw; ++k) {
+            word_lens[words_base + k] = r_lens[k];
+            word_flags[words_base + k] = r_flags[k];
+        }
+        for (int64_t d = 0; d < nd; ++d) {
+            doc_tok_offs[d0 + d] = r_dto[d] + ids_base;
+            if (doc_flags) doc_flags[d0 + d] = r_dflags[d];
+        }
+        for (int k = 0; k < 4; ++k) counters[k] += r_ctr[k];
+        n_out[0] += r_nout[0];
+        n_out[1] += r_nout[1];
+        for (int k = 2; k < 8; k += 2)
+            if (rg == 0 || r_nout[k] - r_nout[k + 1] > n_out[k] - n_out[k + 1]) {
+                n_out[k] = r_nout[k];
+                n_out[k + 1] = r_nout[k + 1];
+            }
+        ids_base += r_nout[0];
+        words_base += r_nout[1];
     }
-    {   // kernels B (no block-level cooperation: run the threads one after the other)
-        HostBlk blk{0, 1, nullptr};
-        const int64_t g = 37;
-        pb_thread(blk, P);
-        for (int64_t t = 0; t < g; ++t) pb_long_thread(blk, P, t, g);
-    }
-    {   // kernel C
-        auto S = std::make_unique<CSmem>();
-        HostShared sh(PC_THREADS);
-        std::vector<std::thread> th;
-        for (int t = 0; t < PC_THREADS; ++t)
-            th.emplace_back([&, t] {
-                HostBlk blk{t, PC_THREADS, &sh};
-                pc_kernel(blk, P, *S);
-            });
-        for (auto& x : th) x.join();
-    }
-    pd_finish(P);
+    doc_tok_offs[n_docs] = ids_base;
     return 0;
 }
 }

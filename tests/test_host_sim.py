@@ -138,7 +138,7 @@ def test_spm_rule_matches_reference_pretokenizer(host_sim):
 # by a std::thread emulation of CUDA blocks, against (a) the general path's rule + the C oracle and (b) the
 # reference-shaped normaliser.
 # ------------------------------------------------------------------------------------------------
-def _run_fused(host_sim, h, spm, docs, nthreads=4, n_slots=0, ids_cap=None, odd_cap=0, pool_cap=0, lp_cap=0):
+def _run_fused(host_sim, h, spm, docs, nthreads=4, n_slots=0, ids_cap=None, odd_cap=0, pool_cap=0, lp_cap=0, n_ranges=1):
     raw = b"".join(docs)
     text = np.frombuffer(raw + b"\0" * 64, np.uint8).copy()
     offs = np.zeros(len(docs) + 1, np.int64)
@@ -155,7 +155,7 @@ def _run_fused(host_sim, h, spm, docs, nthreads=4, n_slots=0, ids_cap=None, odd_
     nout = np.zeros(8, np.int64)
     host_sim.sim_encode_corpus_pipe(h, spm, text.ctypes.data, n, offs.ctypes.data, len(docs), ids.ctypes.data, cap,
                                     wl.ctypes.data, wf.ctypes.data, wcap, dto.ctypes.data, dfl.ctypes.data,
-                                    ctr.ctypes.data, nout.ctypes.data, nthreads, n_slots, odd_cap, pool_cap, lp_cap)
+                                    ctr.ctypes.data, nout.ctypes.data, nthreads, n_slots, odd_cap, pool_cap, lp_cap, n_ranges)
     return dict(ids=ids[:min(nout[0], cap)], wl=wl[:nout[1]], wf=wf[:nout[1]], dto=dto, dfl=dfl, ctr=ctr, nout=nout)
 
 
@@ -224,6 +224,11 @@ def test_pipeline_code_s2orc_shaped_text(host_sim):
     wtext, woffs = pack([w.encode() for w in words])
     o_ids, o_lens, _ = COracle(vb, 1).encode_words(wtext, woffs)
     assert np.array_equal(r["wl"][:n50], o_lens) and np.array_equal(r["ids"][:len(o_ids)], o_ids)
+    # the same corpus as 2 / 7 consecutive document ranges sharing one word table (chunked host path)
+    for nr in (2, 7):
+        rr = _run_fused(host_sim, h, 1, docs, nthreads=4, n_ranges=nr)
+        assert np.array_equal(rr["ids"], r["ids"]) and np.array_equal(rr["wl"], r["wl"])
+        assert np.array_equal(rr["dto"], r["dto"]) and rr["ctr"].tolist() == r["ctr"].tolist()
     for slots in (1 << 16, 256):
         r2 = _run_fused(host_sim, h, 1, docs, nthreads=3, n_slots=slots)
         assert np.array_equal(r2["ids"], r["ids"]) and np.array_equal(r2["wl"], r["wl"])
@@ -266,7 +271,8 @@ def test_pipeline_code_edge_cases(host_sim):
                          for _ in range(rng.randint(50, 20000)))
             cuts = sorted(set(rng.randint(1, len(blob) - 1) for _ in range(rng.randint(0, 40))))
             docs = [blob[a:b] for a, b in zip([0] + cuts, cuts + [len(blob)])]
-        _check_fused(host_sim, h, vb, docs, nthreads=rng.choice([1, 2, 5, 8]), n_slots=rng.choice([0, 0, 64, 1024]))
+        _check_fused(host_sim, h, vb, docs, nthreads=rng.choice([1, 2, 5, 8]), n_slots=rng.choice([0, 0, 64, 1024]),
+                     n_ranges=rng.choice([1, 1, 2, 5]))
     # words far longer than a tile
     big = [b"x" * 3000 + b" y " + b"z" * 9000 + b" end", "é".encode() * 5000]
     _check_fused(host_sim, h, vb, big, nthreads=4)
@@ -370,7 +376,8 @@ def test_pipeline_code_bytelevel_rules(host_sim):
         for trial in range(25):
             docs = ["".join(rng.choice(soup) for _ in range(rng.randint(1, 60))).encode()
                     for _ in range(rng.choice([1, 5, 60]))]
-            _check_bytelevel(host_sim, h, tok, vb, rule, docs, nthreads=rng.choice([1, 3, 8]), n_slots=rng.choice([0, 64]))
+            _check_bytelevel(host_sim, h, tok, vb, rule, docs, nthreads=rng.choice([1, 3, 8]), n_slots=rng.choice([0, 64]),
+                             n_ranges=rng.choice([1, 1, 3]))
         # pieces far longer than a tile / its look-behind: one 20 KB letter run, 9 KB of digits, 6 KB of spaces
         big = [("x" * 20000 + " y").encode(), ("7" * 9000 + "a").encode(), (" " * 6000 + "z\n" * 3000).encode()]
         _check_bytelevel(host_sim, h, tok, vb, rule, big, nthreads=4)
