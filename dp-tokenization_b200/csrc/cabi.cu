@@ -424,8 +424,9 @@ int dpt_encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_t
                             int64_t ids_cap, int32_t* d_word_lens, uint8_t* d_word_flags, int64_t word_cap,
                             int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters, int64_t* d_n_out,
                             void* d_table_workspace, int64_t table_workspace_bytes, void* d_workspace,
-                            int64_t workspace_bytes, int32_t worst_case, void* stream) {
+                            int64_t workspace_bytes, int32_t worst_case, int32_t phases, void* stream) {
     if (int rc = check_ready(v, "dpt_encode_corpus_range")) return rc;
+    if (phases < 0 || phases > 3) return fail(DPT_EINVAL, "dpt_encode_corpus_range: phases must be 0..3");
     if (rule != DPT_RULE_SPM_LLAMA && rule != DPT_RULE_GPT2 && rule != DPT_RULE_LLAMA3)
         return fail(DPT_EINVAL, "dpt_encode_corpus_range: rule not available on device in this build");
     std::string err;
@@ -433,7 +434,7 @@ int dpt_encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_t
                                             doc_begin, doc_end, reset_table, n_bytes_total, table_word_cap, d_ids, ids_cap,
                                             d_word_lens, d_word_flags, word_cap, d_doc_tok_offs, d_doc_flags, d_counters,
                                             d_n_out, d_table_workspace, table_workspace_bytes, d_workspace, workspace_bytes,
-                                            worst_case, (cudaStream_t)stream, err);
+                                            worst_case, phases, (cudaStream_t)stream, err);
     return rc ? fail(rc, err) : DPT_OK;
 }
 

@@ -116,7 +116,7 @@ struct PipeParams {
     int64_t* doc_first_word;      // n_docs + 1
     unsigned long long* tags;     // n_slots, zeroed by the launcher
     ResRec* res;                  // n_slots
-    uint32_t* pending;            // 4 length classes x n_slots
+    uint32_t* pending;            // 4 length classes x pend_stride (private to the range: ranges may overlap in time)
     OddWord* odd;                 // odd_cap
     ResRec* odd_res;              // odd_cap
     int32_t* pool;                // pool_cap ids of words with more than 7 tokens (persistent, like the table)
@@ -132,6 +132,7 @@ struct PipeParams {
     uint32_t slot_mask;           // n_slots - 1 (power of two, <= 2^30)
     int32_t n_tiles, n_ctiles;
     int32_t tile_first;           // global index (byte offset / PA_T) of this launch's first tile
+    int64_t pend_stride;          // capacity of one length class of `pending`
     int32_t spm;  // 1: SPM_LLAMA rule; 0: byte-level rules
     int32_t rule;
     int32_t vec_ok;  // word_lens / word_flags are aligned for 16- / 8-byte stores
@@ -684,7 +685,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
         for (uint32_t i = tid; i < npend; i += nt) {
             const uint32_t v = S.pend[i], cls = v >> 30;
             const uint32_t r = blk.atomic_add_ret(&S.cur_c[cls], 1u);
-            P.pending[(size_t)cls * ((size_t)P.slot_mask + 1) + S.base_c[cls] + r] = v & REF_INDEX;
+            P.pending[(size_t)cls * (size_t)P.pend_stride + S.base_c[cls] + r] = v & REF_INDEX;
         }
         blk.sync();
         if (tid == 0) {
@@ -802,7 +803,7 @@ DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint64_t i, const uint32_t* npc,
         i -= npc[cls];
         --cls;
     }
-    const uint32_t slot = P.pending[(size_t)cls * ((size_t)P.slot_mask + 1) + i];
+    const uint32_t slot = P.pending[(size_t)cls * (size_t)P.pend_stride + i];
     const unsigned long long t = P.tags[slot];
     it.pos = pp_tag_pos(t);
     it.end = it.pos + pp_tag_len(t);

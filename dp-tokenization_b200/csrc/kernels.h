@@ -35,7 +35,7 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
                         int64_t table_word_cap, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens, uint8_t* d_word_flags,
                         int64_t word_cap, int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters,
                         int64_t* d_n_out, void* d_table_ws, int64_t table_ws_bytes, void* d_ws, int64_t ws_bytes,
-                        int32_t worst, cudaStream_t st, std::string& err);
+                        int32_t worst, int32_t phases, cudaStream_t st, std::string& err);
 int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, int64_t n_bytes, const int64_t* d_doc_offs,
                        int64_t n_docs, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens, uint8_t* d_word_flags,
                        int64_t word_cap, int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters,

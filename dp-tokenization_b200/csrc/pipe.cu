@@ -197,7 +197,6 @@ int64_t corpus_table_workspace(int64_t n_bytes_total, int64_t word_cap_total, in
     b += align_up(sizeof(PipePersist), 256);
     b += align_up(z.n_slots * 8, 256);    // tags
     b += align_up(z.n_slots * 32, 256);   // res
-    b += align_up(z.n_slots * 16, 256);   // pending (4 length classes)
     b += align_up(z.pool_cap * 4, 256);   // pool
     return b + 1024;
 }
@@ -208,6 +207,7 @@ int64_t corpus_range_workspace(int64_t range_bytes, int64_t range_docs, int64_t 
     b += align_up(sizeof(PipeCtl), 256);
     b += align_up(z.n_tiles * 8 + 8, 256) + align_up(z.n_ctiles * 8 + 8, 256);
     b += align_up(word_cap * 4 + 64, 256);                   // refs
+    b += align_up(word_cap * 16 + 64, 256);                  // pending (4 length classes x word_cap)
     b += align_up((range_docs + 1) * 8, 256);                // doc_first_word
     b += align_up(z.odd_cap * 16, 256) + align_up(z.odd_cap * 32, 256);  // odd, odd_res
     b += align_up((word_cap + z.odd_cap) * 4, 256);          // longq
@@ -225,7 +225,7 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
                         int64_t table_word_cap, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens, uint8_t* d_word_flags,
                         int64_t word_cap, int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters,
                         int64_t* d_n_out, void* d_table_ws, int64_t table_ws_bytes, void* d_ws, int64_t ws_bytes,
-                        int32_t worst, cudaStream_t st, std::string& err) {
+                        int32_t worst, int32_t phases, cudaStream_t st, std::string& err) {
     const int64_t range_bytes = byte_end - byte_begin, range_docs = doc_end - doc_begin;
     if (n_bytes_total <= 0 || n_docs_total <= 0 || word_cap <= 0 || range_bytes <= 0 || range_docs <= 0 || byte_begin < 0 ||
         byte_end > n_bytes_total || doc_begin < 0 || doc_end > n_docs_total || !d_text || !d_doc_offs || !d_doc_tok_offs ||
@@ -296,12 +296,12 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
         P.tags = (unsigned long long*)take(tz.n_slots * 8);
         const int64_t zero_bytes = used;
         P.res = (ResRec*)take(tz.n_slots * 32);
-        P.pending = (uint32_t*)take(tz.n_slots * 16);
         P.pool = (int32_t*)take(tz.pool_cap * 4);
         P.pool_cap = tz.pool_cap;
         P.slot_mask = (uint32_t)(tz.n_slots - 1);
         if (reset_table) cudaMemsetAsync(base, 0, (size_t)zero_bytes, st);
     }
+    const bool do_scan = (phases & 1) != 0, do_emit = (phases & 2) != 0;
     {   // range part: everything that must start zeroed is contiguous
         char* base = (char*)d_ws;
         int64_t used = 0;
@@ -316,6 +316,8 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
         P.desc_t = (unsigned long long*)take(z.n_ctiles * 8 + 8);
         const int64_t zero_bytes = used;
         P.refs = (uint32_t*)take(word_cap * 4 + 64);
+        P.pending = (uint32_t*)take(word_cap * 16 + 64);
+        P.pend_stride = word_cap;
         P.doc_first_word = (int64_t*)take((range_docs + 1) * 8);
         P.odd = (OddWord*)take(z.odd_cap * 16);
         P.odd_res = (ResRec*)take(z.odd_cap * 32);
@@ -326,7 +328,7 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
         P.lp_b = (uint16_t*)take(z.lp_cap * 2);
         P.odd_cap = z.odd_cap;
         P.lp_cap = z.lp_cap;
-        cudaMemsetAsync(base, 0, (size_t)zero_bytes, st);
+        if (do_scan) cudaMemsetAsync(base, 0, (size_t)zero_bytes, st);
     }
     P.tile_first = (int32_t)(byte_begin / PA_T);
     P.n_tiles = (int32_t)((byte_end + PA_T - 1) / PA_T - byte_begin / PA_T);
@@ -334,6 +336,7 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
     P.spm = rule == DPT_RULE_SPM_LLAMA ? 1 : 0;
     P.rule = rule;
     P.vec_ok = ((((uintptr_t)d_word_lens) & 15u) == 0 && (((uintptr_t)d_word_flags) & 7u) == 0) ? 1 : 0;
+    if (do_scan) {
     if (d_doc_flags) cudaMemsetAsync(d_doc_flags, 0, (size_t)range_docs, st);
     {
         ProfScope prof(P.spm ? "k_scan_dedup" : "k_scan_dedup_bl", st);
@@ -353,6 +356,8 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
         k_dp_distinct_long<<<(unsigned)(sm_count * 2), PB_THREADS, 0, st>>>(P);
         ++g_launches;
     }
+    }
+    if (do_emit) {
     {
         ProfScope prof("k_emit", st);
         k_emit<<<(unsigned)z.n_ctiles, PC_THREADS, 0, st>>>(P);
@@ -362,6 +367,7 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
         ProfScope prof("k_pipe_finish", st);
         k_pipe_finish<<<1, 32, 0, st>>>(P);
         ++g_launches;
+    }
     }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -387,7 +393,7 @@ int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, 
     const int64_t tb_al = align_up(tb, 256);
     return encode_corpus_range(v, rule, d_text, n_bytes, d_doc_offs, n_docs, 0, n_bytes, 0, n_docs, 1, n_bytes, word_cap, d_ids,
                                ids_cap, d_word_lens, d_word_flags, word_cap, d_doc_tok_offs, d_doc_flags, d_counters, d_n_out,
-                               d_ws, tb_al, (char*)d_ws + tb_al, ws_bytes - tb_al, worst, st, err);
+                               d_ws, tb_al, (char*)d_ws + tb_al, ws_bytes - tb_al, worst, 3, st, err);
 }
 
 }  // namespace dpt

@@ -64,7 +64,7 @@ SIGNATURES = {
     "dpt_corpus_table_workspace": (_i64, [_i64, _i64, _i32]),
     "dpt_encode_corpus_range_workspace": (_i64, [_i32, _i64, _i64, _i64, _i32]),
     "dpt_encode_corpus_range": (C.c_int, [_p, _i32, _p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i64, _p, _i64, _p, _p,
-                                          _i64, _p, _p, _p, _p, _p, _i64, _p, _i64, _i32, _p]),
+                                          _i64, _p, _p, _p, _p, _p, _i64, _p, _i64, _i32, _i32, _p]),
     "dpt_encode_corpus_general": (C.c_int, [_p, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _p,
                                             _i64, _i32, _p]),
     "dpt_lattice_word": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _i32, _p, _p, _p]),

@@ -170,9 +170,10 @@ class Engine:
         """``h_text``: uint8 HOST tensor (pinned for full speed) of concatenated non-empty documents; ``doc_offs``:
         int64[n_docs+1] numpy array.  The corpus is cut at document boundaries into ranges of about ``chunk_bytes``.
         Range k is copied into its place in ONE device text buffer on the copy-in stream, tokenized by
-        ``dpt_encode_corpus_range`` on the compute stream (the word table is shared by all ranges of the call, so a
-        word is still solved once per corpus) and its ids are copied out on the copy-out stream over a ring of
-        ``n_streams`` output slots: PCIe in both directions and the SMs work at the same time.  Returns host tensors."""
+        ``dpt_encode_corpus_range`` (scan + DP on one of two scan streams, emit on the emit stream; the word table is
+        shared by all ranges of the call, so a word is still solved once per corpus) and its ids are copied out on the
+        copy-out stream over a ring of ``n_streams`` output slots: PCIe in both directions and the SMs work at the same
+        time, and the latency-bound DP kernel of one range runs beside the scan of the next.  Returns host tensors."""
         assert h_text.dtype == torch.uint8 and not h_text.is_cuda
         doc_offs = np.ascontiguousarray(doc_offs, dtype=np.int64)
         n_docs = len(doc_offs) - 1
@@ -201,12 +202,14 @@ class Engine:
                 ws_bytes = lib.dpt_encode_corpus_range_workspace(rule, max_b, max_d, word_cap, 0)
                 tws_bytes = lib.dpt_corpus_table_workspace(n_bytes, word_cap_total, 0)
                 self._host = dict(
-                    streams=[torch.cuda.Stream(device=dev) for _ in range(3)],  # copy-in, compute, copy-out
+                    streams=[torch.cuda.Stream(device=dev) for _ in range(5)],  # copy-in, scan x2, emit, copy-out
+                    ev_reset=torch.cuda.Event(),
                     d_text=torch.empty(n_bytes, dtype=torch.uint8, device=dev),
                     d_offs=torch.empty(n_docs + 1, dtype=torch.int64, device=dev),
                     h_offs=torch.empty(n_docs + 1, dtype=torch.int64).pin_memory(),
                     table_ws=torch.empty(int(tws_bytes), dtype=torch.uint8, device=dev),
-                    slots=[dict(ev_in=torch.cuda.Event(), ev_comp=torch.cuda.Event(), ev_out=torch.cuda.Event(),
+                    slots=[dict(ev_in=torch.cuda.Event(), ev_ab=torch.cuda.Event(), ev_comp=torch.cuda.Event(),
+                                ev_out=torch.cuda.Event(),
                                 ids=torch.empty(ids_cap, dtype=torch.int32, device=dev),
                                 lens=torch.empty(word_cap, dtype=torch.int32, device=dev),
                                 flags=torch.empty(word_cap, dtype=torch.uint8, device=dev),
@@ -221,9 +224,9 @@ class Engine:
                 self._host_key = key
             H = self._host
             slots = H["slots"]
-            s_in, s_comp, s_out = H["streams"]
+            s_in, s_scan0, s_scan1, s_emit, s_out = H["streams"]
             cur = torch.cuda.current_stream(dev)
-            for st in (s_in, s_comp, s_out):
+            for st in H["streams"]:
                 st.wait_stream(cur)
             H["h_offs"].copy_(torch.from_numpy(doc_offs))
             with torch.cuda.stream(s_in):
@@ -261,6 +264,21 @@ class Engine:
                 totals[:] += np.asarray(h[8:12], dtype=np.int64)
                 ids_base += n_ids
 
+            def range_call(sl, k, phases, reset, stream):
+                lo, hi = cuts[k], cuts[k + 1]
+                check(lib.dpt_encode_corpus_range(
+                    self.vocab.handle, rule, _ptr(H["d_text"]), n_bytes, _ptr(H["d_offs"]), n_docs, int(doc_offs[lo]),
+                    int(doc_offs[hi]), lo, hi, reset, word_cap_total, _ptr(sl["ids"]), ids_cap, _ptr(sl["lens"]),
+                    _ptr(sl["flags"]), word_cap, _ptr(sl["doc_tok"]), _ptr(sl["doc_flags"]), _ptr(sl["counters"]),
+                    _ptr(sl["n_out"]), _ptr(H["table_ws"]), H["table_ws"].numel(), _ptr(sl["ws"]), sl["ws"].numel(), 0,
+                    phases, C.c_void_p(stream.cuda_stream)))
+
+            # clear the word table once; both scan streams start behind that
+            with torch.cuda.stream(s_scan0):
+                range_call(slots[0], 0, 0, 1, s_scan0)
+                H["ev_reset"].record(s_scan0)
+            s_scan1.wait_event(H["ev_reset"])
+            prev_ab = None
             for k in range(n_chunks):
                 sl = slots[k % n_streams]
                 if len(pending) >= n_streams:               # the slot's previous range must have left the GPU
@@ -272,22 +290,32 @@ class Engine:
                     H["d_text"][b0:b1].copy_(h_text[b0:b1], non_blocking=True)
                     sl["ev_in"].record(s_in)
                     mark("h2d-end", k, s_in)
-                with torch.cuda.stream(s_comp):
-                    s_comp.wait_event(sl["ev_in"])
-                    s_comp.wait_event(sl["ev_out"])         # the slot's previous ids have been copied out
-                    mark("comp-begin", k, s_comp)
-                    check(lib.dpt_encode_corpus_range(
-                        self.vocab.handle, rule, _ptr(H["d_text"]), n_bytes, _ptr(H["d_offs"]), n_docs, b0, b1, lo, hi,
-                        1 if k == 0 else 0, word_cap_total, _ptr(sl["ids"]), ids_cap, _ptr(sl["lens"]), _ptr(sl["flags"]),
-                        word_cap, _ptr(sl["doc_tok"]), _ptr(sl["doc_flags"]), _ptr(sl["counters"]), _ptr(sl["n_out"]),
-                        _ptr(H["table_ws"]), H["table_ws"].numel(), _ptr(sl["ws"]), sl["ws"].numel(), 0,
-                        C.c_void_p(s_comp.cuda_stream)))
+                # phase 1 (scan + dedup + DP of the new words) alternates between two streams: the scan of range k+1
+                # runs beside the latency-bound DP kernel of range k
+                s_scan = s_scan0 if k % 2 == 0 else s_scan1
+                with torch.cuda.stream(s_scan):
+                    s_scan.wait_event(sl["ev_in"])
+                    s_scan.wait_event(sl["ev_comp"])        # the slot's previous range has been emitted
+                    mark("scan-begin", k, s_scan)
+                    range_call(sl, k, 1, 0, s_scan)
+                    sl["ev_ab"].record(s_scan)
+                    mark("scan-end", k, s_scan)
+                # phase 2 (emit) needs the DP results of every range up to k: ev_ab of k and of k-1 (the two scan
+                # streams are each in order, so these two cover all earlier ranges)
+                with torch.cuda.stream(s_emit):
+                    s_emit.wait_event(sl["ev_ab"])
+                    if prev_ab is not None:
+                        s_emit.wait_event(prev_ab)
+                    s_emit.wait_event(sl["ev_out"])         # the slot's previous ids have been copied out
+                    mark("emit-begin", k, s_emit)
+                    range_call(sl, k, 2, 0, s_emit)
                     sl["h_small"][:8].copy_(sl["n_out"], non_blocking=True)
                     sl["h_small"][8:12].copy_(sl["counters"], non_blocking=True)
                     sl["h_doc_tok"][:hi - lo + 1].copy_(sl["doc_tok"][:hi - lo + 1], non_blocking=True)
                     sl["h_doc_flags"][:hi - lo].copy_(sl["doc_flags"][:hi - lo], non_blocking=True)
-                    sl["ev_comp"].record(s_comp)
-                    mark("comp-end", k, s_comp)
+                    sl["ev_comp"].record(s_emit)
+                    mark("emit-end", k, s_emit)
+                prev_ab = sl["ev_ab"]
                 pending.append((k, sl))
             while pending:
                 finalize(*pending.pop(0))
@@ -295,7 +323,8 @@ class Engine:
             if overflow:
                 # rare: a range exceeded a capacity.  The text is resident: redo the corpus through the retrying
                 # device-resident call and copy the result out.
-                s_comp.synchronize()
+                for st in H["streams"]:
+                    st.synchronize()
                 res = self.encode_corpus(H["d_text"], H["d_offs"], rule)
                 ids_base = res.n_ids
                 if out_ids.numel() < ids_base:

@@ -210,7 +210,12 @@ int dpt_encode_corpus(const dpt_vocab* v, int32_t rule,
  *      the previous range unless reset_table != 0 (pass 1 for the first range): a word is still solved once per
  *      corpus, not once per chunk.  d_doc_offs holds corpus-global offsets; outputs are range-local exactly as
  *      dpt_encode_corpus would produce them for the range alone (ids from 0, d_doc_tok_offs[doc_end-doc_begin+1],
- *      d_doc_flags[doc_end-doc_begin]).  d_workspace: dpt_encode_corpus_range_workspace (per range). */
+ *      d_doc_flags[doc_end-doc_begin]).  d_workspace: dpt_encode_corpus_range_workspace (per range).
+ *      phases: bit 0 = scan + dedup + DP of the range's new words, bit 1 = emit; 3 = the whole range.  Split calls
+ *      let consecutive ranges overlap on different streams: the scan/DP of range k+1 may run beside the DP/emit of
+ *      range k (the table is updated atomically); only emit(k+1) must be ordered after scan+DP(k) - the caller
+ *      inserts that stream dependency - and after its own phase 1.  phases = 0 with reset_table = 1 just clears the
+ *      table. */
 int64_t dpt_corpus_table_workspace(int64_t n_bytes_total, int64_t word_cap_total, int32_t worst_case);
 int64_t dpt_encode_corpus_range_workspace(int32_t rule, int64_t range_bytes, int64_t range_docs, int64_t word_cap,
                                           int32_t worst_case);
@@ -224,7 +229,8 @@ int dpt_encode_corpus_range(const dpt_vocab* v, int32_t rule,
                             int64_t* d_doc_tok_offs, uint8_t* d_doc_flags,
                             int64_t* d_counters, int64_t* d_n_out,
                             void* d_table_workspace, int64_t table_workspace_bytes,
-                            void* d_workspace, int64_t workspace_bytes, int32_t worst_case, void* stream);
+                            void* d_workspace, int64_t workspace_bytes, int32_t worst_case, int32_t phases,
+                            void* stream);
 
 /* ---- the same contract WITHOUT deduplication: normalise -> DP count per word -> scan -> DP emit per word
  *      (what dpt_pretokenize + dpt_encode_words compose to); synchronises the stream once.  Kept as

@@ -171,7 +171,6 @@ int32_t sim_encode_corpus_pipe(void* vv, int32_t rule, const uint8_t* text, int6
     PipePersist persist{};
     std::vector<unsigned long long> tags(n_slots, 0);
     std::vector<ResRec> res(n_slots);
-    std::vector<uint32_t> pending(4 * n_slots);
     std::vector<int32_t> pool(pool_cap);
     memset(counters, 0, 32);
     memset(n_out, 0, 64);
@@ -209,7 +208,8 @@ int32_t sim_encode_corpus_pipe(void* vv, int32_t rule, const uint8_t* text, int6
         PipeCtl ctl{};
         std::vector<unsigned long long> dw(n_tiles + 1, 0), dt(n_ctiles + 1, 0);
         std::vector<ResRec> odd_res(odd_cap);
-        std::vector<uint32_t> refs(r_word_cap + 16), longq(r_word_cap + odd_cap + 16);
+        std::vector<uint32_t> refs(r_word_cap + 16), longq(r_word_cap + odd_cap + 16), pending(4 * r_word_cap + 16);
+        P.pend_stride = r_word_cap;
         std::vector<int64_t> dfw(nd + 1, -1);
         std::vector<OddWord> odd(odd_cap);
         std::vector<uint8_t> lpn(lp_cap);

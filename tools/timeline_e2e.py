@@ -23,5 +23,18 @@ r = eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_SPM_LLAMA, chunk_bytes=c
 torch.cuda.synchronize()
 print("wall", (time.perf_counter() - t0) * 1e3, "ms")
 start = eng._trace[0][2]
-for name, k, ev, host_t in eng._trace:
+for name, k, ev, host_t in sorted(eng._trace, key=lambda t: start.elapsed_time(t[2])):
     print(f"{name:10s} chunk {k}: gpu {start.elapsed_time(ev):7.3f} ms   host-enqueue {1e3*(host_t - eng._trace[0][3]):7.3f} ms")
+
+# per-kernel device time summed over the ranges of one call (CUDA events around every launch)
+from dptok import engine as eng_mod
+eng._trace = None
+eng_mod.profile_enable(True)
+r = eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_SPM_LLAMA, chunk_bytes=chunk, n_streams=ns, out_ids=h_ids)
+torch.cuda.synchronize()
+eng_mod.profile_enable(False)
+tot = 0.0
+for name, cnt, ms in eng_mod.profile_report():
+    print(f"{name:22s} launches {cnt:3d}  total {ms:7.3f} ms  per launch {ms/cnt:7.3f}")
+    tot += ms
+print("sum of kernel times", tot)
