@@ -449,6 +449,19 @@ int dpt_lattice_word(const dpt_vocab* v, const uint8_t* d_text, int32_t n_bytes,
     return rc ? fail(rc, "dpt_lattice_word: launch failed") : DPT_OK;
 }
 
+int dpt_pad_batch(const int32_t* d_ids_a, const int64_t* d_doc_tok_offs_a, const int32_t* d_ids_b,
+                  const int64_t* d_doc_tok_offs_b, int64_t doc_begin, int64_t n_rows, int64_t row_len, int64_t pad_id,
+                  int32_t pad_left, int64_t* d_input_ids, int64_t* d_attention_mask, int64_t* d_row_lens, void* stream) {
+    if (n_rows <= 0 || row_len <= 0 || n_rows >= (1ll << 31) || !d_ids_a || !d_doc_tok_offs_a || !d_input_ids ||
+        (d_ids_b && !d_doc_tok_offs_b))
+        return fail(DPT_EINVAL, "dpt_pad_batch: bad argument");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return fail(DPT_ECUDA, "dpt_pad_batch: no CUDA device");
+    const int rc = dpt::pad_batch(d_ids_a, d_doc_tok_offs_a, d_ids_b, d_doc_tok_offs_b, doc_begin, n_rows, row_len, pad_id,
+                                  pad_left, d_input_ids, d_attention_mask, d_row_lens, (cudaStream_t)stream);
+    return rc ? fail(rc, "dpt_pad_batch: launch failed") : DPT_OK;
+}
+
 int dpt_roundtrip_check(const dpt_vocab* v, const int32_t* d_ids, const int64_t* d_doc_tok_offs, const uint8_t* d_text,
                         const int64_t* d_doc_offs, int64_t n_docs, int32_t skip_bos, uint8_t* d_ok, void* stream) {
     if (int rc = check_ready(v, "dpt_roundtrip_check")) return rc;

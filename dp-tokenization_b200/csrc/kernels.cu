@@ -508,6 +508,36 @@ __global__ void k_roundtrip(DptVocabView V, const int32_t* __restrict__ ids, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// training-data feed on device: token stream -> padded int64 batch.
+// One block per row.  Row r = ids of document doc_begin + r of stream A, optionally followed by the ids of the
+// same document of stream B (the custom collator of main_biomed_translation.py:104-124 concatenates
+// input_ids + labels), truncated to row_len, padded with pad_id on the right (or left); attention_mask is 1 on
+// real tokens (main_analyze_s2orc.py:88-89) and 0 on padding (DataCollatorWithPadding).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_pad_batch(const int32_t* __restrict__ ids_a, const int64_t* __restrict__ offs_a, const int32_t* __restrict__ ids_b,
+            const int64_t* __restrict__ offs_b, int64_t doc_begin, int64_t row_len, int64_t pad_id, int32_t pad_left,
+            int64_t* __restrict__ input_ids, int64_t* __restrict__ attention_mask, int64_t* __restrict__ row_lens) {
+    const int64_t r = blockIdx.x, d = doc_begin + r;
+    const int64_t a0 = offs_a[d], na = offs_a[d + 1] - a0;
+    const int64_t b0 = ids_b ? offs_b[d] : 0, nb = ids_b ? offs_b[d + 1] - b0 : 0;
+    int64_t n = na + nb;
+    if (n > row_len) n = row_len;
+    const int64_t shift = pad_left ? row_len - n : 0;
+    int64_t* out = input_ids + r * row_len;
+    int64_t* am = attention_mask ? attention_mask + r * row_len : nullptr;
+    for (int64_t p = threadIdx.x; p < row_len; p += blockDim.x) {
+        const int64_t q = p - shift;
+        const bool real = q >= 0 && q < n;
+        int64_t v = pad_id;
+        if (real) v = q < na ? (int64_t)ids_a[a0 + q] : (int64_t)ids_b[b0 + (q - na)];
+        out[p] = v;
+        if (am) am[p] = real ? 1 : 0;
+    }
+    if (threadIdx.x == 0 && row_lens) row_lens[r] = n;
+}
+
+// ---------------------------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------------------------
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
@@ -718,6 +748,14 @@ int roundtrip_check(const dpt_vocab* v, const int32_t* d_ids, const int64_t* d_d
                     const int64_t* d_doc_offs, int64_t n_docs, int32_t skip_bos, uint8_t* d_ok, cudaStream_t st) {
     DPT_LAUNCH(k_roundtrip, blocks_for(n_docs, 128), 128, st, v->d_view, d_ids, d_doc_tok_offs, d_text, d_doc_offs, n_docs,
                skip_bos, d_ok);
+    return cudaGetLastError() == cudaSuccess ? DPT_OK : DPT_ECUDA;
+}
+
+int pad_batch(const int32_t* d_ids_a, const int64_t* d_offs_a, const int32_t* d_ids_b, const int64_t* d_offs_b,
+              int64_t doc_begin, int64_t n_rows, int64_t row_len, int64_t pad_id, int32_t pad_left, int64_t* d_input_ids,
+              int64_t* d_attention_mask, int64_t* d_row_lens, cudaStream_t st) {
+    DPT_LAUNCH(k_pad_batch, (unsigned)n_rows, 128, st, d_ids_a, d_offs_a, d_ids_b, d_offs_b, doc_begin, row_len, pad_id, pad_left,
+               d_input_ids, d_attention_mask, d_row_lens);
     return cudaGetLastError() == cudaSuccess ? DPT_OK : DPT_ECUDA;
 }
 

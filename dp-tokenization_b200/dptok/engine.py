@@ -412,6 +412,35 @@ class Engine:
         preds = [pr[po[u]:po[u + 1]] for u in range(n_units + 1)]
         return ld, preds
 
+    # ---- training-data feed on device ------------------------------------------------------------
+    def pad_batch(self, res: EncodeResult, pad_id: int, doc_begin: int = 0, n_rows: Optional[int] = None,
+                  row_len: Optional[int] = None, pad_left: bool = False, labels: Optional[EncodeResult] = None):
+        """``input_ids`` / ``attention_mask`` (int64 [n_rows, row_len], on the device) for documents
+        ``doc_begin .. doc_begin + n_rows`` of an encode result: what ``tokenized_dict['input_ids']`` +
+        ``[1] * len`` (main_analyze_s2orc.py:87-89) become under ``DataCollatorWithPadding``.  With ``labels`` (a second
+        encode result over the same documents, e.g. the target sentences) every row is ids + label ids like the custom
+        collator of main_biomed_translation.py:104-124.  ``row_len`` defaults to the longest row (one device max)."""
+        offs = res.doc_tok_offs
+        n_docs = offs.numel() - 1
+        if n_rows is None:
+            n_rows = n_docs - doc_begin
+        dev = self.device
+        with torch.cuda.device(dev):
+            lens = offs[doc_begin + 1:doc_begin + n_rows + 1] - offs[doc_begin:doc_begin + n_rows]
+            if labels is not None:
+                lo = labels.doc_tok_offs
+                lens = lens + (lo[doc_begin + 1:doc_begin + n_rows + 1] - lo[doc_begin:doc_begin + n_rows])
+            if row_len is None:
+                row_len = max(int(lens.max().item()), 1)
+            input_ids = torch.empty((n_rows, row_len), dtype=torch.int64, device=dev)
+            mask = torch.empty((n_rows, row_len), dtype=torch.int64, device=dev)
+            row_lens = torch.empty(n_rows, dtype=torch.int64, device=dev)
+            check(lib.dpt_pad_batch(_ptr(res.ids), _ptr(offs), _ptr(labels.ids) if labels is not None else None,
+                                    _ptr(labels.doc_tok_offs) if labels is not None else None, doc_begin, n_rows, row_len,
+                                    int(pad_id), 1 if pad_left else 0, _ptr(input_ids), _ptr(mask), _ptr(row_lens),
+                                    self._stream()))
+        return input_ids, mask, row_lens
+
     # ---- decode / round trip on device (SURVEY.md 8 row f4) ---------------------------------------
     def roundtrip_ok(self, res: EncodeResult, text: torch.Tensor, doc_offs: torch.Tensor, skip_bos: bool) -> torch.Tensor:
         n_docs = doc_offs.numel() - 1

@@ -139,9 +139,24 @@ def dp_tokenize_llama(llama_tokenizer, pretokenize_option="llama", cache_dir=Non
                     out[k] = per_doc[pos]
             if untok and all(ambiguous[pos] == 0 for pos in range(len(easy))):
                 _raise_untokenizable()
-        for k, s in enumerate(texts):
-            if out[k] is None:  # word split depends on the BPE merge order: ask the tokenizer, DP on GPU
-                out[k] = _encode_presplit(host_split(s))
+        hard = [k for k in range(len(texts)) if out[k] is None]
+        if hard:
+            # word split depends on the BPE merge order (or the text holds special tokens): ask the tokenizer for the
+            # split exactly like pretokenize_with_llama, then ONE device pass over the words of all these texts
+            per_doc = [host_split(texts[k]) for k in hard]
+            flat = [w.encode("utf-8") for doc in per_doc for w in doc]
+            if flat:
+                text, offs = pack_documents(flat)
+                res = engine.encode_words(torch.from_numpy(text.copy()).to(dev), torch.from_numpy(offs).to(dev),
+                                          want_tok_offs=True)
+                if int(res.counters[_cabi.CTR_UNTOKENIZABLE]):
+                    _raise_untokenizable()
+                ids = res.ids.cpu().numpy()
+                to = res.word_tok_offs.cpu().numpy()
+            w = 0
+            for k, doc in zip(hard, per_doc):
+                out[k] = ids[to[w]:to[w + len(doc)]].tolist() if doc else []
+                w += len(doc)
         return out
 
     if pretokenize_option == "llama":

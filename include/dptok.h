@@ -265,6 +265,19 @@ int dpt_roundtrip_check(const dpt_vocab* v, const int32_t* d_ids, const int64_t*
                         const uint8_t* d_text, const int64_t* d_doc_offs, int64_t n_docs,
                         int32_t skip_bos, uint8_t* d_ok, void* stream);
 
+/* ---- training-data feed on device: token stream -> padded int64 batch, no host round trip.
+ *      Replaces tokenized_dict['input_ids'] / ['attention_mask'] = [1] * len (main_analyze_s2orc.py:87-89) followed
+ *      by DataCollatorWithPadding, and - with a second stream - the custom collator of
+ *      main_biomed_translation.py:104-124 that concatenates input_ids + labels and pads with pad_token_id.
+ *      Row r = ids of document doc_begin + r of stream A (d_ids_a, d_doc_tok_offs_a as written by the encode calls),
+ *      followed by that document's ids of stream B if d_ids_b != NULL; truncated to row_len; padded with pad_id on the
+ *      right (pad_left = 0) or left.  d_input_ids / d_attention_mask: int64[n_rows * row_len] (mask may be NULL);
+ *      d_row_lens: int64[n_rows] real tokens per row (may be NULL). */
+int dpt_pad_batch(const int32_t* d_ids_a, const int64_t* d_doc_tok_offs_a,
+                  const int32_t* d_ids_b, const int64_t* d_doc_tok_offs_b,
+                  int64_t doc_begin, int64_t n_rows, int64_t row_len, int64_t pad_id, int32_t pad_left,
+                  int64_t* d_input_ids, int64_t* d_attention_mask, int64_t* d_row_lens, void* stream);
+
 const char* dpt_last_error(void);
 const char* dpt_version(void);
 /* number of kernel launches issued by this library in the calling process (bench "gpu_launches") */

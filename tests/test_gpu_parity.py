@@ -383,3 +383,67 @@ def test_host_chunked_path_equals_resident_path(dev):
         assert np.array_equal(hr.doc_tok_offs, res.doc_tok_offs.cpu().numpy())
         assert np.array_equal(hr.doc_flags, res.doc_flags.cpu().numpy()) and hr.doc_flags[7] == 1
         assert hr.counters.tolist() == res.counters.cpu().tolist()
+
+
+def test_pad_batch_on_device(dev):
+    """Row f3: padded input_ids / attention_mask built on the device == what main_analyze_s2orc.py:87-89 +
+    DataCollatorWithPadding, and the input_ids + labels collator of main_biomed_translation.py:104-124, build on the host."""
+    from dptok import _cabi, synth
+    from dptok.engine import pack_documents
+    tok, t2i, eng = _llama_engine("llama2_2k", dev)
+    docs = [d.encode() for d in synth.sample_text(40_000, seed=9)]
+    tgt = [d[::-1].replace(b"  ", b" ").strip() or b"x" for d in docs]
+    text, offs = pack_documents(docs)
+    a = eng.encode_corpus(_to_dev(text, dev), _to_dev(offs, dev), _cabi.RULE_SPM_LLAMA)
+    text2, offs2 = pack_documents(tgt)
+    b = eng.encode_corpus(_to_dev(text2, dev), _to_dev(offs2, dev), _cabi.RULE_SPM_LLAMA)
+    ids_a, oa = a.ids.cpu().numpy(), a.doc_tok_offs.cpu().numpy()
+    ids_b, ob = b.ids.cpu().numpy(), b.doc_tok_offs.cpu().numpy()
+    rows_a = [ids_a[oa[d]:oa[d + 1]].tolist() for d in range(len(docs))]
+    rows_ab = [rows_a[d] + ids_b[ob[d]:ob[d + 1]].tolist() for d in range(len(docs))]
+    pad = 0
+    for rows, labels, left in ((rows_a, None, False), (rows_a, None, True), (rows_ab, b, False)):
+        for doc_begin, n_rows in ((0, len(docs)), (3, 7)):
+            inp, mask, lens = eng.pad_batch(a, pad, doc_begin=doc_begin, n_rows=n_rows, pad_left=left, labels=labels)
+            sel = rows[doc_begin:doc_begin + n_rows]
+            L = max(len(r) for r in sel)
+            exp = np.full((n_rows, L), pad, np.int64)
+            em = np.zeros((n_rows, L), np.int64)
+            for r, row in enumerate(sel):
+                if left:
+                    exp[r, L - len(row):] = row
+                    em[r, L - len(row):] = 1
+                else:
+                    exp[r, :len(row)] = row
+                    em[r, :len(row)] = 1
+            assert inp.dtype == torch.int64 and np.array_equal(inp.cpu().numpy(), exp)
+            assert np.array_equal(mask.cpu().numpy(), em) and lens.cpu().tolist() == [len(r) for r in sel]
+    # truncation to a fixed row length
+    inp, mask, lens = eng.pad_batch(a, pad, row_len=16)
+    assert inp.shape == (len(docs), 16) and all(inp[r, :16].tolist() == (rows_a[r] + [pad] * 16)[:16] for r in range(len(docs)))
+
+
+def test_corpus_statistics_driver(dev):
+    """Row f2: dptok.stats.probe_dp_vs_default == a literal restatement of main_analyze_s2orc.py:251-307 on the oracle."""
+    from dptok import assets, stats, synth
+    from oracle import adapters
+    tok = assets.load_hf("llama2_2k")
+    docs = synth.sample_text(60_000, seed=11)[:60] + ["the weather", "naïve 日本 12 %", "a  b"]
+    out = stats.probe_dp_vs_default(tok, docs, domains=["d%d" % (k % 3) for k in range(len(docs))])
+    inv = {i: t for t, i in tok.get_vocab().items()}
+    n_improved = 0
+    for k, a in enumerate(docs):
+        dp = adapters.llama_encode(tok, a)
+        default = tok.encode(a)
+        assert out["dp_length"][k] == len(dp) and out["default_length"][k] == len(default)
+        imp, worse = [], []
+        if len(dp) < len(default):
+            n_improved += 1
+            for token in adapters.llama_words(tok, a):
+                d2, f2 = adapters.llama_encode(tok, token), tok.encode(token)
+                if len(d2) < len(f2):
+                    imp.append([inv[i] for i in d2])
+                    worse.append([inv[i] for i in f2])
+        assert out["improved_tokens"][k] == imp and out["worse_tokens"][k] == worse
+    assert out["total_improved"] == n_improved and out["total"] == len(docs)
+    assert all(dl <= fl for dl, fl in zip(out["dp_length"], out["default_length"]))
