@@ -266,9 +266,10 @@ DPT_HD void pp_load16(const uint8_t* base4, int64_t off, int len, uint32_t v[4])
     v[3] = sh ? (a3 >> sh) | (a4 << (32u - sh)) : a3;
 #endif
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int rem = len - 4 * k;
-        v[k] &= rem >= 4 ? ~0u : rem <= 0 ? 0u : ((1u << (8 * rem)) - 1u);
+    for (int k = 0; k < 4; ++k) {  // keep min(max(len - 4k, 0), 4) bytes of word k
+        int rem = len - 4 * k;
+        rem = rem < 0 ? 0 : rem > 4 ? 4 : rem;
+        v[k] &= (uint32_t)((1ull << (8 * rem)) - 1ull);
     }
 }
 DPT_HD uint32_t pp_hash_step(uint32_t h, uint32_t v) {

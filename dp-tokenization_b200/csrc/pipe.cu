@@ -128,8 +128,8 @@ struct DevBlk {
     }
 };
 
-// SPM_LLAMA rule: 21 KB of shared memory and <= 40 registers -> 6 CTAs (48 warps) per SM
-__global__ void __launch_bounds__(PA_THREADS, 6) k_scan_dedup(const __grid_constant__ PipeParams P) {
+// SPM_LLAMA rule: 20 KB of shared memory and <= 32 registers -> 8 CTAs (64 warps) per SM
+__global__ void __launch_bounds__(PA_THREADS, 8) k_scan_dedup(const __grid_constant__ PipeParams P) {
     __shared__ ASmemT<true> S;
     DevBlk blk;
     pa_kernel<DevBlk, true>(blk, P, S);
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(PA_THREADS) k_scan_dedup_bl(const __grid_const
     pa_kernel<DevBlk, false>(blk, P, S);
 }
 
-__global__ void __launch_bounds__(PB_THREADS) k_dp_distinct(const __grid_constant__ PipeParams P) {
+__global__ void __launch_bounds__(PB_THREADS, 16) k_dp_distinct(const __grid_constant__ PipeParams P) {
     DevBlk blk;
     pb_thread(blk, P);
 }
@@ -348,7 +348,7 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
     }
     {
         ProfScope prof("k_dp_distinct", st);
-        k_dp_distinct<<<(unsigned)(sm_count * 12), PB_THREADS, 0, st>>>(P);
+        k_dp_distinct<<<(unsigned)(sm_count * 16), PB_THREADS, 0, st>>>(P);
         ++g_launches;
     }
     {
