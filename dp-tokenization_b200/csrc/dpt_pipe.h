@@ -46,6 +46,8 @@ constexpr int PA_THREADS = 256;
 constexpr int PA_MAXLEN = 63;                 // longest word body (bytes) that goes through the dedup table
 constexpr int PA_PROBES = 8;
 constexpr int PB_THREADS = 128;
+constexpr int PB_CLASSES = 4;                 // length classes of the DP work queues (8 measured no better: lane
+                                              // imbalance comes from walk depths, not from word length)
 constexpr int PB_LOCAL = 72;                  // normalised bytes solved with per-thread local state in kernel B
 constexpr int PC_THREADS = 256;
 constexpr int PC_PER = 8;                     // words per thread in kernel C
@@ -81,7 +83,7 @@ struct OddWord {
 
 struct PipeCtl {  // device-side counters, zeroed by the launcher
     unsigned int ticket_a, ticket_c;
-    unsigned int n_pending[4];  // distinct words queued for the DP, by length class (keeps a warp's lanes alike)
+    unsigned int n_pending[PB_CLASSES];  // distinct words queued for the DP, by length class (keeps a warp's lanes alike)
     unsigned int n_odd, n_long;
     unsigned long long lp_used, n_words, n_untok, n_too_long;
     unsigned long long b_cursor;  // next unclaimed item of kernel B's work list
@@ -158,7 +160,7 @@ struct ASmemT {
     uint32_t stage[PA_WIN];   // refs of the current window, written out coalesced once the word offset is known
     uint32_t scan[40];
     int32_t tile, d_first, n_entries;
-    uint32_t n_pend, n_pend_c[4], cur_c[4], base_c[4];
+    uint32_t n_pend, n_pend_c[PB_CLASSES], cur_c[PB_CLASSES], base_c[PB_CLASSES];
     int32_t n_sync, s_first;
     long long region_doc_end, first_sync_global;
     unsigned long long base_w;
@@ -284,7 +286,10 @@ DPT_HD uint32_t pp_eq4(uint32_t x, uint32_t c4) {
     t = ~(t | z | 0x7F7F7F7Fu);                 // 0x80 in every byte of z that is zero
     return ((t >> 7) * 0x01020408u) >> 24;      // gather the four flag bits
 }
-DPT_HD int pp_len_class(int len) { return len <= 6 ? 0 : len <= 10 ? 1 : len <= 16 ? 2 : 3; }
+// length class of a word body: lanes of a warp of kernel B get words of one class, i.e. of similar DP cost
+DPT_HD int pp_len_class(int len) {
+    return len <= 6 ? 0 : len <= 10 ? 1 : len <= 16 ? 2 : 3;
+}
 DPT_HD uint32_t pp_tail_mask(int nbytes) { return nbytes >= 4 ? ~0u : ((1u << (8 * nbytes)) - 1u); }
 
 DPT_HD unsigned long long pp_tag(uint32_t hash, int len, int64_t pos) {
@@ -349,7 +354,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
         if (tid == 0) {
             S.d_first = (int32_t)pp_lower_bound(P.doc_offs, P.n_docs + 1, g0 < 0 ? 0 : g0);
             S.n_pend = 0;
-            for (int c = 0; c < 4; ++c) S.n_pend_c[c] = S.cur_c[c] = 0;
+            for (int c = 0; c < PB_CLASSES; ++c) S.n_pend_c[c] = S.cur_c[c] = 0;
         }
     }
     blk.sync();
@@ -611,7 +616,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                             if (t == 0) {  // first occurrence of this word: claim the slot, queue the DP
                                 const uint32_t li = blk.atomic_add_ret(&S.n_pend, 1u);
                                 const uint32_t cls = (uint32_t)pp_len_class(len);
-                                S.pend[li] = slot | (cls << 30);
+                                S.pend[li] = slot | (cls << 29);
                                 blk.atomic_add(&S.n_pend_c[cls], 1u);
                                 ref = slot;
                                 done = true;
@@ -679,19 +684,19 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
             }
         }
         // ---- distinct words claimed in this window -> the DP queues (by length class) -------------------------------
-        for (int c = tid; c < 4; c += nt)
+        for (int c = tid; c < PB_CLASSES; c += nt)
             S.base_c[c] = S.n_pend_c[c] ? blk.atomic_add_ret(&P.ctl->n_pending[c], S.n_pend_c[c]) : 0u;
         blk.sync();
         const uint32_t npend = S.n_pend;
         for (uint32_t i = tid; i < npend; i += nt) {
-            const uint32_t v = S.pend[i], cls = v >> 30;
+            const uint32_t v = S.pend[i], cls = v >> 29;
             const uint32_t r = blk.atomic_add_ret(&S.cur_c[cls], 1u);
             P.pending[(size_t)cls * (size_t)P.pend_stride + S.base_c[cls] + r] = v & REF_INDEX;
         }
         blk.sync();
         if (tid == 0) {
             S.n_pend = 0;
-            for (int c = 0; c < 4; ++c) S.n_pend_c[c] = S.cur_c[c] = 0;
+            for (int c = 0; c < PB_CLASSES; ++c) S.n_pend_c[c] = S.cur_c[c] = 0;
         }
         lo += PA_WIN;
         if (lo < ne) blk.sync();
@@ -799,7 +804,7 @@ DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint64_t i, const uint32_t* npc,
         return it;
     }
     i -= n_odd;
-    uint32_t cls = 3;
+    uint32_t cls = PB_CLASSES - 1;
     while (cls > 0 && i >= npc[cls]) {
         i -= npc[cls];
         --cls;
@@ -818,9 +823,14 @@ DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint64_t i, const uint32_t* npc,
 // between them.
 template <class Blk>
 DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
-    const uint32_t npc[4] = {P.ctl->n_pending[0], P.ctl->n_pending[1], P.ctl->n_pending[2], P.ctl->n_pending[3]};
+    uint32_t npc[PB_CLASSES];
+    uint64_t total = 0;
+    for (int c = 0; c < PB_CLASSES; ++c) {
+        npc[c] = P.ctl->n_pending[c];
+        total += npc[c];
+    }
     const uint32_t n_odd = P.ctl->n_odd < (uint32_t)P.odd_cap ? P.ctl->n_odd : (uint32_t)P.odd_cap;
-    const uint64_t total = (uint64_t)npc[0] + npc[1] + npc[2] + npc[3] + n_odd;
+    total += n_odd;
     for (;;) {
         // every warp claims the next 32 items (dynamic: a warp stuck on long words does not hold the others back)
         const uint64_t i = blk.warp_take(&P.ctl->b_cursor);
@@ -876,7 +886,8 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
 // long words: one thread each, state in a global scratch pool (13 bytes per normalised position)
 template <class Blk>
 DPT_PIPE_FN void pb_long_thread(Blk& blk, const PipeParams& P, int64_t gtid, int64_t gthreads) {
-    const uint32_t npc[4] = {P.ctl->n_pending[0], P.ctl->n_pending[1], P.ctl->n_pending[2], P.ctl->n_pending[3]};
+    uint32_t npc[PB_CLASSES];
+    for (int c = 0; c < PB_CLASSES; ++c) npc[c] = P.ctl->n_pending[c];
     const uint32_t n_odd = P.ctl->n_odd < (uint32_t)P.odd_cap ? P.ctl->n_odd : (uint32_t)P.odd_cap;
     const uint32_t n_long = P.ctl->n_long;
     for (uint64_t k = (uint64_t)gtid; k < n_long; k += (uint64_t)gthreads) {

@@ -207,7 +207,7 @@ int64_t corpus_range_workspace(int64_t range_bytes, int64_t range_docs, int64_t 
     b += align_up(sizeof(PipeCtl), 256);
     b += align_up(z.n_tiles * 8 + 8, 256) + align_up(z.n_ctiles * 8 + 8, 256);
     b += align_up(word_cap * 4 + 64, 256);                   // refs
-    b += align_up(word_cap * 16 + 64, 256);                  // pending (4 length classes x word_cap)
+    b += align_up(word_cap * 4 * PB_CLASSES + 64, 256);      // pending (length classes x min(word_cap, n_slots); upper bound)
     b += align_up((range_docs + 1) * 8, 256);                // doc_first_word
     b += align_up(z.odd_cap * 16, 256) + align_up(z.odd_cap * 32, 256);  // odd, odd_res
     b += align_up((word_cap + z.odd_cap) * 4, 256);          // longq
@@ -316,8 +316,8 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
         P.desc_t = (unsigned long long*)take(z.n_ctiles * 8 + 8);
         const int64_t zero_bytes = used;
         P.refs = (uint32_t*)take(word_cap * 4 + 64);
-        P.pending = (uint32_t*)take(word_cap * 16 + 64);
-        P.pend_stride = word_cap;
+        P.pend_stride = word_cap < tz.n_slots ? word_cap : tz.n_slots;  // a pending word owns a table slot
+        P.pending = (uint32_t*)take(P.pend_stride * 4 * PB_CLASSES + 64);
         P.doc_first_word = (int64_t*)take((range_docs + 1) * 8);
         P.odd = (OddWord*)take(z.odd_cap * 16);
         P.odd_res = (ResRec*)take(z.odd_cap * 32);

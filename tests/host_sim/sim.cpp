@@ -208,7 +208,7 @@ int32_t sim_encode_corpus_pipe(void* vv, int32_t rule, const uint8_t* text, int6
         PipeCtl ctl{};
         std::vector<unsigned long long> dw(n_tiles + 1, 0), dt(n_ctiles + 1, 0);
         std::vector<ResRec> odd_res(odd_cap);
-        std::vector<uint32_t> refs(r_word_cap + 16), longq(r_word_cap + odd_cap + 16), pending(4 * r_word_cap + 16);
+        std::vector<uint32_t> refs(r_word_cap + 16), longq(r_word_cap + odd_cap + 16), pending(PB_CLASSES * r_word_cap + 16);
         P.pend_stride = r_word_cap;
         std::vector<int64_t> dfw(nd + 1, -1);
         std::vector<OddWord> odd(odd_cap);
