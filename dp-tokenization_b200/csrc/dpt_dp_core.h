@@ -235,16 +235,18 @@ DPT_HD uint32_t dpt_da_load(const uint32_t* da, uint32_t slot) {
 #endif
 }
 
-DPT_HD void dpt_forward_flat32(const DptVocabView& V, const uint8_t* s, int32_t n, uint32_t* best, uint8_t* A, uint8_t* B,
-                               uint32_t* As, uint32_t* Bs) {
+DPT_HD void dpt_forward_flat32(const DptVocabView& V, const uint8_t* s, int32_t n, uint32_t* best, uint32_t* Ap,
+                               uint32_t* Bp) {
+    // Ap/Bp: packed back-pointers  slot | distance << 22  (distance <= DPT_FLAT32_MAX, slots < 2^22): one 4-byte store
+    // per back-pointer and relaxation instead of a distance and a slot each
     const bool cp_mode = V.unit_mode != 0;
     uint32_t u = 0;
     for (int32_t p = 0; p <= n; ++p) {
         const bool b = (p == 0 || p == n || !cp_mode) ? true : dpt_is_cp_start(s[p]);
         best[p] = b ? ((u << 17) | 0x1FFFFu) : DPT_K32_NONE;  // phantom: len = unit index, not reachable
         if (b) ++u;
-        A[p] = 0;
-        B[p] = 0;
+        Ap[p] = 0;
+        Bp[p] = 0;
     }
     if (n > 0) best[0] = 0xFFFFu;  // origin: len 0, reachable, longest 0
     const uint32_t* __restrict__ da = V.da;
@@ -277,52 +279,37 @@ DPT_HD void dpt_forward_flat32(const DptVocabView& V, const uint8_t* s, int32_t 
             const uint32_t bi = best[i];
             if (bi != DPT_K32_NONE) {
                 const uint32_t k = dpt_k32_extend(kj, cl);
-                const uint32_t packed = slot | (cl << 22);  // cl <= 255 here, slots < 2^22
-                if ((k >> 16) <= (bi >> 16)) {
-                    A[i] = (uint8_t)(i - j);
-                    As[i] = packed;
-                }
+                const uint32_t packed = slot | ((uint32_t)(i - j) << 22);
+                if ((k >> 16) <= (bi >> 16)) Ap[i] = packed;
                 if (k <= bi) {
                     best[i] = k;
-                    B[i] = (uint8_t)(i - j);
-                    Bs[i] = packed;
+                    Bp[i] = packed;
                 }
             }
         }
     }
 }
 
-DPT_HD bool dpt_backward_flat32(const DptVocabView& V, int32_t n, const uint32_t* best, const uint8_t* A, const uint8_t* B,
-                                const uint32_t* As, const uint32_t* Bs, int32_t* out_ids, int64_t out_cap) {
-    const uint32_t kn = best[n];
-    if (!dpt_k32_reach(kn)) return false;
-    const uint32_t target = dpt_k32_longest(kn);
-    int64_t slot_out = (int64_t)dpt_k32_len(kn) - 1;
-    bool got = false;
-    int32_t i = n;
-    while (i > 0 && slot_out >= 0) {
-        const int32_t d = got ? A[i] : B[i];
-        if (d <= 0 || d > i) break;  // cannot happen on a reachable path; never spin on corrupt state
-        const uint32_t ts = got ? As[i] : Bs[i];
-        if (!got && (ts >> 22) == target) got = true;
-        if (slot_out < out_cap) out_ids[slot_out] = V.slot_id[ts & 0x3FFFFFu];
-        --slot_out;
-        i -= d;
-    }
-    return true;
-}
-
-// Backward chase shared by the compact variants: word_len ids into out_ids[0..word_len) in text order.
-DPT_HD void dpt_backward_chase(const DptVocabView& V, int32_t n, uint32_t word_len, uint32_t target, const uint8_t* A,
-                               const uint8_t* B, const uint32_t* As, const uint32_t* Bs, int32_t* out_ids, int64_t out_cap) {
+// Backward chase for dpt_forward_flat32: word_len ids into out_ids[0..word_len) in text order.  The code-point count of
+// a token is only needed until the token of length `target` has been taken.
+DPT_HD void dpt_backward_chase(const DptVocabView& V, const uint8_t* s, int32_t n, uint32_t word_len, uint32_t target,
+                               const uint32_t* Ap, const uint32_t* Bp, int32_t* out_ids, int64_t out_cap) {
+    const bool cp_mode = V.unit_mode != 0;
     int64_t slot_out = (int64_t)word_len - 1;
     bool got = false;
     int32_t i = n;
     while (i > 0 && slot_out >= 0) {
-        const int32_t d = got ? A[i] : B[i];
+        const uint32_t ts = got ? Ap[i] : Bp[i];
+        const int32_t d = (int32_t)(ts >> 22);
         if (d <= 0 || d > i) break;  // cannot happen on a reachable path; never spin on corrupt state
-        const uint32_t ts = got ? As[i] : Bs[i];
-        if (!got && (ts >> 22) == target) got = true;
+        if (!got) {
+            uint32_t cl = (uint32_t)d;
+            if (cp_mode) {
+                cl = 0;
+                for (int32_t p = i - d; p < i; ++p) cl += dpt_is_cp_start(s[p]) ? 1u : 0u;
+            }
+            if (cl == target) got = true;
+        }
         if (slot_out < out_cap) out_ids[slot_out] = V.slot_id[ts & 0x3FFFFFu];
         --slot_out;
         i -= d;

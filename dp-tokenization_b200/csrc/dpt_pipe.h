@@ -850,10 +850,8 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
         }
         blk.reconverge();
         const int32_t n = nlen > 0 ? nlen : 0;
-        uint32_t best[PB_LOCAL + 1];
-        uint8_t A[PB_LOCAL + 1], B[PB_LOCAL + 1];
-        uint32_t As[PB_LOCAL + 1], Bs[PB_LOCAL + 1];
-        dpt_forward_flat32(P.V, norm, n, best, A, B, As, Bs);
+        uint32_t best[PB_LOCAL + 1], Ap[PB_LOCAL + 1], Bp[PB_LOCAL + 1];
+        dpt_forward_flat32(P.V, norm, n, best, Ap, Bp);
         blk.reconverge();
         if (!valid || nlen < 0) continue;
         ResRec rec;
@@ -869,14 +867,14 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
         rec.meta = (word_len & 0xFFFFFFu) | (reach ? 0u : RES_UNTOK);
         if (reach) {
             if (word_len <= (uint32_t)RES_INLINE) {
-                dpt_backward_flat32(P.V, n, best, A, B, As, Bs, rec.ids, RES_INLINE);
+                dpt_backward_chase(P.V, norm, n, word_len, dpt_k32_longest(kn), Ap, Bp, rec.ids, RES_INLINE);
             } else {
                 const unsigned long long off = blk.atomic_add_u64_ret(&P.persist->pool_used, (unsigned long long)word_len);
                 rec.meta |= RES_POOLED;
                 rec.ids[0] = (int32_t)(uint32_t)(off & 0xFFFFFFFFull);
                 rec.ids[1] = (int32_t)(uint32_t)(off >> 32);
                 if ((int64_t)(off + word_len) <= P.pool_cap)
-                    dpt_backward_flat32(P.V, n, best, A, B, As, Bs, P.pool + off, (int64_t)word_len);
+                    dpt_backward_chase(P.V, norm, n, word_len, dpt_k32_longest(kn), Ap, Bp, P.pool + off, (int64_t)word_len);
             }
         }
         *it.out = rec;
@@ -927,6 +925,29 @@ DPT_PIPE_FN void pb_long_thread(Blk& blk, const PipeParams& P, int64_t gtid, int
 // =========================================================================================================
 // Kernel C: scan + emit
 // =========================================================================================================
+// streaming (evict-first) accesses for data touched once, so the result records keep their L2 lines
+DPT_PIPE_FN uint4 pc_ld_stream(const uint4* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+DPT_PIPE_FN void pc_st_stream(uint4* p, uint4 v) {
+#if defined(__CUDA_ARCH__)
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+DPT_PIPE_FN void pc_st_stream(int32_t* p, int32_t v) {
+#if defined(__CUDA_ARCH__)
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 DPT_PIPE_FN const ResRec* pc_record_ptr(const PipeParams& P, uint32_t ref) {
     if ((ref & REF_KIND) == REF_ODD) {
         const uint32_t j = ref & REF_INDEX;
@@ -953,8 +974,8 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
     uint32_t ref[PC_PER], meta[PC_PER];
     uint32_t mine = 0, untok = 0;
     if (w0 + PC_PER <= n_words) {  // two 16-byte loads of 8 refs
-        const uint4 r0 = *reinterpret_cast<const uint4*>(P.refs + w0);
-        const uint4 r1 = *reinterpret_cast<const uint4*>(P.refs + w0 + 4);
+        const uint4 r0 = pc_ld_stream(reinterpret_cast<const uint4*>(P.refs + w0));
+        const uint4 r1 = pc_ld_stream(reinterpret_cast<const uint4*>(P.refs + w0 + 4));
         ref[0] = r0.x; ref[1] = r0.y; ref[2] = r0.z; ref[3] = r0.w;
         ref[4] = r1.x; ref[5] = r1.y; ref[6] = r1.z; ref[7] = r1.w;
     } else {
@@ -979,8 +1000,8 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
         uint4 l0, l1;
         l0.x = meta[0] & 0xFFFFFFu; l0.y = meta[1] & 0xFFFFFFu; l0.z = meta[2] & 0xFFFFFFu; l0.w = meta[3] & 0xFFFFFFu;
         l1.x = meta[4] & 0xFFFFFFu; l1.y = meta[5] & 0xFFFFFFu; l1.z = meta[6] & 0xFFFFFFu; l1.w = meta[7] & 0xFFFFFFu;
-        *reinterpret_cast<uint4*>(P.word_lens + w0) = l0;
-        *reinterpret_cast<uint4*>(P.word_lens + w0 + 4) = l1;
+        pc_st_stream(reinterpret_cast<uint4*>(P.word_lens + w0), l0);
+        pc_st_stream(reinterpret_cast<uint4*>(P.word_lens + w0 + 4), l1);
         unsigned long long f = 0;
 #pragma unroll
         for (int k = 0; k < PC_PER; ++k)
@@ -1045,7 +1066,7 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
         const int64_t base_t = (int64_t)S.base_t;
         if (staged)
             for (uint32_t q = (uint32_t)tid; q < total; q += (uint32_t)blk.nthreads())
-                if (base_t + q < P.ids_cap) P.ids[base_t + q] = S.ids[q];
+                if (base_t + q < P.ids_cap) pc_st_stream(P.ids + base_t + q, S.ids[q]);
         // document token offsets
         int64_t gt = base_t + off;
 #pragma unroll
