@@ -25,6 +25,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "dp-tokenization_b200"))
 
+WORKLOADS = {
+    # name: (asset, vocabulary family, rule, description)
+    "s2orc_llama2": ("llama2_32k", "spm", "RULE_SPM_LLAMA",
+                     "configs[1]: Llama-2-shaped 32k SentencePiece-BPE vocab, 100 MB synthetic S2ORC-shaped abstracts per GPU"),
+    "pairs_gpt2": ("gpt2_50k", "bytelevel", "RULE_GPT2",
+                   "configs[2]: GPT-2-shaped 50k byte-level BPE vocab, en/de biomedical-translation-shaped sentence pairs"),
+    "longdocs_llama3": ("llama3_128k", "bytelevel", "RULE_LLAMA3",
+                        "configs[3]-shaped: Llama-3-shaped 128k byte-level vocab, 8-64 KB documents (60 % English, 40 % "
+                        "Arabic script with diacritics)"),
+}
 METRIC = "corpus_bytes_per_sec"
 UNIT = "bytes/s"
 ASSET = "llama2_32k"
@@ -169,6 +179,8 @@ def main():
     ap.add_argument("--size-mb", type=float, default=100.0, help="corpus bytes per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="s2orc_llama2", choices=sorted(WORKLOADS),
+                    help="default = BASELINE.json configs[1]; the others are extra measurements, not the contract line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -206,12 +218,24 @@ def main():
 
     # ---- workload: this rank's shard (documents are independent; each rank generates its own) ----
     n_bytes_target = int(args.size_mb * 1e6)
-    lexicon = synth.make_lexicon(200_000, seed=0)
-    text, doc_offs = synth.gen_documents(n_bytes_target, seed=rank, lexicon=lexicon)
+    asset, family, rule_name, workload_desc = WORKLOADS[args.workload]
+    RULE = getattr(_cabi, rule_name)
+    if args.workload == "s2orc_llama2":
+        lexicon = synth.make_lexicon(200_000, seed=0)
+        text, doc_offs = synth.gen_documents(n_bytes_target, seed=rank, lexicon=lexicon)
+    elif args.workload == "pairs_gpt2":
+        text, doc_offs = synth.gen_sentence_pairs(n_bytes_target, seed=rank)
+    else:
+        t_en, o_en = synth.gen_documents(int(0.6 * n_bytes_target), seed=rank, words_per_doc=(1200, 9000))
+        t_ar, o_ar = synth.gen_documents(int(0.4 * n_bytes_target), seed=rank + 1000, flavour="ar", words_per_doc=(800, 6000))
+        text = np.concatenate([t_en, t_ar])
+        doc_offs = np.concatenate([o_en, o_ar[1:] + o_en[-1]])
     n_bytes, n_docs = len(text), len(doc_offs) - 1
-    tok = assets.load_hf(ASSET)
-    t2i = tok.get_vocab()
-    engine = Engine(CompiledVocab.from_token_map(t2i, "spm"), dev)
+    if family == "spm":
+        t2i = assets.load_hf(asset).get_vocab()
+    else:
+        t2i = {t: k for k, t in enumerate(assets.load_spec(asset)["model"]["vocab"])}
+    engine = Engine(CompiledVocab.from_token_map(t2i, family), dev)
     h_text = torch.from_numpy(text).pin_memory()
     h_offs = torch.from_numpy(doc_offs).pin_memory()
     d_text = h_text.to(dev, non_blocking=True)
@@ -219,7 +243,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step():
-        res = engine.encode_corpus(d_text, d_offs, _cabi.RULE_SPM_LLAMA)
+        res = engine.encode_corpus(d_text, d_offs, RULE)
         stats = reduce_counters(res.counters, None) if world > 1 else None
         return res, stats
 
@@ -244,7 +268,7 @@ def main():
     for k in range(args.steps):
         flush.fill_(k & 0xFF)
         ev[k][0].record()
-        res = engine.encode_corpus(d_text, d_offs, _cabi.RULE_SPM_LLAMA, ids_cap=ids_cap, word_cap=word_cap)
+        res = engine.encode_corpus(d_text, d_offs, RULE, ids_cap=ids_cap, word_cap=word_cap)
         if world > 1:
             reduce_counters(res.counters, None)
         ev[k][1].record()
@@ -295,7 +319,7 @@ def main():
         h_ids = torch.empty(ids_cap, dtype=torch.int32).pin_memory()
 
         def e2e_step():
-            r = engine.encode_corpus_host(h_text, doc_offs, _cabi.RULE_SPM_LLAMA, out_ids=h_ids)
+            r = engine.encode_corpus_host(h_text, doc_offs, RULE, out_ids=h_ids)
             if world > 1:
                 c = torch.from_numpy(r.counters).to(dev)
                 reduce_counters(c, None)
@@ -320,7 +344,7 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "s2orc_llama2":
         r = cpu_reference_leg(16_000_000, budget_s=15.0)
         cpu = {"value": r["bytes_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "tokens_per_sec": r["tokens_per_s"],
@@ -334,8 +358,7 @@ def main():
             "dtype": "int32", "data": "synthetic",
             "tokens_per_sec": g_tokens * args.steps / (total_ms / 1e3),
             "bytes_per_token": g_bytes / max(g_tokens, 1),
-            "config": {"workload": "configs[1]: Llama-2-shaped 32k SentencePiece-BPE vocab, 100 MB synthetic S2ORC-shaped "
-                                   "abstracts per GPU", "vocab": ASSET, "bytes_per_gpu": n_bytes, "docs_per_gpu": n_docs,
+            "config": {"workload": workload_desc, "vocab": asset, "bytes_per_gpu": n_bytes, "docs_per_gpu": n_docs,
                        "words_per_gpu": n_words, "tokens_per_gpu": n_tokens, "parallelism": f"doc-sharded x{world}",
                        "l2": "256 MiB buffer written between timed steps (L2 flush)", "timing": "CUDA events per step"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),

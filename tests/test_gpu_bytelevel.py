@@ -98,3 +98,36 @@ def test_bytelevel_adapter_batch_uses_device_rule(dev):
         out = enc.batch(docs)
         for d, ids in zip(docs[:40] + docs[-2:], out[:40] + out[-2:]):
             assert ids == enc(d) and dec(ids) == d
+
+
+def test_full_size_properties_llama3_100mb(dev):
+    """BASELINE.json configs[3]/[4] shape at 100 MB (Llama-3-shaped 128k byte-level vocabulary, 8-64 KB English documents
+    followed by Arabic-script documents with diacritics, split regex on the device): size-independent properties - the
+    device decode round-trips every document, counters are consistent, two runs are identical, the DP never uses more
+    tokens than the default BPE - plus exact oracle parity (tokenizers' pieces + C oracle) on a document sample."""
+    from dptok import _cabi, synth
+    tok, v2i, vb, eng = _engine("llama3_128k", dev)
+    t_en, o_en = synth.gen_documents(60_000_000, seed=0, words_per_doc=(1200, 9000))
+    t_ar, o_ar = synth.gen_documents(40_000_000, seed=1, flavour="ar", words_per_doc=(800, 6000))
+    text = np.concatenate([t_en, t_ar])
+    doc_offs = np.concatenate([o_en, o_ar[1:] + o_en[-1]])
+    n_docs = len(doc_offs) - 1
+    d_text, d_offs = _to_dev(text, dev), _to_dev(doc_offs, dev)
+    res = eng.encode_corpus(d_text, d_offs, _cabi.RULE_LLAMA3)
+    c = res.counters.cpu().tolist()
+    assert c[0] == len(text) and c[1] == res.n_words and c[2] == res.n_ids and c[3] == 0
+    assert int(res.word_lens.sum()) == res.n_ids
+    assert bool(eng.roundtrip_ok(res, d_text, d_offs, skip_bos=False).all())
+    dto = res.doc_tok_offs.cpu().numpy()
+    assert dto[0] == 0 and dto[-1] == res.n_ids and (np.diff(dto) > 0).all()
+    res2 = eng.encode_corpus(d_text, d_offs, _cabi.RULE_LLAMA3)
+    assert torch.equal(res.ids, res2.ids) and torch.equal(res.word_lens, res2.word_lens)
+    ids = res.ids.cpu().numpy()
+    raw = text.tobytes()
+    sample = random.Random(1).sample(range(n_docs), 120)
+    docs = [raw[doc_offs[d]:doc_offs[d + 1]] for d in sample]
+    words, o_ids, o_lens, o_untok, o_dto = _expected(tok, vb, docs)
+    for k, d in enumerate(sample):
+        assert np.array_equal(ids[dto[d]:dto[d + 1]], o_ids[o_dto[k]:o_dto[k + 1]])
+    for k, d in enumerate(sample[:15]):
+        assert dto[d + 1] - dto[d] <= len(tok.encode(docs[k].decode()).ids)
