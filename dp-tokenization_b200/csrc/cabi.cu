@@ -426,7 +426,7 @@ int dpt_encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_t
                             void* d_table_workspace, int64_t table_workspace_bytes, void* d_workspace,
                             int64_t workspace_bytes, int32_t worst_case, int32_t phases, void* stream) {
     if (int rc = check_ready(v, "dpt_encode_corpus_range")) return rc;
-    if (phases < 0 || phases > 3) return fail(DPT_EINVAL, "dpt_encode_corpus_range: phases must be 0..3");
+    if (phases < 0 || phases > 7) return fail(DPT_EINVAL, "dpt_encode_corpus_range: phases must be 0..7");
     if (rule != DPT_RULE_SPM_LLAMA && rule != DPT_RULE_GPT2 && rule != DPT_RULE_LLAMA3)
         return fail(DPT_EINVAL, "dpt_encode_corpus_range: rule not available on device in this build");
     std::string err;

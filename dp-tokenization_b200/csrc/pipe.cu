@@ -301,7 +301,7 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
         P.slot_mask = (uint32_t)(tz.n_slots - 1);
         if (reset_table) cudaMemsetAsync(base, 0, (size_t)zero_bytes, st);
     }
-    const bool do_scan = (phases & 1) != 0, do_emit = (phases & 2) != 0;
+    const bool do_scan = (phases & 1) != 0, do_dp = (phases & 2) != 0, do_emit = (phases & 4) != 0;
     {   // range part: everything that must start zeroed is contiguous
         char* base = (char*)d_ws;
         int64_t used = 0;
@@ -346,6 +346,8 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
             k_scan_dedup_bl<<<(unsigned)P.n_tiles, PA_THREADS, 0, st>>>(P);
         ++g_launches;
     }
+    }
+    if (do_dp) {
     {
         ProfScope prof("k_dp_distinct", st);
         k_dp_distinct<<<(unsigned)(sm_count * 16), PB_THREADS, 0, st>>>(P);
@@ -393,7 +395,7 @@ int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, 
     const int64_t tb_al = align_up(tb, 256);
     return encode_corpus_range(v, rule, d_text, n_bytes, d_doc_offs, n_docs, 0, n_bytes, 0, n_docs, 1, n_bytes, word_cap, d_ids,
                                ids_cap, d_word_lens, d_word_flags, word_cap, d_doc_tok_offs, d_doc_flags, d_counters, d_n_out,
-                               d_ws, tb_al, (char*)d_ws + tb_al, ws_bytes - tb_al, worst, 3, st, err);
+                               d_ws, tb_al, (char*)d_ws + tb_al, ws_bytes - tb_al, worst, 7, st, err);
 }
 
 }  // namespace dpt

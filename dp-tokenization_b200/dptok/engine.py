@@ -170,8 +170,8 @@ class Engine:
         """``h_text``: uint8 HOST tensor (pinned for full speed) of concatenated non-empty documents; ``doc_offs``:
         int64[n_docs+1] numpy array.  The corpus is cut at document boundaries into ranges of about ``chunk_bytes``.
         Range k is copied into its place in ONE device text buffer on the copy-in stream, tokenized by
-        ``dpt_encode_corpus_range`` (scan + DP on one of two scan streams, emit on the emit stream; the word table is
-        shared by all ranges of the call, so a word is still solved once per corpus) and its ids are copied out on the
+        ``dpt_encode_corpus_range`` (scans in order on the scan stream, DP kernels on two alternating streams, emit on
+        the emit stream; the word table is shared by all ranges of the call, so a word is still solved once per corpus) and its ids are copied out on the
         copy-out stream over a ring of ``n_streams`` output slots: PCIe in both directions and the SMs work at the same
         time, and the latency-bound DP kernel of one range runs beside the scan of the next.  Returns host tensors."""
         assert h_text.dtype == torch.uint8 and not h_text.is_cuda
@@ -202,13 +202,14 @@ class Engine:
                 ws_bytes = lib.dpt_encode_corpus_range_workspace(rule, max_b, max_d, word_cap, 0)
                 tws_bytes = lib.dpt_corpus_table_workspace(n_bytes, word_cap_total, 0)
                 self._host = dict(
-                    streams=[torch.cuda.Stream(device=dev) for _ in range(5)],  # copy-in, scan x2, emit, copy-out
+                    streams=[torch.cuda.Stream(device=dev) for _ in range(6)],  # copy-in, scan, DP x2, emit, copy-out
                     ev_reset=torch.cuda.Event(),
                     d_text=torch.empty(n_bytes, dtype=torch.uint8, device=dev),
                     d_offs=torch.empty(n_docs + 1, dtype=torch.int64, device=dev),
                     h_offs=torch.empty(n_docs + 1, dtype=torch.int64).pin_memory(),
                     table_ws=torch.empty(int(tws_bytes), dtype=torch.uint8, device=dev),
-                    slots=[dict(ev_in=torch.cuda.Event(), ev_ab=torch.cuda.Event(), ev_comp=torch.cuda.Event(),
+                    slots=[dict(ev_in=torch.cuda.Event(), ev_a=torch.cuda.Event(), ev_ab=torch.cuda.Event(),
+                                ev_comp=torch.cuda.Event(),
                                 ev_out=torch.cuda.Event(),
                                 ids=torch.empty(ids_cap, dtype=torch.int32, device=dev),
                                 lens=torch.empty(word_cap, dtype=torch.int32, device=dev),
@@ -224,7 +225,7 @@ class Engine:
                 self._host_key = key
             H = self._host
             slots = H["slots"]
-            s_in, s_scan0, s_scan1, s_emit, s_out = H["streams"]
+            s_in, s_scan, s_dp0, s_dp1, s_emit, s_out = H["streams"]
             cur = torch.cuda.current_stream(dev)
             for st in H["streams"]:
                 st.wait_stream(cur)
@@ -273,11 +274,9 @@ class Engine:
                     _ptr(sl["n_out"]), _ptr(H["table_ws"]), H["table_ws"].numel(), _ptr(sl["ws"]), sl["ws"].numel(), 0,
                     phases, C.c_void_p(stream.cuda_stream)))
 
-            # clear the word table once; both scan streams start behind that
-            with torch.cuda.stream(s_scan0):
-                range_call(slots[0], 0, 0, 1, s_scan0)
-                H["ev_reset"].record(s_scan0)
-            s_scan1.wait_event(H["ev_reset"])
+            # clear the word table once, on the scan stream, in front of the first scan
+            with torch.cuda.stream(s_scan):
+                range_call(slots[0], 0, 0, 1, s_scan)
             prev_ab = None
             for k in range(n_chunks):
                 sl = slots[k % n_streams]
@@ -290,25 +289,31 @@ class Engine:
                     H["d_text"][b0:b1].copy_(h_text[b0:b1], non_blocking=True)
                     sl["ev_in"].record(s_in)
                     mark("h2d-end", k, s_in)
-                # phase 1 (scan + dedup + DP of the new words) alternates between two streams: the scan of range k+1
-                # runs beside the latency-bound DP kernel of range k
-                s_scan = s_scan0 if k % 2 == 0 else s_scan1
+                # scans run in range order on ONE stream: a range may only reference table slots claimed by itself or
+                # by an earlier range (whose DP results emit(k) waits for)
                 with torch.cuda.stream(s_scan):
                     s_scan.wait_event(sl["ev_in"])
                     s_scan.wait_event(sl["ev_comp"])        # the slot's previous range has been emitted
                     mark("scan-begin", k, s_scan)
                     range_call(sl, k, 1, 0, s_scan)
-                    sl["ev_ab"].record(s_scan)
+                    sl["ev_a"].record(s_scan)
                     mark("scan-end", k, s_scan)
-                # phase 2 (emit) needs the DP results of every range up to k: ev_ab of k and of k-1 (the two scan
-                # streams are each in order, so these two cover all earlier ranges)
+                # the latency-bound DP kernel of range k alternates between two streams and runs beside scan(k+1)
+                s_dp = s_dp0 if k % 2 == 0 else s_dp1
+                with torch.cuda.stream(s_dp):
+                    s_dp.wait_event(sl["ev_a"])
+                    range_call(sl, k, 2, 0, s_dp)
+                    sl["ev_ab"].record(s_dp)
+                    mark("dp-end", k, s_dp)
+                # emit needs the DP results of every range up to k: ev_ab of k and of k-1 (the two DP streams are each in
+                # order, so these two cover all earlier ranges)
                 with torch.cuda.stream(s_emit):
                     s_emit.wait_event(sl["ev_ab"])
                     if prev_ab is not None:
                         s_emit.wait_event(prev_ab)
                     s_emit.wait_event(sl["ev_out"])         # the slot's previous ids have been copied out
                     mark("emit-begin", k, s_emit)
-                    range_call(sl, k, 2, 0, s_emit)
+                    range_call(sl, k, 4, 0, s_emit)
                     sl["h_small"][:8].copy_(sl["n_out"], non_blocking=True)
                     sl["h_small"][8:12].copy_(sl["counters"], non_blocking=True)
                     sl["h_doc_tok"][:hi - lo + 1].copy_(sl["doc_tok"][:hi - lo + 1], non_blocking=True)

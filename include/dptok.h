@@ -211,11 +211,12 @@ int dpt_encode_corpus(const dpt_vocab* v, int32_t rule,
  *      corpus, not once per chunk.  d_doc_offs holds corpus-global offsets; outputs are range-local exactly as
  *      dpt_encode_corpus would produce them for the range alone (ids from 0, d_doc_tok_offs[doc_end-doc_begin+1],
  *      d_doc_flags[doc_end-doc_begin]).  d_workspace: dpt_encode_corpus_range_workspace (per range).
- *      phases: bit 0 = scan + dedup + DP of the range's new words, bit 1 = emit; 3 = the whole range.  Split calls
- *      let consecutive ranges overlap on different streams: the scan/DP of range k+1 may run beside the DP/emit of
- *      range k (the table is updated atomically); only emit(k+1) must be ordered after scan+DP(k) - the caller
- *      inserts that stream dependency - and after its own phase 1.  phases = 0 with reset_table = 1 just clears the
- *      table. */
+ *      phases: bit 0 = scan + dedup (kernel A), bit 1 = DP of the words this range claimed (kernels B), bit 2 = emit
+ *      (kernels C, D); 7 = the whole range.  Split calls let consecutive ranges overlap on different streams under
+ *      these rules, which the caller enforces with stream dependencies:  scan(k+1) after scan(k)  (a range may only
+ *      reference slots claimed by itself or an earlier range);  DP(k) after scan(k);  emit(k) after DP(j) for every
+ *      j <= k.  DP(k) may run beside scan(k+1) and emit(k-1) - it is latency-bound and leaves most of the SMs idle.
+ *      phases = 0 with reset_table = 1 just clears the table. */
 int64_t dpt_corpus_table_workspace(int64_t n_bytes_total, int64_t word_cap_total, int32_t worst_case);
 int64_t dpt_encode_corpus_range_workspace(int32_t rule, int64_t range_bytes, int64_t range_docs, int64_t word_cap,
                                           int32_t worst_case);

@@ -131,3 +131,23 @@ def test_full_size_properties_llama3_100mb(dev):
         assert np.array_equal(ids[dto[d]:dto[d + 1]], o_ids[o_dto[k]:o_dto[k + 1]])
     for k, d in enumerate(sample[:15]):
         assert dto[d + 1] - dto[d] <= len(tok.encode(docs[k].decode()).ids)
+
+
+def test_host_chunked_path_bytelevel(dev):
+    """Engine.encode_corpus_host with the Llama-3 rule: ranges overlap on several streams and share one word table; the
+    stitched result must equal the resident single-batch result for every chunking (repeated: the overlap is timing
+    dependent)."""
+    from dptok import _cabi, synth
+    tok, v2i, vb, eng = _engine("llama3_128k", dev)
+    t_en, o_en = synth.gen_documents(18_000_000, seed=3, words_per_doc=(1200, 9000))
+    t_ar, o_ar = synth.gen_documents(12_000_000, seed=4, flavour="ar", words_per_doc=(800, 6000))
+    text = np.concatenate([t_en, t_ar])
+    doc_offs = np.concatenate([o_en, o_ar[1:] + o_en[-1]])
+    res = eng.encode_corpus(_to_dev(text, dev), _to_dev(doc_offs, dev), _cabi.RULE_LLAMA3)
+    ids, dto, ctr = res.ids.cpu().numpy(), res.doc_tok_offs.cpu().numpy(), res.counters.cpu().tolist()
+    h_text = torch.from_numpy(text.copy()).pin_memory()
+    for rep in range(3):
+        for chunk, ns in ((1 << 20, 3), (3_000_000, 2), (8 << 20, 4)):
+            hr = eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_LLAMA3, chunk_bytes=chunk, n_streams=ns)
+            assert hr.n_ids == res.n_ids and hr.counters.tolist() == ctr
+            assert np.array_equal(hr.ids.numpy(), ids) and np.array_equal(hr.doc_tok_offs, dto)
