@@ -466,12 +466,32 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                     dend = nd < PA_R ? g0 + nd : (int64_t)S.region_doc_end;
                 }
                 const int64_t stop = limit < dend ? limit : dend;
+                // Inside the region the scanner reads the shared-memory copy of the text (index g -> S.text[g - g0]).
+                // It looks at most one character past the end of a piece, so a piece end more than 4 bytes in front of
+                // the region end was decided on loaded bytes only; closer than that the scan stops and the word stays
+                // open (its end is then found from global memory by the probe loop).
+                const int64_t rend = g0 + PA_R;
+                const int64_t send = dend < rend ? dend : rend;
+                const uint8_t* tsm = S.text - g0;
+                bool undecided = false;
                 while (p < stop) {
+                    int64_t pe;
+                    if (p >= g0) {
+                        pe = dpt_piece_end(P.rule, U, tsm, p, send);
+                        if (send < dend && pe + 4 > rend) {
+                            undecided = true;
+                            const int64_t r = p - g0;
+                            blk.atomic_or(&S.mWS[r >> 5], 1u << (r & 31));
+                            break;
+                        }
+                    } else {
+                        pe = dpt_piece_end(P.rule, U, P.text, p, dend);  // the stretch that starts before the region
+                    }
                     const int64_t r = p - g0;
                     if (r >= 0) blk.atomic_or(&S.mWS[r >> 5], 1u << (r & 31));
-                    p = dpt_piece_end(P.rule, U, P.text, p, dend);
+                    p = pe;
                 }
-                if (p >= g0 && p < g0 + PA_R && p < n) {  // the piece start the scan landed on (next sync / tile end)
+                if (!undecided && p >= g0 && p < g0 + PA_R && p < n) {  // the piece start the scan landed on
                     const int64_t r = p - g0;
                     blk.atomic_or(&S.mWS[r >> 5], 1u << (r & 31));
                 }

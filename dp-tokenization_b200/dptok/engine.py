@@ -170,10 +170,10 @@ class Engine:
         """``h_text``: uint8 HOST tensor (pinned for full speed) of concatenated non-empty documents; ``doc_offs``:
         int64[n_docs+1] numpy array.  The corpus is cut at document boundaries into ranges of about ``chunk_bytes``.
         Range k is copied into its place in ONE device text buffer on the copy-in stream, tokenized by
-        ``dpt_encode_corpus_range`` (scans in order on the scan stream, DP kernels on two alternating streams, emit on
-        the emit stream; the word table is shared by all ranges of the call, so a word is still solved once per corpus) and its ids are copied out on the
+        ``dpt_encode_corpus_range`` on the compute stream (ranges in order; the word table is shared by all ranges
+        of the call, so a word is still solved once per corpus) and its ids are copied out on the
         copy-out stream over a ring of ``n_streams`` output slots: PCIe in both directions and the SMs work at the same
-        time, and the latency-bound DP kernel of one range runs beside the scan of the next.  Returns host tensors."""
+        time.  Returns host tensors."""
         assert h_text.dtype == torch.uint8 and not h_text.is_cuda
         doc_offs = np.ascontiguousarray(doc_offs, dtype=np.int64)
         n_docs = len(doc_offs) - 1
@@ -202,7 +202,7 @@ class Engine:
                 ws_bytes = lib.dpt_encode_corpus_range_workspace(rule, max_b, max_d, word_cap, 0)
                 tws_bytes = lib.dpt_corpus_table_workspace(n_bytes, word_cap_total, 0)
                 self._host = dict(
-                    streams=[torch.cuda.Stream(device=dev) for _ in range(6)],  # copy-in, scan, DP x2, emit, copy-out
+                    streams=[torch.cuda.Stream(device=dev) for _ in range(3)],  # copy-in, compute, copy-out
                     ev_reset=torch.cuda.Event(),
                     d_text=torch.empty(n_bytes, dtype=torch.uint8, device=dev),
                     d_offs=torch.empty(n_docs + 1, dtype=torch.int64, device=dev),
@@ -225,7 +225,7 @@ class Engine:
                 self._host_key = key
             H = self._host
             slots = H["slots"]
-            s_in, s_scan, s_dp0, s_dp1, s_emit, s_out = H["streams"]
+            s_in, s_comp, s_out = H["streams"]
             cur = torch.cuda.current_stream(dev)
             for st in H["streams"]:
                 st.wait_stream(cur)
@@ -274,10 +274,6 @@ class Engine:
                     _ptr(sl["n_out"]), _ptr(H["table_ws"]), H["table_ws"].numel(), _ptr(sl["ws"]), sl["ws"].numel(), 0,
                     phases, C.c_void_p(stream.cuda_stream)))
 
-            # clear the word table once, on the scan stream, in front of the first scan
-            with torch.cuda.stream(s_scan):
-                range_call(slots[0], 0, 0, 1, s_scan)
-            prev_ab = None
             for k in range(n_chunks):
                 sl = slots[k % n_streams]
                 if len(pending) >= n_streams:               # the slot's previous range must have left the GPU
@@ -289,38 +285,21 @@ class Engine:
                     H["d_text"][b0:b1].copy_(h_text[b0:b1], non_blocking=True)
                     sl["ev_in"].record(s_in)
                     mark("h2d-end", k, s_in)
-                # scans run in range order on ONE stream: a range may only reference table slots claimed by itself or
-                # by an earlier range (whose DP results emit(k) waits for)
-                with torch.cuda.stream(s_scan):
-                    s_scan.wait_event(sl["ev_in"])
-                    s_scan.wait_event(sl["ev_comp"])        # the slot's previous range has been emitted
-                    mark("scan-begin", k, s_scan)
-                    range_call(sl, k, 1, 0, s_scan)
-                    sl["ev_a"].record(s_scan)
-                    mark("scan-end", k, s_scan)
-                # the latency-bound DP kernel of range k alternates between two streams and runs beside scan(k+1)
-                s_dp = s_dp0 if k % 2 == 0 else s_dp1
-                with torch.cuda.stream(s_dp):
-                    s_dp.wait_event(sl["ev_a"])
-                    range_call(sl, k, 2, 0, s_dp)
-                    sl["ev_ab"].record(s_dp)
-                    mark("dp-end", k, s_dp)
-                # emit needs the DP results of every range up to k: ev_ab of k and of k-1 (the two DP streams are each in
-                # order, so these two cover all earlier ranges)
-                with torch.cuda.stream(s_emit):
-                    s_emit.wait_event(sl["ev_ab"])
-                    if prev_ab is not None:
-                        s_emit.wait_event(prev_ab)
-                    s_emit.wait_event(sl["ev_out"])         # the slot's previous ids have been copied out
-                    mark("emit-begin", k, s_emit)
-                    range_call(sl, k, 4, 0, s_emit)
+                # ranges are tokenized in order on ONE compute stream: a range may only reference table slots claimed by
+                # itself or an earlier range, and emit(k) needs every DP result up to k.  (Measured: splitting the range
+                # call into scan / DP / emit phases on separate streams - dpt_encode_corpus_range's `phases` - costs
+                # more in launches and events than the overlap of the latency-bound DP kernel gains: 4.0 vs 3.4 ms.)
+                with torch.cuda.stream(s_comp):
+                    s_comp.wait_event(sl["ev_in"])
+                    s_comp.wait_event(sl["ev_out"])         # the slot's previous ids have been copied out
+                    mark("comp-begin", k, s_comp)
+                    range_call(sl, k, 7, 1 if k == 0 else 0, s_comp)
                     sl["h_small"][:8].copy_(sl["n_out"], non_blocking=True)
                     sl["h_small"][8:12].copy_(sl["counters"], non_blocking=True)
                     sl["h_doc_tok"][:hi - lo + 1].copy_(sl["doc_tok"][:hi - lo + 1], non_blocking=True)
                     sl["h_doc_flags"][:hi - lo].copy_(sl["doc_flags"][:hi - lo], non_blocking=True)
-                    sl["ev_comp"].record(s_emit)
-                    mark("emit-end", k, s_emit)
-                prev_ab = sl["ev_ab"]
+                    sl["ev_comp"].record(s_comp)
+                    mark("comp-end", k, s_comp)
                 pending.append((k, sl))
             while pending:
                 finalize(*pending.pop(0))
