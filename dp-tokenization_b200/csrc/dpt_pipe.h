@@ -155,13 +155,15 @@ struct ASmemT {
     uint32_t mCX[PA_NW + 2];  // positions that make their word "odd" (solved from the raw text, not deduplicated)
     uint32_t mSY[PA_NW + 2];  // byte-level rules: synchronisation points of the split scanner
     uint32_t cnt[PA_NW + 2];
+    uint32_t dsn[PA_NW + 2];  // byte-level rules: document starts in front of each mask word
     uint16_t wlist[WL_CAP];   // region index of the words of the current window (| 0x8000: a document's '<s>' word)
+    uint16_t dslist[kSpm ? 2 : PA_R + 32];  // byte-level rules: region indices of the document starts, in order
     uint32_t pend[PA_WIN];    // table slots claimed in the current window
     uint32_t stage[PA_WIN];   // refs of the current window, written out coalesced once the word offset is known
     uint32_t scan[40];
     int32_t tile, d_first, n_entries;
     uint32_t n_pend, n_pend_c[PB_CLASSES], cur_c[PB_CLASSES], base_c[PB_CLASSES];
-    int32_t n_sync, s_first;
+    int32_t n_sync, s_first, n_ds;
     long long region_doc_end, first_sync_global;
     unsigned long long base_w;
 };
@@ -387,9 +389,42 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
 
     // ---- boundary rule -> word starts ---------------------------------------------------------------------
     if (!spm) {
-        // Byte-level rules (dpt_split_rules.h).  (1) synchronisation points: document starts and every space whose
-        // next character is a non-whitespace character of the same document.
+        // Byte-level rules (dpt_split_rules.h).  (0) for every mask word the next document start at or after it
+        // (documents are long: without this every "where does this document end" question scans the whole mask).
         const DptUniView U{P.V.uni1, P.V.uni2};
+        {
+            const int chunk = (PA_NW + nt - 1) / nt;
+            const int w0 = tid * chunk, w1 = (w0 + chunk) < PA_NW ? (w0 + chunk) : PA_NW;
+            uint32_t mine = 0;
+            for (int w = w0; w < w1; ++w) mine += (uint32_t)pp_popc(S.mDS[w]);
+            uint32_t total;
+            uint32_t off = blk.exclusive_scan(mine, S.scan, total);
+            for (int w = w0; w < w1; ++w) {
+                S.dsn[w] = off;  // document starts in front of mask word w
+                uint32_t bits = S.mDS[w];
+                while (bits) {
+                    S.dslist[off++] = (uint16_t)((w << 5) + pp_ctz(bits));
+                    bits &= bits - 1;
+                }
+            }
+            if (tid == 0) {
+                S.n_ds = (int32_t)total;
+                const int64_t di = (int64_t)S.d_first + (int64_t)total;
+                S.region_doc_end = di <= P.n_docs ? P.doc_offs[di] : n;  // end of the document open at the region's end
+            }
+        }
+        blk.sync();
+        const int n_ds = S.n_ds;
+        // next document start strictly after region index r, or PA_R
+        auto next_ds = [&](int r) -> int {
+            const int w = r >> 5;
+            const uint32_t hi = (r & 31) == 31 ? 0u : (S.mDS[w] & (~0u << ((r & 31) + 1)));
+            if (hi) return (w << 5) + pp_ctz(hi);
+            const int k = (int)S.dsn[w] + pp_popc(S.mDS[w]);
+            return k < n_ds ? (int)S.dslist[k] : PA_R;
+        };
+        // (1) synchronisation points: document starts and every space whose next character is a non-whitespace
+        // character of the same document
         for (int w = tid; w < PA_NW; w += nt) {
             const uint32_t ds = S.mDS[w];
             uint32_t sy = ds, sp = S.mSP[w];
@@ -397,7 +432,9 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                 const int r = (w << 5) + pp_ctz(sp);
                 sp &= sp - 1;
                 if (r > PA_R - 6) continue;  // next character may not be loaded completely: no sync, scanned through
-                const int dend = pp_mask_next(S.mDS, r + 1, PA_R);
+                // only a document start within the next character can matter here
+                const uint64_t near = (((uint64_t)S.mDS[w] | ((uint64_t)S.mDS[w + 1] << 32)) >> (r & 31)) >> 1;
+                const int dend = (near & 0x1Fu) ? r + 1 + pp_ctz((uint32_t)(near & 0x1Fu)) : r + 8;
                 if (dpt_is_sync_space(U, S.text, r, dend)) sy |= 1u << (r & 31);
             }
             S.mSY[w] = sy;
@@ -413,16 +450,11 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                 if (m) sf = (w << 5) + 31 - pp_clz(m);
             }
             S.s_first = sf;
-            // end of the document that is open at the end of the region
-            int nds = 0;
-            for (int w = 0; w < PA_NW; ++w) nds += pp_popc(S.mDS[w]);
-            const int64_t di = (int64_t)S.d_first + nds;
-            S.region_doc_end = di <= P.n_docs ? P.doc_offs[di] : n;
             S.first_sync_global = -1;
             if (sf < 0) {  // no sync point in the look-behind: walk back through the text (rare: a piece-free run > 32 B)
                 const int64_t d = pp_upper_bound(P.doc_offs, P.n_docs + 1, t0) - 1;
                 const int64_t dstart = P.doc_offs[d < 0 ? 0 : d];
-                const int nd = pp_mask_next(S.mDS, own_lo + 1, PA_R);
+                const int nd = next_ds(own_lo);
                 const int64_t dend = nd < PA_R ? g0 + nd : (int64_t)S.region_doc_end;
                 int64_t q = g0 - 1;
                 while (q > dstart && !dpt_is_sync_space(U, P.text, q, dend)) --q;
@@ -458,11 +490,8 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                 int64_t p = idx < 0 ? (int64_t)S.first_sync_global : g0 + S.wlist[idx];
                 const int64_t limit = idx + 1 < ns ? g0 + S.wlist[idx + 1] : g0 + PA_R;
                 int64_t dend;
-                if (idx < 0) {
-                    const int nd = pp_mask_next(S.mDS, own_lo + 1, PA_R);
-                    dend = nd < PA_R ? g0 + nd : (int64_t)S.region_doc_end;
-                } else {
-                    const int nd = pp_mask_next(S.mDS, S.wlist[idx] + 1, PA_R);
+                {
+                    const int nd = next_ds(idx < 0 ? own_lo : (int)S.wlist[idx]);
                     dend = nd < PA_R ? g0 + nd : (int64_t)S.region_doc_end;
                 }
                 const int64_t stop = limit < dend ? limit : dend;
