@@ -235,10 +235,19 @@ DPT_HD uint32_t dpt_da_load(const uint32_t* da, uint32_t slot) {
 #endif
 }
 
-DPT_HD void dpt_forward_flat32(const DptVocabView& V, const uint8_t* s, int32_t n, uint32_t* best, uint32_t* Ap,
-                               uint32_t* Bp) {
-    // Ap/Bp: packed back-pointers  slot | distance << 22  (distance <= DPT_FLAT32_MAX, slots < 2^22): one 4-byte store
-    // per back-pointer and relaxation instead of a distance and a slot each
+// The forward pass as a resumable state machine: dpt_flat32_init sets up the per-position arrays, every call of
+// dpt_flat32_step advances the (start j, end i) walk by at most one trie step and returns false once the pass is
+// complete.  Kernel B keeps one of these per lane, steps all lanes of a warp in lock step and hands a finished lane
+// its next word while the others keep walking (dpt_pipe.h: pb_thread), so a lane never idles for long.
+struct DptFlat32 {
+    int32_t j, i;          // current start position, current end position
+    uint32_t entry, cl, kj;
+    bool walking;
+};
+// Ap/Bp: packed back-pointers  slot | distance << 22  (distance <= DPT_FLAT32_MAX, slots < 2^22): one 4-byte store
+// per back-pointer and relaxation instead of a distance and a slot each
+DPT_HD void dpt_flat32_init(const DptVocabView& V, const uint8_t* s, int32_t n, uint32_t* best, uint32_t* Ap, uint32_t* Bp,
+                            DptFlat32& st) {
     const bool cp_mode = V.unit_mode != 0;
     uint32_t u = 0;
     for (int32_t p = 0; p <= n; ++p) {
@@ -249,44 +258,57 @@ DPT_HD void dpt_forward_flat32(const DptVocabView& V, const uint8_t* s, int32_t 
         Bp[p] = 0;
     }
     if (n > 0) best[0] = 0xFFFFu;  // origin: len 0, reachable, longest 0
-    const uint32_t* __restrict__ da = V.da;
-    int32_t j = -1, i = 0;
-    uint32_t entry = 0, cl = 0, kj = 0;
-    bool walking = false;
-    for (;;) {
-        if (!walking) {
-            if (++j >= n) break;
-            kj = best[j];
-            entry = DPT_DA_ROOT_ENTRY;
-            i = j;
-            cl = 0;
-            walking = kj != DPT_K32_NONE;
-            if (!walking) continue;
-        }
-        const uint32_t base = entry >> DPT_DA_BASE_SHIFT;
-        const uint32_t c = i < n ? (uint32_t)s[i] : 0x100u;
-        const uint32_t slot = base + (c & 0xFFu);
-        uint32_t e = 0;
-        if (base != 0 && c < 0x100u) e = dpt_da_load(da, slot);
-        if ((e & DPT_DA_MATCH_MASK) != (DPT_DA_OCCUPIED | c)) {
-            walking = false;
-            continue;
-        }
-        entry = e;
-        ++i;
-        cl += (!cp_mode || dpt_is_cp_start(c)) ? 1u : 0u;
-        if (e & DPT_DA_TERMINAL) {
-            const uint32_t bi = best[i];
-            if (bi != DPT_K32_NONE) {
-                const uint32_t k = dpt_k32_extend(kj, cl);
-                const uint32_t packed = slot | ((uint32_t)(i - j) << 22);
-                if ((k >> 16) <= (bi >> 16)) Ap[i] = packed;
-                if (k <= bi) {
-                    best[i] = k;
-                    Bp[i] = packed;
-                }
+    st.j = -1;
+    st.i = 0;
+    st.entry = 0;
+    st.cl = 0;
+    st.kj = 0;
+    st.walking = false;
+}
+DPT_HD bool dpt_flat32_step(const DptVocabView& V, const uint8_t* s, int32_t n, uint32_t* best, uint32_t* Ap, uint32_t* Bp,
+                            DptFlat32& st) {
+    const bool cp_mode = V.unit_mode != 0;
+    if (!st.walking) {  // next start position (same iteration as its first trie step)
+        if (++st.j >= n) return false;
+        st.kj = best[st.j];
+        st.entry = DPT_DA_ROOT_ENTRY;
+        st.i = st.j;
+        st.cl = 0;
+        st.walking = st.kj != DPT_K32_NONE;  // not a unit boundary: nothing starts here
+        if (!st.walking) return true;
+    }
+    const uint32_t base = st.entry >> DPT_DA_BASE_SHIFT;
+    const uint32_t c = (uint32_t)s[st.i];  // i < n whenever a walk is open
+    const uint32_t slot = base + c;
+    uint32_t e = 0;
+    if (base != 0) e = dpt_da_load(V.da, slot);
+    if ((e & DPT_DA_MATCH_MASK) != (DPT_DA_OCCUPIED | c)) {
+        st.walking = false;
+        return true;
+    }
+    st.entry = e;
+    const int32_t i = ++st.i;
+    st.cl += (!cp_mode || dpt_is_cp_start(c)) ? 1u : 0u;
+    if (e & DPT_DA_TERMINAL) {
+        const uint32_t bi = best[i];
+        if (bi != DPT_K32_NONE) {
+            const uint32_t k = dpt_k32_extend(st.kj, st.cl);
+            const uint32_t packed = slot | ((uint32_t)(i - st.j) << 22);
+            if ((k >> 16) <= (bi >> 16)) Ap[i] = packed;
+            if (k <= bi) {
+                best[i] = k;
+                Bp[i] = packed;
             }
         }
+    }
+    if (i >= n) st.walking = false;  // end of the word: the walk from j is over
+    return true;
+}
+DPT_HD void dpt_forward_flat32(const DptVocabView& V, const uint8_t* s, int32_t n, uint32_t* best, uint32_t* Ap,
+                               uint32_t* Bp) {
+    DptFlat32 st;
+    dpt_flat32_init(V, s, n, best, Ap, Bp, st);
+    while (dpt_flat32_step(V, s, n, best, Ap, Bp, st)) {
     }
 }
 

@@ -49,6 +49,14 @@ constexpr int PB_THREADS = 128;
 constexpr int PB_CLASSES = 4;                 // length classes of the DP work queues (8 measured no better: lane
                                               // imbalance comes from walk depths, not from word length)
 constexpr int PB_LOCAL = 72;                  // normalised bytes solved with per-thread local state in kernel B
+// kernel B: finished lanes take new words once fewer lanes than this are still walking.  1 = a warp finishes its 32
+// words before it takes the next 32.  Measured on the B200 (100 MB S2ORC-shaped corpus): 1 -> 0.350 ms, 12 -> 0.404,
+// 20 -> 0.438, 28 -> 0.526: every refill runs the long normalise / initialise / backward code for a few lanes while
+// the others wait, which costs more than the idle lanes of the hot loop
+#ifndef DPT_PB_REFILL
+#define DPT_PB_REFILL 1
+#endif
+constexpr int PB_REFILL = DPT_PB_REFILL;
 constexpr int PC_THREADS = 256;
 constexpr int PC_PER = 8;                     // words per thread in kernel C
 constexpr int PA_WIN = 1024;                  // words of a tile handled per pass (a 4 KB tile holds ~520; more -> more passes)
@@ -160,8 +168,10 @@ struct ASmemT {
     uint16_t dslist[kSpm ? 2 : PA_R + 32];  // byte-level rules: region indices of the document starts, in order
     uint32_t pend[PA_WIN];    // table slots claimed in the current window
     uint32_t stage[PA_WIN];   // refs of the current window, written out coalesced once the word offset is known
+    alignas(16) uint32_t lut[17][4];  // lut[len]: byte masks of the first min(len,16) bytes of a 16-byte window
     uint32_t scan[40];
     int32_t tile, d_first, n_entries;
+    uint32_t any_cx;          // some mCX bit is set in this tile (rare: the per-word range test is skipped otherwise)
     uint32_t n_pend, n_pend_c[PB_CLASSES], cur_c[PB_CLASSES], base_c[PB_CLASSES];
     int32_t n_sync, s_first, n_ds;
     long long region_doc_end, first_sync_global;
@@ -276,6 +286,23 @@ DPT_HD void pp_load16(const uint8_t* base4, int64_t off, int len, uint32_t v[4])
         v[k] &= (uint32_t)((1ull << (8 * rem)) - 1ull);
     }
 }
+// 16 bytes at byte offset `off` of a 4-byte-aligned buffer, unmasked (the caller masks with ASmemT::lut[len])
+DPT_HD void pp_load16_raw(const uint8_t* base4, int64_t off, uint32_t v[4]) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(base4 + (off & ~(int64_t)3));
+    const uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3], a4 = w[4];
+    const uint32_t sh = (uint32_t)(off & 3) * 8u;
+#if defined(__CUDA_ARCH__)
+    v[0] = __funnelshift_r(a0, a1, sh);
+    v[1] = __funnelshift_r(a1, a2, sh);
+    v[2] = __funnelshift_r(a2, a3, sh);
+    v[3] = __funnelshift_r(a3, a4, sh);
+#else
+    v[0] = sh ? (a0 >> sh) | (a1 << (32u - sh)) : a0;
+    v[1] = sh ? (a1 >> sh) | (a2 << (32u - sh)) : a1;
+    v[2] = sh ? (a2 >> sh) | (a3 << (32u - sh)) : a2;
+    v[3] = sh ? (a3 >> sh) | (a4 << (32u - sh)) : a3;
+#endif
+}
 DPT_HD uint32_t pp_hash_step(uint32_t h, uint32_t v) {
     h = (h ^ v) * 0x9E3779B1u;
     return h ^ (h >> 15);
@@ -331,22 +358,43 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
     const int tvalid = (int)((n - t0) < PA_T ? (n - t0) : PA_T);
     const int own_lo = PA_HALO + (int)(P.byte_begin > t0 ? P.byte_begin - t0 : 0), own_hi = PA_HALO + tvalid;
     constexpr bool spm = kSpm;
+    // bits of mask word w that belong to this tile's own bytes [own_lo, own_hi) / to [0, own_hi): for a full tile
+    // (all but the first and last of a range) these are whole words
+    const bool full_tile = own_lo == PA_HALO && own_hi == PA_HALO + PA_T;
+    auto own_mask = [&](int w) -> uint32_t {
+        if (full_tile) return ((uint32_t)(w - PA_HALO / 32) < (uint32_t)(PA_T / 32)) ? ~0u : 0u;
+        return pp_range_mask(w, own_lo, own_hi);
+    };
+    auto upto_mask = [&](int w) -> uint32_t {
+        if (full_tile) return w < (PA_HALO + PA_T) / 32 ? ~0u : 0u;
+        return pp_range_mask(w, 0, own_hi);
+    };
 
     // ---- load: coalesced 16-byte loads of the region ------------------------------------------------------
     {
         const bool aligned = (((uintptr_t)P.text) & 15u) == 0;
-        for (int i = tid; i < PA_R / 16; i += nt) {
-            const int64_t g = g0 + 16 * (int64_t)i;
-            if (aligned && g >= 0 && g + 16 <= n) {
-                *reinterpret_cast<uint4*>(&S.text[16 * i]) = *reinterpret_cast<const uint4*>(P.text + g);
-            } else {
-                for (int k = 0; k < 16; ++k) {
-                    const int64_t q = g + k;
-                    S.text[16 * i + k] = (q >= 0 && q < n) ? P.text[q] : (uint8_t)0;
+        if (aligned && g0 >= 0 && g0 + PA_R <= n) {  // the whole region is there (every tile but the first and the last few)
+            const uint4* src = reinterpret_cast<const uint4*>(P.text + g0);
+            for (int i = tid; i < PA_R / 16; i += nt) *reinterpret_cast<uint4*>(&S.text[16 * i]) = src[i];
+        } else {
+            for (int i = tid; i < PA_R / 16; i += nt) {
+                const int64_t g = g0 + 16 * (int64_t)i;
+                if (aligned && g >= 0 && g + 16 <= n) {
+                    *reinterpret_cast<uint4*>(&S.text[16 * i]) = *reinterpret_cast<const uint4*>(P.text + g);
+                } else {
+                    for (int k = 0; k < 16; ++k) {
+                        const int64_t q = g + k;
+                        S.text[16 * i + k] = (q >= 0 && q < n) ? P.text[q] : (uint8_t)0;
+                    }
                 }
             }
         }
         for (int i = tid; i < 64; i += nt) S.text[PA_R + i] = 0;
+        for (int i = tid; i < 17 * 4; i += nt) {
+            int rem = (i >> 2) - 4 * (i & 3);
+            rem = rem < 0 ? 0 : rem > 4 ? 4 : rem;
+            S.lut[i >> 2][i & 3] = rem >= 4 ? ~0u : ((1u << (8 * rem)) - 1u);
+        }
         for (int w = tid; w < PA_NW + 2; w += nt) {
             S.mDS[w] = 0;
             S.mSY[w] = 0;
@@ -356,6 +404,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
         if (tid == 0) {
             S.d_first = (int32_t)pp_lower_bound(P.doc_offs, P.n_docs + 1, g0 < 0 ? 0 : g0);
             S.n_pend = 0;
+            S.any_cx = 0;
             for (int c = 0; c < PB_CLASSES; ++c) S.n_pend_c[c] = S.cur_c[c] = 0;
         }
     }
@@ -372,8 +421,15 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
             const uint32_t cont = pp_eq4(x.x & 0xC0C0C0C0u, 0x80808080u) | (pp_eq4(x.y & 0xC0C0C0C0u, 0x80808080u) << 4) |
                                   (pp_eq4(x.z & 0xC0C0C0C0u, 0x80808080u) << 8) | (pp_eq4(x.w & 0xC0C0C0C0u, 0x80808080u) << 12);
             cs = ~cont & 0xFFFFu;
-            for (int k = 0; k < 16; ++k)
-                m3 |= (uint32_t)(t[k] == DPT_MARK0 && t[k + 1] == DPT_MARK1 && t[k + 2] == DPT_MARK2) << k;
+            if (spm) {  // raw U+2581 candidates: only where the lead byte E2 occurs
+                uint32_t e2 = pp_eq4(x.x, 0x01010101u * DPT_MARK0) | (pp_eq4(x.y, 0x01010101u * DPT_MARK0) << 4) |
+                              (pp_eq4(x.z, 0x01010101u * DPT_MARK0) << 8) | (pp_eq4(x.w, 0x01010101u * DPT_MARK0) << 12);
+                while (e2) {
+                    const int k = pp_ctz(e2);
+                    e2 &= e2 - 1;
+                    m3 |= (uint32_t)(t[k + 1] == DPT_MARK1 && t[k + 2] == DPT_MARK2) << k;
+                }
+            }
         }
         reinterpret_cast<uint16_t*>(S.mCS)[hw] = (uint16_t)cs;
         reinterpret_cast<uint16_t*>(S.mSP)[hw] = (uint16_t)sp;
@@ -531,8 +587,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
             const uint32_t ds = S.mDS[w];
             const uint32_t ws = S.mWS[w] | ds;
             S.mWS[w] = ws;
-            S.cnt[w] = (uint32_t)pp_popc(ws & pp_range_mask(w, own_lo, own_hi)) |
-                       ((uint32_t)pp_popc(ds & pp_range_mask(w, 0, own_hi)) << 16);
+            S.cnt[w] = (uint32_t)pp_popc(ws & own_mask(w)) | ((uint32_t)pp_popc(ds & upto_mask(w)) << 16);
         }
     } else
     {
@@ -562,10 +617,11 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
             S.mCF[w] = cs | ds;
             S.mWS[w] = ws;
             S.mCX[w] = cx;
-            const uint32_t rm = pp_range_mask(w, own_lo, own_hi);
+            if (cx) S.any_cx = 1u;
+            const uint32_t rm = own_mask(w);
             // words (and '<s>' words) that start in this tile | document starts up to here << 16
             S.cnt[w] = (uint32_t)(pp_popc(ws & rm) + (spm ? pp_popc(ds & rm) : 0)) |
-                       ((uint32_t)pp_popc(ds & pp_range_mask(w, 0, own_hi)) << 16);
+                       ((uint32_t)pp_popc(ds & upto_mask(w)) << 16);
             amb &= rm;
             while (amb && P.doc_flags) {
                 const int r = (w << 5) + pp_ctz(amb);
@@ -607,12 +663,12 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
         {
             uint32_t off = my_off, dord = my_dord;
             for (int w = w0; w < w1; ++w) {
-                uint32_t bits = S.mWS[w] & pp_range_mask(w, own_lo, own_hi);
-                const uint32_t dsw = S.mDS[w] & pp_range_mask(w, 0, own_hi);
+                uint32_t bits = S.mWS[w] & own_mask(w);
+                const uint32_t dsw = S.mDS[w] & upto_mask(w);
                 while (bits) {
                     const int r = (w << 5) + pp_ctz(bits);
                     bits &= bits - 1;
-                    if (spm && pp_bit(S.mDS, r)) {
+                    if (spm && ((dsw >> (r & 31)) & 1u)) {
                         if ((int)off >= lo && (int)off < hi) {
                             // index of this document = first document of the region + document starts before r
                             const uint32_t before = dord + (uint32_t)pp_popc(dsw & ((1u << (r & 31)) - 1u));
@@ -638,20 +694,24 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                 continue;  // staged with its document index by the list build
             } else {
                 const bool ds = pp_bit(S.mDS, ws);
-                const int we = pp_mask_next(S.mWS, ws + 1, PA_R);
+                // the word ends where the next entry of the list starts (a '<s>' entry sits on its document's first
+                // word); the last entry of a window looks the end up in the word-start mask
+                const int we = k + 1 < nwin ? (int)(S.wlist[k + 1] & 0x7FFFu) : pp_mask_next(S.mWS, ws + 1, PA_R);
                 const int ml = !spm ? 0 : ds ? 0 : (S.text[ws] == 0x20u ? 1 : 3);
                 const int b = ws + ml, len = we - b;
                 const bool open = we >= PA_R;
-                bool odd = open || len > PA_MAXLEN || len < 0 || pp_any_in_range(S.mCX, ws, we);
+                bool odd = open || len > PA_MAXLEN || len < 0 || (S.any_cx && pp_any_in_range(S.mCX, ws, we));
                 ref = 0;
                 if (!odd) {
-                    // hash the body: the first 16 bytes straight-line (four zero-padded words, no loop: 19 of 20 words
-                    // end here with every lane active), longer bodies 4 more bytes per step
+                    // hash of the length and the first 16 bytes of the body (four zero-padded words, straight-line: every
+                    // lane active).  Longer bodies hash like their 16-byte prefix: the table verifies the bytes anyway, and
+                    // bodies of one length that share 16 bytes are too few to lengthen the probe sequences.
                     uint32_t wv[4];
-                    pp_load16(S.text, b, len, wv);
+                    pp_load16_raw(S.text, b, wv);
+                    const uint4 lm = *reinterpret_cast<const uint4*>(S.lut[len < 16 ? len : 16]);
+                    wv[0] &= lm.x; wv[1] &= lm.y; wv[2] &= lm.z; wv[3] &= lm.w;
                     uint32_t h = 0x811C9DC5u ^ (uint32_t)len;
                     h = pp_hash_step(pp_hash_step(pp_hash_step(pp_hash_step(h, wv[0]), wv[1]), wv[2]), wv[3]);
-                    for (int q = 16; q < len; q += 4) h = pp_hash_step(h, pp_load4(S.text, b + q) & pp_tail_mask(len - q));
                     h *= 0x2C1B3C6Du;
                     h ^= h >> 13;
                     const int64_t g_b = g0 + b;
@@ -679,8 +739,9 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                                 const uint8_t* base4 = P.text - ((uintptr_t)P.text & 3u);
                                 const int64_t ro = rp + (int64_t)((uintptr_t)P.text & 3u);
                                 uint32_t rv[4];
-                                pp_load16(base4, ro, len, rv);
-                                same = ((rv[0] ^ wv[0]) | (rv[1] ^ wv[1]) | (rv[2] ^ wv[2]) | (rv[3] ^ wv[3])) == 0;
+                                pp_load16_raw(base4, ro, rv);
+                                same = (((rv[0] & lm.x) ^ wv[0]) | ((rv[1] & lm.y) ^ wv[1]) | ((rv[2] & lm.z) ^ wv[2]) |
+                                        ((rv[3] & lm.w) ^ wv[3])) == 0;
                                 for (int q = 16; q < len && same; q += 4)
                                     same = ((pp_load4(base4, ro + q) ^ pp_load4(S.text, b + q)) & pp_tail_mask(len - q)) == 0;
                             } else {
@@ -756,8 +817,15 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
 
 template <class Blk, bool kSpm>
 DPT_PIPE_FN void pa_kernel(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S) {
-    // tiles are handed out in corpus order by an atomic ticket, so the look-back only ever waits for tiles held
-    // by CTAs that are already running
+    // The look-back of a tile waits for its predecessors, so a tile must only start once every earlier tile has.
+    // On the device the hardware dispatches CTAs in blockIdx order (the assumption CUB's decoupled look-back scan is
+    // built on), so tile = blockIdx.x and no CTA begins with a global atomic round trip; a persistent block (the host
+    // emulation) takes tiles in corpus order from an atomic ticket.
+    if (!blk.persistent()) {
+        const int tile = blk.block_index();
+        if (tile < P.n_tiles) pa_run_tile<Blk, kSpm>(blk, P, S, tile);
+        return;
+    }
     for (;;) {
         if (blk.tid() == 0) S.tile = (int32_t)blk.atomic_add_ret(&P.ctl->ticket_a, 1u);
         blk.sync();
@@ -867,9 +935,36 @@ DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint64_t i, const uint32_t* npc,
     return it;
 }
 
-// one thread per distinct word, DP state in local memory.  The loop body is written so that the lanes of a warp
-// go through the same sequence of single loops (normalise, forward state machine, backward chase) and reconverge
-// between them.
+// One thread per distinct word, DP state in local memory; the forward pass is the resumable state machine of
+// dpt_dp_core.h.  The lanes of a warp step their words in lock step; words differ a lot in their step counts, so a
+// warp that simply waited for its longest word ran the hot loop with 11 of 32 lanes (ncu, v11).  Here a lane that has
+// finished its word leaves the hot loop only when fewer than PB_REFILL lanes are still walking (or every 4 steps when
+// nothing is left to take): the finished lanes then write their records and take new words from the work list
+// (normalise, initialise) while the unfinished lanes keep their walk state in registers, and all re-enter the loop.
+template <class Blk>
+DPT_PIPE_FN void pb_finish_word(Blk& blk, const PipeParams& P, const uint8_t* norm, int32_t n, const uint32_t* best,
+                                const uint32_t* Ap, const uint32_t* Bp, ResRec* out) {
+    ResRec rec;
+    for (int k = 0; k < RES_INLINE; ++k) rec.ids[k] = 0;
+    const uint32_t kn = best[n];
+    const uint32_t word_len = dpt_k32_len(kn);
+    const bool reach = dpt_k32_reach(kn);
+    rec.meta = (word_len & 0xFFFFFFu) | (reach ? 0u : RES_UNTOK);
+    if (reach) {
+        if (word_len <= (uint32_t)RES_INLINE) {
+            dpt_backward_chase(P.V, norm, n, word_len, dpt_k32_longest(kn), Ap, Bp, rec.ids, RES_INLINE);
+        } else {
+            const unsigned long long off = blk.atomic_add_u64_ret(&P.persist->pool_used, (unsigned long long)word_len);
+            rec.meta |= RES_POOLED;
+            rec.ids[0] = (int32_t)(uint32_t)(off & 0xFFFFFFFFull);
+            rec.ids[1] = (int32_t)(uint32_t)(off >> 32);
+            if ((int64_t)(off + word_len) <= P.pool_cap)
+                dpt_backward_chase(P.V, norm, n, word_len, dpt_k32_longest(kn), Ap, Bp, P.pool + off, (int64_t)word_len);
+        }
+    }
+    *out = rec;
+}
+
 template <class Blk>
 DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
     uint32_t npc[PB_CLASSES];
@@ -880,53 +975,61 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
     }
     const uint32_t n_odd = P.ctl->n_odd < (uint32_t)P.odd_cap ? P.ctl->n_odd : (uint32_t)P.odd_cap;
     total += n_odd;
+    uint8_t norm[PB_LOCAL + 8];
+    uint32_t best[PB_LOCAL + 1], Ap[PB_LOCAL + 1], Bp[PB_LOCAL + 1];
+    DptFlat32 st;
+    st.j = st.i = 0;
+    st.entry = st.cl = st.kj = 0;
+    st.walking = false;
+    ResRec* out = nullptr;
+    int32_t n = 0;
+    bool have = false;  // this lane holds a word whose forward pass is not complete
+    bool more = true;   // warp-uniform: the work list may still hold items
     for (;;) {
-        // every warp claims the next 32 items (dynamic: a warp stuck on long words does not hold the others back)
-        const uint64_t i = blk.warp_take(&P.ctl->b_cursor);
-        if (!blk.warp_any(i < total)) break;
-        const bool valid = i < total;
-        PbItem it;
-        it.out = nullptr;
-        uint8_t norm[PB_LOCAL + 8];
-        int32_t nlen = 0;
-        if (valid) {
-            it = pb_item(P, i, npc, n_odd);
-            nlen = pb_normalise(P, it.pos, it.end, it.marker, norm, PB_LOCAL);
-            if (nlen < 0) {
-                const uint32_t q = blk.atomic_add_ret(&P.ctl->n_long, 1u);
-                P.longq[q] = (uint32_t)i;
+        if (more) {
+            // lanes without a word take the next items of the list (one atomic per warp)
+            const bool ask = !have;
+            const uint64_t idx = blk.warp_take_n(&P.ctl->b_cursor, ask);
+            const bool got = ask && idx < total;
+            more = !blk.warp_any(ask && !got);
+            if (got) {
+                const PbItem it = pb_item(P, idx, npc, n_odd);
+                const int32_t nlen = pb_normalise(P, it.pos, it.end, it.marker, norm, PB_LOCAL);
+                if (nlen < 0) {  // too long for the local state: the long-word kernel solves it
+                    const uint32_t q = blk.atomic_add_ret(&P.ctl->n_long, 1u);
+                    P.longq[q] = (uint32_t)idx;
+                } else if (nlen == 0) {  // cannot happen (documents are non-empty); keep the record defined
+                    ResRec rec;
+                    for (int k = 0; k < RES_INLINE; ++k) rec.ids[k] = 0;
+                    rec.meta = RES_UNTOK;
+                    *it.out = rec;
+                } else {
+                    out = it.out;
+                    n = nlen;
+                    dpt_flat32_init(P.V, norm, n, best, Ap, Bp, st);
+                    have = true;
+                }
             }
+            blk.reconverge();
         }
-        blk.reconverge();
-        const int32_t n = nlen > 0 ? nlen : 0;
-        uint32_t best[PB_LOCAL + 1], Ap[PB_LOCAL + 1], Bp[PB_LOCAL + 1];
-        dpt_forward_flat32(P.V, norm, n, best, Ap, Bp);
-        blk.reconverge();
-        if (!valid || nlen < 0) continue;
-        ResRec rec;
-        for (int k = 0; k < RES_INLINE; ++k) rec.ids[k] = 0;
-        if (nlen == 0) {  // cannot happen (documents are non-empty); keep the record defined
-            rec.meta = RES_UNTOK;
-            *it.out = rec;
+        if (!blk.warp_any(have)) {
+            if (!more) break;
             continue;
         }
-        const uint32_t kn = best[n];
-        const uint32_t word_len = dpt_k32_len(kn);
-        const bool reach = dpt_k32_reach(kn);
-        rec.meta = (word_len & 0xFFFFFFu) | (reach ? 0u : RES_UNTOK);
-        if (reach) {
-            if (word_len <= (uint32_t)RES_INLINE) {
-                dpt_backward_chase(P.V, norm, n, word_len, dpt_k32_longest(kn), Ap, Bp, rec.ids, RES_INLINE);
-            } else {
-                const unsigned long long off = blk.atomic_add_u64_ret(&P.persist->pool_used, (unsigned long long)word_len);
-                rec.meta |= RES_POOLED;
-                rec.ids[0] = (int32_t)(uint32_t)(off & 0xFFFFFFFFull);
-                rec.ids[1] = (int32_t)(uint32_t)(off >> 32);
-                if ((int64_t)(off + word_len) <= P.pool_cap)
-                    dpt_backward_chase(P.V, norm, n, word_len, dpt_k32_longest(kn), Ap, Bp, P.pool + off, (int64_t)word_len);
-            }
+        // the hot loop: one trie step per lane and iteration
+        const int thresh = more ? PB_REFILL : 1;
+        bool running = have;
+        do {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (running) running = dpt_flat32_step(P.V, norm, n, best, Ap, Bp, st);
+        } while (blk.warp_count(running) >= thresh);
+        blk.reconverge();
+        if (have && !running) {
+            pb_finish_word(blk, P, norm, n, best, Ap, Bp, out);
+            have = false;
         }
-        *it.out = rec;
+        blk.reconverge();
     }
 }
 
@@ -997,6 +1100,13 @@ DPT_PIPE_FN void pc_st_stream(int32_t* p, int32_t v) {
 #endif
 }
 
+DPT_PIPE_FN uint4 pc_ld_head(const ResRec* r) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(reinterpret_cast<const uint4*>(r));
+#else
+    return *reinterpret_cast<const uint4*>(r);
+#endif
+}
 DPT_PIPE_FN const ResRec* pc_record_ptr(const PipeParams& P, uint32_t ref) {
     if ((ref & REF_KIND) == REF_ODD) {
         const uint32_t j = ref & REF_INDEX;
@@ -1021,6 +1131,7 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
     const int64_t n_words = (int64_t)P.ctl->n_words < P.word_cap ? (int64_t)P.ctl->n_words : P.word_cap;
     const int64_t w0 = (int64_t)tile * PC_TILE + (int64_t)tid * PC_PER;
     uint32_t ref[PC_PER], meta[PC_PER];
+    uint4 head[PC_PER];  // first half of every word's result record: meta + ids[0..2] (pooled: meta + pool offset)
     uint32_t mine = 0, untok = 0;
     if (w0 + PC_PER <= n_words) {  // two 16-byte loads of 8 refs
         const uint4 r0 = pc_ld_stream(reinterpret_cast<const uint4*>(P.refs + w0));
@@ -1031,11 +1142,30 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
 #pragma unroll
         for (int k = 0; k < PC_PER; ++k) ref[k] = w0 + k < n_words ? P.refs[w0 + k] : REF_BOS;
     }
+    // one 16-byte load per word (eight independent ones in flight per thread): words of up to three tokens - nine of ten -
+    // need nothing else from their record, so the id copy below does not wait for memory a second time
 #pragma unroll
     for (int k = 0; k < PC_PER; ++k) {
-        meta[k] = RES_UNTOK;
+        uint4 h;
+        h.x = RES_UNTOK;
+        h.y = h.z = h.w = 0u;
         if (w0 + k < n_words) {
-            meta[k] = pc_meta(P, ref[k]);
+            if ((ref[k] & REF_KIND) == REF_BOS) {
+                h.x = (uint32_t)P.V.bos_len | (P.V.bos_ntok ? 0u : RES_UNTOK);
+                h.y = (uint32_t)P.V.bos_ids[0];
+                h.z = (uint32_t)P.V.bos_ids[1];
+                h.w = (uint32_t)P.V.bos_ids[2];
+            } else {
+                const ResRec* r = pc_record_ptr(P, ref[k]);
+                if (r) h = pc_ld_head(r);
+            }
+        }
+        head[k] = h;
+    }
+#pragma unroll
+    for (int k = 0; k < PC_PER; ++k) {
+        meta[k] = head[k].x;
+        if (w0 + k < n_words) {
             if (meta[k] & RES_UNTOK) ++untok; else mine += meta[k] & 0xFFFFFFu;
         }
     }
@@ -1079,31 +1209,23 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
 #pragma unroll
         for (int k = 0; k < PC_PER; ++k) {
             if (w0 + k >= n_words) break;
-            const uint32_t kind = ref[k] & REF_KIND;
             if (meta[k] & RES_UNTOK) continue;
             const uint32_t nk = meta[k] & 0xFFFFFFu;
             if (nk == 0) continue;
-            if (kind == REF_BOS) {
-                for (uint32_t q = 0; q < nk && q < 3; ++q)
-                    if (gt + q < cap) dst[gt + q] = P.V.bos_ids[q];
+            if (meta[k] & RES_POOLED) {
+                const int64_t po = (int64_t)head[k].y | ((int64_t)head[k].z << 32);
+                for (uint32_t q = 0; q < nk; ++q)
+                    if (gt + q < cap && po + q < P.pool_cap) dst[gt + q] = P.pool[po + q];
             } else {
-                const ResRec* r = pc_record_ptr(P, ref[k]);
-                if (meta[k] & RES_POOLED) {
-                    const int64_t po = (int64_t)(uint32_t)r->ids[0] | ((int64_t)(uint32_t)r->ids[1] << 32);
-                    for (uint32_t q = 0; q < nk; ++q)
-                        if (gt + q < cap && po + q < P.pool_cap) dst[gt + q] = P.pool[po + q];
-                } else {
-                    const uint4 a = *reinterpret_cast<const uint4*>(r);             // meta, ids[0..2]
-                    if (gt < cap) dst[gt] = (int32_t)a.y;
-                    if (nk > 1 && gt + 1 < cap) dst[gt + 1] = (int32_t)a.z;
-                    if (nk > 2 && gt + 2 < cap) dst[gt + 2] = (int32_t)a.w;
-                    if (nk > 3) {
-                        const uint4 c = *(reinterpret_cast<const uint4*>(r) + 1);   // ids[3..6]
-                        if (gt + 3 < cap) dst[gt + 3] = (int32_t)c.x;
-                        if (nk > 4 && gt + 4 < cap) dst[gt + 4] = (int32_t)c.y;
-                        if (nk > 5 && gt + 5 < cap) dst[gt + 5] = (int32_t)c.z;
-                        if (nk > 6 && gt + 6 < cap) dst[gt + 6] = (int32_t)c.w;
-                    }
+                if (gt < cap) dst[gt] = (int32_t)head[k].y;
+                if (nk > 1 && gt + 1 < cap) dst[gt + 1] = (int32_t)head[k].z;
+                if (nk > 2 && gt + 2 < cap) dst[gt + 2] = (int32_t)head[k].w;
+                if (nk > 3 && (ref[k] & REF_KIND) != REF_BOS) {  // '<s>' contributes at most three ids
+                    const uint4 c = *(reinterpret_cast<const uint4*>(pc_record_ptr(P, ref[k])) + 1);   // ids[3..6]
+                    if (gt + 3 < cap) dst[gt + 3] = (int32_t)c.x;
+                    if (nk > 4 && gt + 4 < cap) dst[gt + 4] = (int32_t)c.y;
+                    if (nk > 5 && gt + 5 < cap) dst[gt + 5] = (int32_t)c.z;
+                    if (nk > 6 && gt + 6 < cap) dst[gt + 6] = (int32_t)c.w;
                 }
             }
             gt += nk;
@@ -1140,6 +1262,12 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
 
 template <class Blk>
 DPT_PIPE_FN void pc_kernel(Blk& blk, const PipeParams& P, CSmem& S) {
+    if (!blk.persistent()) {  // tile = blockIdx.x, see pa_kernel
+        const int tile = blk.block_index();
+        const int64_t n_words = (int64_t)P.ctl->n_words < P.word_cap ? (int64_t)P.ctl->n_words : P.word_cap;
+        if (tile < P.n_ctiles && (int64_t)tile * PC_TILE < n_words) pc_run_tile(blk, P, S, tile);
+        return;
+    }
     for (;;) {
         if (blk.tid() == 0) S.tile = (int32_t)blk.atomic_add_ret(&P.ctl->ticket_c, 1u);
         blk.sync();

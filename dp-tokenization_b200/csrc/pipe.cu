@@ -9,6 +9,17 @@
 #include "kernels.h"
 #include "vocab.h"
 
+// resident CTAs per SM the kernels are compiled for (register budgets; tuned on the B200, profiles/README.md)
+#ifndef DPT_PA_CTAS
+#define DPT_PA_CTAS 8
+#endif
+#ifndef DPT_PB_CTAS
+#define DPT_PB_CTAS 12
+#endif
+#ifndef DPT_PC_CTAS
+#define DPT_PC_CTAS 4
+#endif
+
 namespace dpt {
 
 __device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long* p) {
@@ -23,7 +34,12 @@ __device__ __forceinline__ void st_relaxed_gpu(unsigned long long* p, unsigned l
 struct DevBlk {
     __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
     __device__ __forceinline__ int nthreads() const { return (int)blockDim.x; }
+#if defined(DPT_TICKET_ORDER)  // tuning variant: tiles from an atomic ticket instead of blockIdx order
+    __device__ __forceinline__ bool persistent() const { return true; }
+#else
     __device__ __forceinline__ bool persistent() const { return false; }
+#endif
+    __device__ __forceinline__ int block_index() const { return (int)blockIdx.x; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
     __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t v) const { atomicOr(p, v); }
     __device__ __forceinline__ void atomic_add(uint32_t* p, uint32_t v) const { atomicAdd(p, v); }
@@ -75,6 +91,16 @@ struct DevBlk {
         return base + (threadIdx.x & 31);
     }
     __device__ __forceinline__ bool warp_any(bool p) const { return __any_sync(0xffffffffu, p); }
+    __device__ __forceinline__ int warp_count(bool p) const { return __popc(__ballot_sync(0xffffffffu, p)); }
+    // kernel B: the lanes with `ask` take consecutive work items (one atomic per warp); other lanes get a don't-care
+    __device__ __forceinline__ unsigned long long warp_take_n(unsigned long long* cursor, bool ask) const {
+        const unsigned m = __ballot_sync(0xffffffffu, ask);
+        const unsigned lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (lane == 0 && m) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        return base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+    }
 
     // decoupled look-back, split in two so a tile can publish early and resolve late.  descriptor = status << 62 |
     // value (1 = this tile's aggregate, 2 = inclusive prefix).  publish: thread 0.  resolve: warp 0 sums the
@@ -129,7 +155,7 @@ struct DevBlk {
 };
 
 // SPM_LLAMA rule: 20 KB of shared memory and <= 32 registers -> 8 CTAs (64 warps) per SM
-__global__ void __launch_bounds__(PA_THREADS, 8) k_scan_dedup(const __grid_constant__ PipeParams P) {
+__global__ void __launch_bounds__(PA_THREADS, DPT_PA_CTAS) k_scan_dedup(const __grid_constant__ PipeParams P) {
     __shared__ ASmemT<true> S;
     DevBlk blk;
     pa_kernel<DevBlk, true>(blk, P, S);
@@ -141,7 +167,7 @@ __global__ void __launch_bounds__(PA_THREADS) k_scan_dedup_bl(const __grid_const
     pa_kernel<DevBlk, false>(blk, P, S);
 }
 
-__global__ void __launch_bounds__(PB_THREADS, 16) k_dp_distinct(const __grid_constant__ PipeParams P) {
+__global__ void __launch_bounds__(PB_THREADS, DPT_PB_CTAS) k_dp_distinct(const __grid_constant__ PipeParams P) {
     DevBlk blk;
     pb_thread(blk, P);
 }
@@ -151,7 +177,7 @@ __global__ void __launch_bounds__(PB_THREADS) k_dp_distinct_long(const __grid_co
     pb_long_thread(blk, P, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 
-__global__ void __launch_bounds__(PC_THREADS) k_emit(const __grid_constant__ PipeParams P) {
+__global__ void __launch_bounds__(PC_THREADS, DPT_PC_CTAS) k_emit(const __grid_constant__ PipeParams P) {
     __shared__ CSmem S;
     DevBlk blk;
     pc_kernel(blk, P, S);

@@ -11,6 +11,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libdptok.so")
+if os.environ.get("DPT_LIB_PATH"):  # development: a tuning variant of the same library (tools/variants.py)
+    LIB_PATH = os.path.abspath(os.environ["DPT_LIB_PATH"])
 
 OK, EINVAL, ECUDA, ECAPACITY, ENOMEM, ESTATE = range(6)
 UNIT_BYTES, UNIT_CODEPOINTS = 0, 1

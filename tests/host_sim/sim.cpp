@@ -28,6 +28,7 @@ struct HostBlk {
     int tid() const { return tid_; }
     int nthreads() const { return nt_; }
     bool persistent() const { return true; }  // ONE emulated CTA walks all tiles in ticket order
+    int block_index() const { return 0; }  // unused: the emulated CTA is persistent
     void sync() const { if (sh) sh->bar.arrive_and_wait(); }
     void atomic_or(uint32_t* p, uint32_t v) const { __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
     void atomic_add(uint32_t* p, uint32_t v) const { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
@@ -55,6 +56,10 @@ struct HostBlk {
     void reconverge() const {}
     unsigned long long warp_take(unsigned long long* cursor) const { return __atomic_fetch_add(cursor, 1ull, __ATOMIC_RELAXED); }
     bool warp_any(bool p) const { return p; }
+    int warp_count(bool p) const { return p ? 1 : 0; }
+    unsigned long long warp_take_n(unsigned long long* cursor, bool ask) const {
+        return ask ? __atomic_fetch_add(cursor, 1ull, __ATOMIC_RELAXED) : ~0ull;
+    }
     // tiles are processed in order by the one emulated CTA: the predecessor's inclusive prefix is always there
     void lookback_publish(unsigned long long* desc, int tile, unsigned long long agg) const {
         if (tid_ == 0) desc[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | agg;
