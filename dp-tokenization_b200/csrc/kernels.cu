@@ -5,6 +5,9 @@
 // tile kernel in fused.cu, which handles the common short-word case at speed.
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
@@ -571,10 +574,12 @@ void profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
 std::string profile_report() {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     std::map<std::string, std::pair<int64_t, double>> agg;
+    const bool list = getenv("DPT_PROF_LIST") != nullptr;  // development: every launch, in order, on stderr
     for (auto& r : g_prof) {
         cudaEventSynchronize(r.b);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, r.a, r.b);
+        if (list) fprintf(stderr, "[dpt prof] %-22s %.4f ms\n", r.name, ms);
         auto& e = agg[r.name];
         e.first += 1;
         e.second += ms;
