@@ -236,14 +236,14 @@ DPT_HD uint32_t dpt_da_load(const uint32_t* da, uint32_t slot) {
 }
 
 // The forward pass as a resumable state machine: dpt_flat32_init sets up the per-position arrays, every call of
-// dpt_flat32_step advances the (start j, end i) walk by at most one trie step and returns false once the pass is
-// complete.  Kernel B keeps one of these per lane, steps all lanes of a warp in lock step and hands a finished lane
-// its next word while the others keep walking (dpt_pipe.h: pb_thread), so a lane never idles for long.
+// dpt_flat32_step advances the (start j, end i) walk by at most one trie step; the pass is complete when j == n.
+// Kernel B keeps one of these per lane and steps all lanes of a warp in lock step (dpt_pipe.h: pb_thread).
+// No flags: entry == 0 means "no walk open" (an open walk always holds an occupied trie entry).
 struct DptFlat32 {
     int32_t j, i;          // current start position, current end position
     uint32_t entry, cl, kj;
-    bool walking;
 };
+DPT_HD bool dpt_flat32_running(const DptFlat32& st, int32_t n) { return st.j < n; }
 // Ap/Bp: packed back-pointers  slot | distance << 22  (distance <= DPT_FLAT32_MAX, slots < 2^22): one 4-byte store
 // per back-pointer and relaxation instead of a distance and a slot each
 DPT_HD void dpt_flat32_init(const DptVocabView& V, const uint8_t* s, int32_t n, uint32_t* best, uint32_t* Ap, uint32_t* Bp,
@@ -263,19 +263,17 @@ DPT_HD void dpt_flat32_init(const DptVocabView& V, const uint8_t* s, int32_t n, 
     st.entry = 0;
     st.cl = 0;
     st.kj = 0;
-    st.walking = false;
 }
-DPT_HD bool dpt_flat32_step(const DptVocabView& V, const uint8_t* s, int32_t n, uint32_t* best, uint32_t* Ap, uint32_t* Bp,
+DPT_HD void dpt_flat32_step(const DptVocabView& V, const uint8_t* s, int32_t n, uint32_t* best, uint32_t* Ap, uint32_t* Bp,
                             DptFlat32& st) {
     const bool cp_mode = V.unit_mode != 0;
-    if (!st.walking) {  // next start position (same iteration as its first trie step)
-        if (++st.j >= n) return false;
+    if (st.entry == 0) {  // next start position (same iteration as its first trie step)
+        if (++st.j >= n) return;
         st.kj = best[st.j];
+        if (st.kj == DPT_K32_NONE) return;  // not a unit boundary: nothing starts here
         st.entry = DPT_DA_ROOT_ENTRY;
         st.i = st.j;
         st.cl = 0;
-        st.walking = st.kj != DPT_K32_NONE;  // not a unit boundary: nothing starts here
-        if (!st.walking) return true;
     }
     const uint32_t base = st.entry >> DPT_DA_BASE_SHIFT;
     const uint32_t c = (uint32_t)s[st.i];  // i < n whenever a walk is open
@@ -283,10 +281,9 @@ DPT_HD bool dpt_flat32_step(const DptVocabView& V, const uint8_t* s, int32_t n, 
     uint32_t e = 0;
     if (base != 0) e = dpt_da_load(V.da, slot);
     if ((e & DPT_DA_MATCH_MASK) != (DPT_DA_OCCUPIED | c)) {
-        st.walking = false;
-        return true;
+        st.entry = 0;
+        return;
     }
-    st.entry = e;
     const int32_t i = ++st.i;
     st.cl += (!cp_mode || dpt_is_cp_start(c)) ? 1u : 0u;
     if (e & DPT_DA_TERMINAL) {
@@ -301,15 +298,13 @@ DPT_HD bool dpt_flat32_step(const DptVocabView& V, const uint8_t* s, int32_t n, 
             }
         }
     }
-    if (i >= n) st.walking = false;  // end of the word: the walk from j is over
-    return true;
+    st.entry = i >= n ? 0u : e;  // end of the word: the walk from j is over
 }
 DPT_HD void dpt_forward_flat32(const DptVocabView& V, const uint8_t* s, int32_t n, uint32_t* best, uint32_t* Ap,
                                uint32_t* Bp) {
     DptFlat32 st;
     dpt_flat32_init(V, s, n, best, Ap, Bp, st);
-    while (dpt_flat32_step(V, s, n, best, Ap, Bp, st)) {
-    }
+    while (dpt_flat32_running(st, n)) dpt_flat32_step(V, s, n, best, Ap, Bp, st);
 }
 
 // Backward chase for dpt_forward_flat32: word_len ids into out_ids[0..word_len) in text order.  The code-point count of

@@ -396,16 +396,30 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
             S.lut[i >> 2][i & 3] = rem >= 4 ? ~0u : ((1u << (8 * rem)) - 1u);
         }
         for (int w = tid; w < PA_NW + 2; w += nt) {
-            S.mDS[w] = 0;
             S.mSY[w] = 0;
             if (!spm) S.mWS[w] = 0;
             if (w >= PA_NW) S.mCS[w] = S.mSP[w] = S.mM3[w] = S.mCF[w] = S.mWS[w] = S.mCX[w] = S.cnt[w] = 0;
         }
-        if (tid == 0) {
-            S.d_first = (int32_t)pp_lower_bound(P.doc_offs, P.n_docs + 1, g0 < 0 ? 0 : g0);
-            S.n_pend = 0;
-            S.any_cx = 0;
-            for (int c = 0; c < PB_CLASSES; ++c) S.n_pend_c[c] = S.cur_c[c] = 0;
+        // Document starts of the region, by the first warp alone while the text loads are in flight: a 32-ary search
+        // for the first document (4 rounds of loads instead of the 16 dependent ones of a binary search, which was the
+        // longest thing in front of the first barrier: ncu v12), then one offset per lane.
+        if (blk.in_first_warp()) {
+            const int lane = blk.lane(), ww = blk.warp_width();
+            for (int w = lane; w < PA_NW + 2; w += ww) S.mDS[w] = 0;
+            blk.reconverge();
+            const int64_t d_first = blk.warp_lower_bound(P.doc_offs, P.n_docs + 1, g0 < 0 ? 0 : g0);
+            for (int64_t k = d_first + lane; k <= P.n_docs; k += ww) {
+                const int64_t o = P.doc_offs[k];
+                if (o >= g0 + PA_R) break;
+                const int r = (int)(o - g0);
+                blk.atomic_or(&S.mDS[r >> 5], 1u << (r & 31));
+            }
+            if (tid == 0) {
+                S.d_first = (int32_t)d_first;
+                S.n_pend = 0;
+                S.any_cx = 0;
+                for (int c = 0; c < PB_CLASSES; ++c) S.n_pend_c[c] = S.cur_c[c] = 0;
+            }
         }
     }
     blk.sync();
@@ -434,12 +448,6 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
         reinterpret_cast<uint16_t*>(S.mCS)[hw] = (uint16_t)cs;
         reinterpret_cast<uint16_t*>(S.mSP)[hw] = (uint16_t)sp;
         reinterpret_cast<uint16_t*>(S.mM3)[hw] = (uint16_t)(spm ? m3 : 0u);
-    }
-    for (int64_t k = (int64_t)S.d_first + tid; k <= P.n_docs; k += nt) {
-        const int64_t o = P.doc_offs[k];
-        if (o >= g0 + PA_R) break;
-        const int r = (int)(o - g0);
-        blk.atomic_or(&S.mDS[r >> 5], 1u << (r & 31));
     }
     blk.sync();
 
@@ -980,9 +988,8 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
     DptFlat32 st;
     st.j = st.i = 0;
     st.entry = st.cl = st.kj = 0;
-    st.walking = false;
     ResRec* out = nullptr;
-    int32_t n = 0;
+    int32_t n = 0;      // 0: no word (dpt_flat32_running is false)
     bool have = false;  // this lane holds a word whose forward pass is not complete
     bool more = true;   // warp-uniform: the work list may still hold items
     for (;;) {
@@ -992,6 +999,7 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
             const uint64_t idx = blk.warp_take_n(&P.ctl->b_cursor, ask);
             const bool got = ask && idx < total;
             more = !blk.warp_any(ask && !got);
+            bool fresh = false;
             if (got) {
                 const PbItem it = pb_item(P, idx, npc, n_odd);
                 const int32_t nlen = pb_normalise(P, it.pos, it.end, it.marker, norm, PB_LOCAL);
@@ -1006,9 +1014,15 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
                 } else {
                     out = it.out;
                     n = nlen;
-                    dpt_flat32_init(P.V, norm, n, best, Ap, Bp, st);
-                    have = true;
+                    fresh = true;
                 }
+            }
+            // the lanes leave the normalisation at different times: bring them together again before the
+            // initialisation loop (ncu, v12: it ran with 4 of 32 lanes inside the divergent region)
+            blk.reconverge();
+            if (fresh) {
+                dpt_flat32_init(P.V, norm, n, best, Ap, Bp, st);
+                have = true;
             }
             blk.reconverge();
         }
@@ -1018,16 +1032,17 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
         }
         // the hot loop: one trie step per lane and iteration
         const int thresh = more ? PB_REFILL : 1;
-        bool running = have;
         do {
 #pragma unroll
             for (int r = 0; r < 4; ++r)
-                if (running) running = dpt_flat32_step(P.V, norm, n, best, Ap, Bp, st);
-        } while (blk.warp_count(running) >= thresh);
+                if (dpt_flat32_running(st, n)) dpt_flat32_step(P.V, norm, n, best, Ap, Bp, st);
+        } while (blk.warp_count(dpt_flat32_running(st, n)) >= thresh);
         blk.reconverge();
-        if (have && !running) {
+        if (have && !dpt_flat32_running(st, n)) {
             pb_finish_word(blk, P, norm, n, best, Ap, Bp, out);
             have = false;
+            n = 0;
+            st.j = 0;
         }
         blk.reconverge();
     }

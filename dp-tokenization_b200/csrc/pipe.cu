@@ -83,6 +83,24 @@ struct DevBlk {
     }
 
     __device__ __forceinline__ void reconverge() const { __syncwarp(); }
+    __device__ __forceinline__ bool in_first_warp() const { return threadIdx.x < 32; }
+    __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31); }
+    __device__ __forceinline__ int warp_width() const { return 32; }
+    // first i in [0, n] with a[i] >= x (a sorted), by the 32 lanes of one warp: every round probes 32 split points
+    __device__ __forceinline__ int64_t warp_lower_bound(const int64_t* a, int64_t n, int64_t x) const {
+        const int lane = (int)(threadIdx.x & 31);
+        int64_t lo = 0, hi = n;
+        while (hi > lo) {
+            const int64_t step = (hi - lo + 32) / 33;
+            const int64_t idx = lo + (int64_t)(lane + 1) * step - 1;
+            const bool less = idx < hi && __ldg(a + idx) < x;
+            const int k = __popc(__ballot_sync(0xffffffffu, less));  // a is sorted: the first k probes are < x
+            const int64_t cut = lo + (int64_t)(k + 1) * step - 1;     // probe k: >= x, or beyond hi
+            lo += (int64_t)k * step;
+            if (k < 32 && cut < hi) hi = cut;
+        }
+        return lo;
+    }
     // kernel B: lane 0 claims 32 consecutive work items for its warp; returns this lane's item index
     __device__ __forceinline__ unsigned long long warp_take(unsigned long long* cursor) const {
         unsigned long long base = 0;
