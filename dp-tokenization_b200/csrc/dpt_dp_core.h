@@ -246,13 +246,16 @@ struct DptFlat32 {
 DPT_HD bool dpt_flat32_running(const DptFlat32& st, int32_t n) { return st.j < n; }
 // Ap/Bp: packed back-pointers  slot | distance << 22  (distance <= DPT_FLAT32_MAX, slots < 2^22): one 4-byte store
 // per back-pointer and relaxation instead of a distance and a slot each
+// upos[p] (optional) = unit index of position p (n <= DPT_FLAT32_MAX): the backward chase reads a token's unit count off
+// it instead of counting code-point starts byte by byte
 DPT_HD void dpt_flat32_init(const DptVocabView& V, const uint8_t* s, int32_t n, uint32_t* best, uint32_t* Ap, uint32_t* Bp,
-                            DptFlat32& st) {
+                            DptFlat32& st, uint8_t* upos = nullptr) {
     const bool cp_mode = V.unit_mode != 0;
     uint32_t u = 0;
     for (int32_t p = 0; p <= n; ++p) {
         const bool b = (p == 0 || p == n || !cp_mode) ? true : dpt_is_cp_start(s[p]);
         best[p] = b ? ((u << 17) | 0x1FFFFu) : DPT_K32_NONE;  // phantom: len = unit index, not reachable
+        if (upos) upos[p] = (uint8_t)u;
         if (b) ++u;
         Ap[p] = 0;
         Bp[p] = 0;
@@ -310,7 +313,8 @@ DPT_HD void dpt_forward_flat32(const DptVocabView& V, const uint8_t* s, int32_t 
 // Backward chase for dpt_forward_flat32: word_len ids into out_ids[0..word_len) in text order.  The code-point count of
 // a token is only needed until the token of length `target` has been taken.
 DPT_HD void dpt_backward_chase(const DptVocabView& V, const uint8_t* s, int32_t n, uint32_t word_len, uint32_t target,
-                               const uint32_t* Ap, const uint32_t* Bp, int32_t* out_ids, int64_t out_cap) {
+                               const uint32_t* Ap, const uint32_t* Bp, int32_t* out_ids, int64_t out_cap,
+                               const uint8_t* upos = nullptr) {
     const bool cp_mode = V.unit_mode != 0;
     int64_t slot_out = (int64_t)word_len - 1;
     bool got = false;
@@ -322,8 +326,12 @@ DPT_HD void dpt_backward_chase(const DptVocabView& V, const uint8_t* s, int32_t 
         if (!got) {
             uint32_t cl = (uint32_t)d;
             if (cp_mode) {
-                cl = 0;
-                for (int32_t p = i - d; p < i; ++p) cl += dpt_is_cp_start(s[p]) ? 1u : 0u;
+                if (upos) {  // tokens start and end on unit boundaries
+                    cl = (uint32_t)upos[i] - (uint32_t)upos[i - d];
+                } else {
+                    cl = 0;
+                    for (int32_t p = i - d; p < i; ++p) cl += dpt_is_cp_start(s[p]) ? 1u : 0u;
+                }
             }
             if (cl == target) got = true;
         }

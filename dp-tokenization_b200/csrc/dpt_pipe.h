@@ -37,12 +37,21 @@ struct alignas(16) uint4 {
 
 namespace dpt {
 
-constexpr int PA_T = 4096;                    // raw bytes per tile of kernel A
+#ifndef DPT_PA_T
+#define DPT_PA_T 4096
+#endif
+#ifndef DPT_PA_THREADS
+#define DPT_PA_THREADS 256
+#endif
+#ifndef DPT_PA_WIN
+#define DPT_PA_WIN 1024
+#endif
+constexpr int PA_T = DPT_PA_T;                // raw bytes per tile of kernel A
 constexpr int PA_HALO = 32;                   // look-behind (multiple of 32 keeps mask words aligned)
 constexpr int PA_LA = 96;                     // look-ahead: a word that ends within it is handled in-tile
 constexpr int PA_R = PA_HALO + PA_T + PA_LA;  // region bytes = 4224 = 132 * 32
 constexpr int PA_NW = PA_R / 32;
-constexpr int PA_THREADS = 256;
+constexpr int PA_THREADS = DPT_PA_THREADS;
 constexpr int PA_MAXLEN = 63;                 // longest word body (bytes) that goes through the dedup table
 constexpr int PA_PROBES = 8;
 constexpr int PB_THREADS = 128;
@@ -59,7 +68,7 @@ constexpr int PB_LOCAL = 72;                  // normalised bytes solved with pe
 constexpr int PB_REFILL = DPT_PB_REFILL;
 constexpr int PC_THREADS = 256;
 constexpr int PC_PER = 8;                     // words per thread in kernel C
-constexpr int PA_WIN = 1024;                  // words of a tile handled per pass (a 4 KB tile holds ~520; more -> more passes)
+constexpr int PA_WIN = DPT_PA_WIN;                  // words of a tile handled per pass (a 4 KB tile holds ~520; more -> more passes)
 constexpr int PC_TILE = PC_THREADS * PC_PER;
 constexpr int PC_STAGE = 6144;                // ids of one kernel-C tile staged in shared memory (more -> direct writes)
 
@@ -168,7 +177,6 @@ struct ASmemT {
     uint16_t dslist[kSpm ? 2 : PA_R + 32];  // byte-level rules: region indices of the document starts, in order
     uint32_t pend[PA_WIN];    // table slots claimed in the current window
     uint32_t stage[PA_WIN];   // refs of the current window, written out coalesced once the word offset is known
-    alignas(16) uint32_t lut[17][4];  // lut[len]: byte masks of the first min(len,16) bytes of a 16-byte window
     uint32_t scan[40];
     int32_t tile, d_first, n_entries;
     uint32_t any_cx;          // some mCX bit is set in this tile (rare: the per-word range test is skipped otherwise)
@@ -286,7 +294,27 @@ DPT_HD void pp_load16(const uint8_t* base4, int64_t off, int len, uint32_t v[4])
         v[k] &= (uint32_t)((1ull << (8 * rem)) - 1ull);
     }
 }
-// 16 bytes at byte offset `off` of a 4-byte-aligned buffer, unmasked (the caller masks with ASmemT::lut[len])
+// PP_TAIL_LUT[len]: byte masks of the first min(len,16) bytes of a 16-byte window (four little-endian words)
+#define PP_TL(n) {(n) >= 4 ? 0xFFFFFFFFu : (n) <= 0 ? 0u : ((1u << (8 * ((n) > 0 && (n) < 4 ? (n) : 0))) - 1u),                 \
+                  (n) >= 8 ? 0xFFFFFFFFu : (n) <= 4 ? 0u : ((1u << (8 * ((n) > 4 && (n) < 8 ? (n) - 4 : 0))) - 1u),             \
+                  (n) >= 12 ? 0xFFFFFFFFu : (n) <= 8 ? 0u : ((1u << (8 * ((n) > 8 && (n) < 12 ? (n) - 8 : 0))) - 1u),           \
+                  (n) >= 16 ? 0xFFFFFFFFu : (n) <= 12 ? 0u : ((1u << (8 * ((n) > 12 && (n) < 16 ? (n) - 12 : 0))) - 1u)}
+#if defined(__CUDACC__)
+static __device__ const uint4 PP_TAIL_LUT[17] = {
+#else
+static const uint4 PP_TAIL_LUT[17] = {
+#endif
+    PP_TL(0), PP_TL(1), PP_TL(2),  PP_TL(3),  PP_TL(4),  PP_TL(5),  PP_TL(6),  PP_TL(7), PP_TL(8),
+    PP_TL(9), PP_TL(10), PP_TL(11), PP_TL(12), PP_TL(13), PP_TL(14), PP_TL(15), PP_TL(16)};
+#undef PP_TL
+DPT_PIPE_FN uint4 pp_tail_lut(int len) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(&PP_TAIL_LUT[len < 16 ? len : 16]);
+#else
+    return PP_TAIL_LUT[len < 16 ? len : 16];
+#endif
+}
+// 16 bytes at byte offset `off` of a 4-byte-aligned buffer, unmasked (the caller masks with pp_tail_lut(len))
 DPT_HD void pp_load16_raw(const uint8_t* base4, int64_t off, uint32_t v[4]) {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(base4 + (off & ~(int64_t)3));
     const uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3], a4 = w[4];
@@ -389,17 +417,17 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                 }
             }
         }
-        for (int i = tid; i < 64; i += nt) S.text[PA_R + i] = 0;
-        for (int i = tid; i < 17 * 4; i += nt) {
-            int rem = (i >> 2) - 4 * (i & 3);
-            rem = rem < 0 ? 0 : rem > 4 ? 4 : rem;
-            S.lut[i >> 2][i & 3] = rem >= 4 ? ~0u : ((1u << (8 * rem)) - 1u);
+        // small fixed jobs go to the last threads of the block (the first warp is busy with the document search)
+        if (tid >= nt - 4) *reinterpret_cast<uint4*>(&S.text[PA_R + 16 * (nt - 1 - tid)]) = uint4{0u, 0u, 0u, 0u};
+        if (tid >= nt - 6 && tid < nt - 4) {  // the two mask words behind the region
+            const int w = PA_NW + (nt - 5 - tid);
+            S.mCS[w] = S.mSP[w] = S.mM3[w] = S.mCF[w] = S.mWS[w] = S.mCX[w] = S.cnt[w] = S.mSY[w] = 0;
         }
-        for (int w = tid; w < PA_NW + 2; w += nt) {
-            S.mSY[w] = 0;
-            if (!spm) S.mWS[w] = 0;
-            if (w >= PA_NW) S.mCS[w] = S.mSP[w] = S.mM3[w] = S.mCF[w] = S.mWS[w] = S.mCX[w] = S.cnt[w] = 0;
-        }
+        if (!spm)
+            for (int w = tid; w < PA_NW; w += nt) {
+                S.mSY[w] = 0;
+                S.mWS[w] = 0;
+            }
         // Document starts of the region, by the first warp alone while the text loads are in flight: a 32-ary search
         // for the first document (4 rounds of loads instead of the 16 dependent ones of a binary search, which was the
         // longest thing in front of the first barrier: ncu v12), then one offset per lane.
@@ -716,7 +744,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                     // bodies of one length that share 16 bytes are too few to lengthen the probe sequences.
                     uint32_t wv[4];
                     pp_load16_raw(S.text, b, wv);
-                    const uint4 lm = *reinterpret_cast<const uint4*>(S.lut[len < 16 ? len : 16]);
+                    const uint4 lm = pp_tail_lut(len);
                     wv[0] &= lm.x; wv[1] &= lm.y; wv[2] &= lm.z; wv[3] &= lm.w;
                     uint32_t h = 0x811C9DC5u ^ (uint32_t)len;
                     h = pp_hash_step(pp_hash_step(pp_hash_step(pp_hash_step(h, wv[0]), wv[1]), wv[2]), wv[3]);
@@ -951,7 +979,7 @@ DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint64_t i, const uint32_t* npc,
 // (normalise, initialise) while the unfinished lanes keep their walk state in registers, and all re-enter the loop.
 template <class Blk>
 DPT_PIPE_FN void pb_finish_word(Blk& blk, const PipeParams& P, const uint8_t* norm, int32_t n, const uint32_t* best,
-                                const uint32_t* Ap, const uint32_t* Bp, ResRec* out) {
+                                const uint32_t* Ap, const uint32_t* Bp, const uint8_t* upos, ResRec* out) {
     ResRec rec;
     for (int k = 0; k < RES_INLINE; ++k) rec.ids[k] = 0;
     const uint32_t kn = best[n];
@@ -960,14 +988,14 @@ DPT_PIPE_FN void pb_finish_word(Blk& blk, const PipeParams& P, const uint8_t* no
     rec.meta = (word_len & 0xFFFFFFu) | (reach ? 0u : RES_UNTOK);
     if (reach) {
         if (word_len <= (uint32_t)RES_INLINE) {
-            dpt_backward_chase(P.V, norm, n, word_len, dpt_k32_longest(kn), Ap, Bp, rec.ids, RES_INLINE);
+            dpt_backward_chase(P.V, norm, n, word_len, dpt_k32_longest(kn), Ap, Bp, rec.ids, RES_INLINE, upos);
         } else {
             const unsigned long long off = blk.atomic_add_u64_ret(&P.persist->pool_used, (unsigned long long)word_len);
             rec.meta |= RES_POOLED;
             rec.ids[0] = (int32_t)(uint32_t)(off & 0xFFFFFFFFull);
             rec.ids[1] = (int32_t)(uint32_t)(off >> 32);
             if ((int64_t)(off + word_len) <= P.pool_cap)
-                dpt_backward_chase(P.V, norm, n, word_len, dpt_k32_longest(kn), Ap, Bp, P.pool + off, (int64_t)word_len);
+                dpt_backward_chase(P.V, norm, n, word_len, dpt_k32_longest(kn), Ap, Bp, P.pool + off, (int64_t)word_len, upos);
         }
     }
     *out = rec;
@@ -985,6 +1013,7 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
     total += n_odd;
     uint8_t norm[PB_LOCAL + 8];
     uint32_t best[PB_LOCAL + 1], Ap[PB_LOCAL + 1], Bp[PB_LOCAL + 1];
+    uint8_t upos[PB_LOCAL + 8];
     DptFlat32 st;
     st.j = st.i = 0;
     st.entry = st.cl = st.kj = 0;
@@ -1021,7 +1050,7 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
             // initialisation loop (ncu, v12: it ran with 4 of 32 lanes inside the divergent region)
             blk.reconverge();
             if (fresh) {
-                dpt_flat32_init(P.V, norm, n, best, Ap, Bp, st);
+                dpt_flat32_init(P.V, norm, n, best, Ap, Bp, st, upos);
                 have = true;
             }
             blk.reconverge();
@@ -1039,7 +1068,7 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
         } while (blk.warp_count(dpt_flat32_running(st, n)) >= thresh);
         blk.reconverge();
         if (have && !dpt_flat32_running(st, n)) {
-            pb_finish_word(blk, P, norm, n, best, Ap, Bp, out);
+            pb_finish_word(blk, P, norm, n, best, Ap, Bp, upos, out);
             have = false;
             n = 0;
             st.j = 0;

@@ -2,6 +2,7 @@
 // C scan+emit -> D counters.  Five launches per corpus, no host synchronisation in between.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "../../include/dptok.h"
@@ -394,7 +395,12 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
     if (do_dp) {
     {
         ProfScope prof("k_dp_distinct", st);
-        k_dp_distinct<<<(unsigned)(sm_count * 16), PB_THREADS, 0, st>>>(P);
+        static int b_ctas = 0;  // CTAs per SM of kernel B's grid (development knob: DPT_B_GRID)
+        if (!b_ctas) {
+            const char* e = getenv("DPT_B_GRID");
+            b_ctas = e && atoi(e) > 0 ? atoi(e) : 16;
+        }
+        k_dp_distinct<<<(unsigned)(sm_count * b_ctas), PB_THREADS, 0, st>>>(P);
         ++g_launches;
     }
     {

@@ -166,14 +166,20 @@ class Engine:
 
     # ---- corpus path from HOST buffers: chunked, H2D / kernels / D2H overlapped ---------------------------------------
     def encode_corpus_host(self, h_text: torch.Tensor, doc_offs: np.ndarray, rule: int, chunk_bytes: int = 16 << 20,
-                           n_streams: int = 3, out_ids: Optional[torch.Tensor] = None) -> "HostResult":
+                           n_streams: int = 3, out_ids: Optional[torch.Tensor] = None,
+                           overlap: bool = False) -> "HostResult":
         """``h_text``: uint8 HOST tensor (pinned for full speed) of concatenated non-empty documents; ``doc_offs``:
         int64[n_docs+1] numpy array.  The corpus is cut at document boundaries into ranges of about ``chunk_bytes``.
         Range k is copied into its place in ONE device text buffer on the copy-in stream, tokenized by
         ``dpt_encode_corpus_range`` on the compute stream (ranges in order; the word table is shared by all ranges
         of the call, so a word is still solved once per corpus) and its ids are copied out on the
         copy-out stream over a ring of ``n_streams`` output slots: PCIe in both directions and the SMs work at the same
-        time.  Returns host tensors."""
+        time.  Returns host tensors.
+
+        Measured on the B200 box (100 MB corpus, tools/sweep_e2e.py): 3.40-3.50 ms for every chunk size from 16 to 34 MB,
+        3 or 8 slots, with or without ``overlap`` (scan / DP / emit of neighbouring ranges on three streams): the path
+        is bound by PCIe, whose two directions together move ~57 GB/s on this box (H2D alone 1.81 ms, D2H alone
+        1.69 ms, 100.5 + 95.2 MB in 3.43 ms when both run)."""
         assert h_text.dtype == torch.uint8 and not h_text.is_cuda
         doc_offs = np.ascontiguousarray(doc_offs, dtype=np.int64)
         n_docs = len(doc_offs) - 1
@@ -202,13 +208,14 @@ class Engine:
                 ws_bytes = lib.dpt_encode_corpus_range_workspace(rule, max_b, max_d, word_cap, 0)
                 tws_bytes = lib.dpt_corpus_table_workspace(n_bytes, word_cap_total, 0)
                 self._host = dict(
-                    streams=[torch.cuda.Stream(device=dev) for _ in range(3)],  # copy-in, compute, copy-out
+                    streams=[torch.cuda.Stream(device=dev) for _ in range(5)],  # copy-in, scan/compute, copy-out, DP, emit
                     ev_reset=torch.cuda.Event(),
                     d_text=torch.empty(n_bytes, dtype=torch.uint8, device=dev),
                     d_offs=torch.empty(n_docs + 1, dtype=torch.int64, device=dev),
                     h_offs=torch.empty(n_docs + 1, dtype=torch.int64).pin_memory(),
                     table_ws=torch.empty(int(tws_bytes), dtype=torch.uint8, device=dev),
                     slots=[dict(ev_in=torch.cuda.Event(), ev_a=torch.cuda.Event(), ev_ab=torch.cuda.Event(),
+                                ev_b=torch.cuda.Event(),
                                 ev_comp=torch.cuda.Event(),
                                 ev_out=torch.cuda.Event(),
                                 ids=torch.empty(ids_cap, dtype=torch.int32, device=dev),
@@ -225,7 +232,7 @@ class Engine:
                 self._host_key = key
             H = self._host
             slots = H["slots"]
-            s_in, s_comp, s_out = H["streams"]
+            s_in, s_comp, s_out, s_dp, s_emit = H["streams"]
             cur = torch.cuda.current_stream(dev)
             for st in H["streams"]:
                 st.wait_stream(cur)
@@ -285,21 +292,39 @@ class Engine:
                     H["d_text"][b0:b1].copy_(h_text[b0:b1], non_blocking=True)
                     sl["ev_in"].record(s_in)
                     mark("h2d-end", k, s_in)
-                # ranges are tokenized in order on ONE compute stream: a range may only reference table slots claimed by
-                # itself or an earlier range, and emit(k) needs every DP result up to k.  (Measured: splitting the range
-                # call into scan / DP / emit phases on separate streams - dpt_encode_corpus_range's `phases` - costs
-                # more in launches and events than the overlap of the latency-bound DP kernel gains: 4.0 vs 3.4 ms.)
-                with torch.cuda.stream(s_comp):
-                    s_comp.wait_event(sl["ev_in"])
-                    s_comp.wait_event(sl["ev_out"])         # the slot's previous ids have been copied out
-                    mark("comp-begin", k, s_comp)
-                    range_call(sl, k, 7, 1 if k == 0 else 0, s_comp)
+                # overlap=False: the three phases of a range run back to back on ONE compute stream
+                if overlap:
+                    # Three in-order streams, one per phase: scan(k+1) and emit(k-1) run beside the DP kernel of range
+                    # k, whose small launches are latency-bound (a batch of long words takes ~0.1-0.2 ms however few
+                    # words there are) and leave most of the GPU idle.  Scans stay in range order (a range may only
+                    # reference table slots claimed by itself or an earlier range), DP kernels too (emit(k) needs every
+                    # DP result up to k: the DP stream is in order, so ev_b of k covers them).
+                    with torch.cuda.stream(s_comp):
+                        s_comp.wait_event(sl["ev_in"])
+                        s_comp.wait_event(sl["ev_comp"])    # the slot's previous range has been emitted (workspace reuse)
+                        mark("comp-begin", k, s_comp)
+                        range_call(sl, k, 1, 1 if k == 0 else 0, s_comp)
+                        sl["ev_a"].record(s_comp)
+                    with torch.cuda.stream(s_dp):
+                        s_dp.wait_event(sl["ev_a"])
+                        range_call(sl, k, 2, 0, s_dp)
+                        sl["ev_b"].record(s_dp)
+                with torch.cuda.stream(s_emit if overlap else s_comp):
+                    cs = s_emit if overlap else s_comp
+                    if overlap:
+                        cs.wait_event(sl["ev_b"])
+                    else:
+                        cs.wait_event(sl["ev_in"])
+                    cs.wait_event(sl["ev_out"])             # the slot's previous ids have been copied out
+                    if not overlap:
+                        mark("comp-begin", k, cs)
+                    range_call(sl, k, 4 if overlap else 7, 0 if overlap else (1 if k == 0 else 0), cs)
                     sl["h_small"][:8].copy_(sl["n_out"], non_blocking=True)
                     sl["h_small"][8:12].copy_(sl["counters"], non_blocking=True)
                     sl["h_doc_tok"][:hi - lo + 1].copy_(sl["doc_tok"][:hi - lo + 1], non_blocking=True)
                     sl["h_doc_flags"][:hi - lo].copy_(sl["doc_flags"][:hi - lo], non_blocking=True)
-                    sl["ev_comp"].record(s_comp)
-                    mark("comp-end", k, s_comp)
+                    sl["ev_comp"].record(cs)
+                    mark("comp-end", k, cs)
                 pending.append((k, sl))
             while pending:
                 finalize(*pending.pop(0))

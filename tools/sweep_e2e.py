@@ -19,11 +19,14 @@ for name, fn in (("H2D 100MB", lambda: d_text.copy_(h_text, non_blocking=True)),
     fn(); torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(5): fn()
     torch.cuda.synchronize(); print(name, (time.perf_counter() - t0) / 5 * 1e3, "ms")
-for chunk_mb in (4, 8, 12, 16, 25, 50, 100):
-    for ns in (2, 3, 4):
-        r = eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_SPM_LLAMA, chunk_bytes=chunk_mb << 20, n_streams=ns, out_ids=h_ids)
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        for _ in range(5):
-            r = eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_SPM_LLAMA, chunk_bytes=chunk_mb << 20, n_streams=ns, out_ids=h_ids)
-        torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
-        print(f"chunk {chunk_mb:4d} MB streams {ns}: {dt*1e3:7.3f} ms  {len(text)/dt/1e9:6.2f} GB/s  chunks {r.n_chunks}")
+ovs = [bool(int(x)) for x in os.environ.get("SWEEP_OVERLAP", "0,1").split(",")]
+for chunk_mb in [int(x) for x in os.environ.get("SWEEP_CHUNKS", "8,12,16,25,34,50").split(",")]:
+    for ns in [int(x) for x in os.environ.get("SWEEP_SLOTS", "3,8").split(",")]:
+        for ov in ovs:
+            kw = dict(chunk_bytes=chunk_mb << 20, n_streams=ns, out_ids=h_ids, overlap=ov)
+            r = eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_SPM_LLAMA, **kw)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for _ in range(5):
+                r = eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_SPM_LLAMA, **kw)
+            torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
+            print(f"chunk {chunk_mb:4d} MB slots {ns} overlap {int(ov)}: {dt*1e3:7.3f} ms  {len(text)/dt/1e9:6.2f} GB/s  chunks {r.n_chunks}", flush=True)

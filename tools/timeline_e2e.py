@@ -14,12 +14,13 @@ h_text = torch.from_numpy(text.copy()).pin_memory()
 h_ids = torch.empty(len(text) // 2 + 200000, dtype=torch.int32).pin_memory()
 chunk = int(sys.argv[1]) << 20 if len(sys.argv) > 1 else 25 << 20
 ns = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+ov = bool(int(sys.argv[3])) if len(sys.argv) > 3 else True
 for _ in range(3):
-    eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_SPM_LLAMA, chunk_bytes=chunk, n_streams=ns, out_ids=h_ids)
+    eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_SPM_LLAMA, chunk_bytes=chunk, n_streams=ns, out_ids=h_ids, overlap=ov)
 torch.cuda.synchronize()
 eng._trace = []
 t0 = time.perf_counter()
-r = eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_SPM_LLAMA, chunk_bytes=chunk, n_streams=ns, out_ids=h_ids)
+r = eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_SPM_LLAMA, chunk_bytes=chunk, n_streams=ns, out_ids=h_ids, overlap=ov)
 torch.cuda.synchronize()
 print("wall", (time.perf_counter() - t0) * 1e3, "ms")
 start = eng._trace[0][2]
@@ -30,7 +31,7 @@ for name, k, ev, host_t in sorted(eng._trace, key=lambda t: start.elapsed_time(t
 from dptok import engine as eng_mod
 eng._trace = None
 eng_mod.profile_enable(True)
-r = eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_SPM_LLAMA, chunk_bytes=chunk, n_streams=ns, out_ids=h_ids)
+r = eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_SPM_LLAMA, chunk_bytes=chunk, n_streams=ns, out_ids=h_ids, overlap=ov)
 torch.cuda.synchronize()
 eng_mod.profile_enable(False)
 tot = 0.0
