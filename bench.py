@@ -360,6 +360,26 @@ def main():
                "ms_per_step": 1e3 * float(tt.item()) / args.steps, "chunks": r.n_chunks,
                "how": "Engine.encode_corpus_host: 16 MB ranges at document boundaries, copy-in / compute / copy-out streams, one word table for the whole corpus, wall clock"}
 
+        # the same call with compact ids (uint16; this vocabulary has at most 65,536 entries): the host path is bound by
+        # PCIe bytes, so halving the bytes that leave the GPU is what moves it.  Extra information, not the `e2e` line.
+        if max(t2i.values()) <= 0xFFFF:
+            h_ids16 = torch.empty(ids_cap, dtype=torch.uint16).pin_memory()
+            r16 = engine.encode_corpus_host(h_text, doc_offs, RULE, out_ids=h_ids16, ids_dtype=torch.uint16)
+            assert r16.n_ids == n_tokens
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                r16 = engine.encode_corpus_host(h_text, doc_offs, RULE, out_ids=h_ids16, ids_dtype=torch.uint16)
+            barrier()
+            dt16 = time.perf_counter() - t0
+            tt16 = torch.tensor([dt16], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt16, op=dist.ReduceOp.MAX)
+            e2e["compact_u16_ids"] = {"value": g_bytes * args.steps / float(tt16.item()), "unit": UNIT,
+                                      "ms_per_step": 1e3 * float(tt16.item()) / args.steps,
+                                      "d2h_bytes_per_step": int(2 * r16.n_ids + 9 * n_docs + 104 * r16.n_chunks),
+                                      "how": "same call with ids_dtype=torch.uint16 (dpt_narrow_ids_u16 on the device)"}
+
     # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "s2orc_llama2":

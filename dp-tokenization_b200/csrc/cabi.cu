@@ -462,6 +462,15 @@ int dpt_pad_batch(const int32_t* d_ids_a, const int64_t* d_doc_tok_offs_a, const
     return rc ? fail(rc, "dpt_pad_batch: launch failed") : DPT_OK;
 }
 
+int dpt_narrow_ids_u16(const int32_t* d_ids, const int64_t* d_n, int64_t cap, uint16_t* d_out, int64_t* d_overflow,
+                       void* stream) {
+    if (!d_ids || !d_n || !d_out || cap <= 0 || cap >= (1ll << 40)) return fail(DPT_EINVAL, "dpt_narrow_ids_u16: bad argument");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return fail(DPT_ECUDA, "dpt_narrow_ids_u16: no CUDA device");
+    const int rc = dpt::narrow_ids_u16(d_ids, d_n, cap, d_out, d_overflow, (cudaStream_t)stream);
+    return rc ? fail(rc, "dpt_narrow_ids_u16: launch failed") : DPT_OK;
+}
+
 int dpt_roundtrip_check(const dpt_vocab* v, const int32_t* d_ids, const int64_t* d_doc_tok_offs, const uint8_t* d_text,
                         const int64_t* d_doc_offs, int64_t n_docs, int32_t skip_bos, uint8_t* d_ok, void* stream) {
     if (int rc = check_ready(v, "dpt_roundtrip_check")) return rc;

@@ -541,6 +541,47 @@ k_pad_batch(const int32_t* __restrict__ ids_a, const int64_t* __restrict__ offs_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Compact output: int32 ids -> uint16 (vocabularies of at most 65,536 entries).  8 ids per thread: two 16-byte loads,
+// one 16-byte store; the count is read from device memory.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_narrow_u16(const int32_t* __restrict__ ids, const int64_t* __restrict__ d_n, int64_t cap, uint16_t* __restrict__ out,
+             int64_t* __restrict__ overflow) {
+    int64_t n = *d_n;
+    if (n > cap) n = cap;
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i0 >= n) return;
+    uint32_t v[8];
+    const bool vec = i0 + 8 <= n && ((((uintptr_t)ids) & 15u) == 0) && ((((uintptr_t)out) & 15u) == 0);
+    if (vec) {
+        const uint4 a = __ldcs(reinterpret_cast<const uint4*>(ids + i0));
+        const uint4 b = __ldcs(reinterpret_cast<const uint4*>(ids + i0 + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = i0 + k < n ? (uint32_t)ids[i0 + k] : 0u;
+    }
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (v[k] > 0xFFFFu) {
+            v[k] = 0xFFFFu;
+            ++bad;
+        }
+    if (bad && overflow) atomicAdd(reinterpret_cast<unsigned long long*>(overflow), (unsigned long long)bad);
+    if (vec) {
+        uint4 o;
+        o.x = v[0] | (v[1] << 16); o.y = v[2] | (v[3] << 16); o.z = v[4] | (v[5] << 16); o.w = v[6] | (v[7] << 16);
+        __stcs(reinterpret_cast<uint4*>(out + i0), o);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (i0 + k < n) out[i0 + k] = (uint16_t)v[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------------------------
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
@@ -753,6 +794,12 @@ int roundtrip_check(const dpt_vocab* v, const int32_t* d_ids, const int64_t* d_d
                     const int64_t* d_doc_offs, int64_t n_docs, int32_t skip_bos, uint8_t* d_ok, cudaStream_t st) {
     DPT_LAUNCH(k_roundtrip, blocks_for(n_docs, 128), 128, st, v->d_view, d_ids, d_doc_tok_offs, d_text, d_doc_offs, n_docs,
                skip_bos, d_ok);
+    return cudaGetLastError() == cudaSuccess ? DPT_OK : DPT_ECUDA;
+}
+
+int narrow_ids_u16(const int32_t* d_ids, const int64_t* d_n, int64_t cap, uint16_t* d_out, int64_t* d_overflow, cudaStream_t st) {
+    const int64_t threads = (cap + 7) / 8;
+    DPT_LAUNCH(k_narrow_u16, (unsigned)((threads + 255) / 256), 256, st, d_ids, d_n, cap, d_out, d_overflow);
     return cudaGetLastError() == cudaSuccess ? DPT_OK : DPT_ECUDA;
 }
 

@@ -62,6 +62,7 @@ int doc_tok_offsets(const int64_t* d_doc_first_word, int64_t n_docs, const int64
 int roundtrip_check(const dpt_vocab* v, const int32_t* d_ids, const int64_t* d_doc_tok_offs, const uint8_t* d_text,
                     const int64_t* d_doc_offs, int64_t n_docs, int32_t skip_bos, uint8_t* d_ok, cudaStream_t st);
 
+int narrow_ids_u16(const int32_t* d_ids, const int64_t* d_n, int64_t cap, uint16_t* d_out, int64_t* d_overflow, cudaStream_t st);
 int pad_batch(const int32_t* d_ids_a, const int64_t* d_offs_a, const int32_t* d_ids_b, const int64_t* d_offs_b,
               int64_t doc_begin, int64_t n_rows, int64_t row_len, int64_t pad_id, int32_t pad_left, int64_t* d_input_ids,
               int64_t* d_attention_mask, int64_t* d_row_lens, cudaStream_t st);

@@ -71,6 +71,7 @@ SIGNATURES = {
                                             _i64, _i32, _p]),
     "dpt_lattice_word": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _i32, _p, _p, _p]),
     "dpt_roundtrip_check": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _p, _p]),
+    "dpt_narrow_ids_u16": (C.c_int, [_p, _p, _i64, _p, _p, _p]),
     "dpt_pad_batch": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _p, _p, _p, _p]),
     "dpt_last_error": (C.c_char_p, []),
     "dpt_version": (C.c_char_p, []),

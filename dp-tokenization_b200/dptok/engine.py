@@ -167,7 +167,7 @@ class Engine:
     # ---- corpus path from HOST buffers: chunked, H2D / kernels / D2H overlapped ---------------------------------------
     def encode_corpus_host(self, h_text: torch.Tensor, doc_offs: np.ndarray, rule: int, chunk_bytes: int = 16 << 20,
                            n_streams: int = 3, out_ids: Optional[torch.Tensor] = None,
-                           overlap: bool = False) -> "HostResult":
+                           overlap: bool = False, ids_dtype: torch.dtype = torch.int32) -> "HostResult":
         """``h_text``: uint8 HOST tensor (pinned for full speed) of concatenated non-empty documents; ``doc_offs``:
         int64[n_docs+1] numpy array.  The corpus is cut at document boundaries into ranges of about ``chunk_bytes``.
         Range k is copied into its place in ONE device text buffer on the copy-in stream, tokenized by
@@ -179,7 +179,12 @@ class Engine:
         Measured on the B200 box (100 MB corpus, tools/sweep_e2e.py): 3.40-3.50 ms for every chunk size from 16 to 34 MB,
         3 or 8 slots, with or without ``overlap`` (scan / DP / emit of neighbouring ranges on three streams): the path
         is bound by PCIe, whose two directions together move ~57 GB/s on this box (H2D alone 1.81 ms, D2H alone
-        1.69 ms, 100.5 + 95.2 MB in 3.43 ms when both run)."""
+        1.69 ms, 100.5 + 95.2 MB in 3.43 ms when both run).  ``ids_dtype=torch.uint16`` (vocabularies whose ids all fit
+        16 bits: Llama-2 32k, GPT-2 50k) narrows the ids on the device (``dpt_narrow_ids_u16``) so that half as many
+        bytes cross PCIe on the way out; an id that does not fit raises."""
+        if ids_dtype not in (torch.int32, torch.uint16):
+            raise ValueError("ids_dtype must be torch.int32 or torch.uint16")
+        narrow = ids_dtype == torch.uint16
         assert h_text.dtype == torch.uint8 and not h_text.is_cuda
         doc_offs = np.ascontiguousarray(doc_offs, dtype=np.int64)
         n_docs = len(doc_offs) - 1
@@ -197,12 +202,13 @@ class Engine:
         word_cap = max_b // 3 + 2 * max_d + 64
         word_cap_total = n_bytes // 3 + 2 * n_docs + 64
         if out_ids is None:
-            out_ids = torch.empty(n_bytes // 2 + 2 * n_docs + 64, dtype=torch.int32).pin_memory()
+            out_ids = torch.empty(n_bytes // 2 + 2 * n_docs + 64, dtype=ids_dtype).pin_memory()
+        assert out_ids.dtype == ids_dtype
         out_doc_tok = np.zeros(n_docs + 1, dtype=np.int64)
         out_doc_flags = np.zeros(n_docs, dtype=np.uint8)
         totals = np.zeros(4, dtype=np.int64)
         with torch.cuda.device(dev):
-            key = (rule, n_bytes, n_docs, max_b, max_d, n_streams)
+            key = (rule, n_bytes, n_docs, max_b, max_d, n_streams, narrow)
             if getattr(self, "_host_key", None) != key:
                 self._host = None
                 ws_bytes = lib.dpt_encode_corpus_range_workspace(rule, max_b, max_d, word_cap, 0)
@@ -219,13 +225,15 @@ class Engine:
                                 ev_comp=torch.cuda.Event(),
                                 ev_out=torch.cuda.Event(),
                                 ids=torch.empty(ids_cap, dtype=torch.int32, device=dev),
+                                ids16=torch.empty(ids_cap if narrow else 1, dtype=torch.uint16, device=dev),
+                                ovf=torch.zeros(1, dtype=torch.int64, device=dev),
                                 lens=torch.empty(word_cap, dtype=torch.int32, device=dev),
                                 flags=torch.empty(word_cap, dtype=torch.uint8, device=dev),
                                 doc_tok=torch.empty(max_d + 1, dtype=torch.int64, device=dev),
                                 doc_flags=torch.empty(max_d, dtype=torch.uint8, device=dev),
                                 counters=torch.empty(4, dtype=torch.int64, device=dev),
                                 n_out=torch.empty(8, dtype=torch.int64, device=dev),
-                                h_small=torch.empty(12, dtype=torch.int64).pin_memory(),
+                                h_small=torch.zeros(13, dtype=torch.int64).pin_memory(),
                                 h_doc_tok=torch.empty(max_d + 1, dtype=torch.int64).pin_memory(),
                                 h_doc_flags=torch.empty(max_d, dtype=torch.uint8).pin_memory(),
                                 ws=torch.empty(int(ws_bytes), dtype=torch.uint8, device=dev)) for _ in range(n_streams)])
@@ -262,9 +270,12 @@ class Engine:
                     sl["ev_out"].record(s_out)
                     return
                 n_ids = h[0]
+                if narrow and h[12]:
+                    sl["ovf"].zero_()
+                    raise _cabi.DptError(_cabi.EINVAL, f"ids_dtype=uint16: {h[12]} token ids of range {k} do not fit 16 bits")
                 with torch.cuda.stream(s_out):              # the host has seen ev_comp: the ids are complete
                     mark("d2h-begin", k, s_out)
-                    out_ids[ids_base:ids_base + n_ids].copy_(sl["ids"][:n_ids], non_blocking=True)
+                    out_ids[ids_base:ids_base + n_ids].copy_((sl["ids16"] if narrow else sl["ids"])[:n_ids], non_blocking=True)
                     sl["ev_out"].record(s_out)
                     mark("d2h-end", k, s_out)
                 out_doc_tok[lo:hi] = sl["h_doc_tok"][:nd].numpy() + ids_base
@@ -319,6 +330,10 @@ class Engine:
                     if not overlap:
                         mark("comp-begin", k, cs)
                     range_call(sl, k, 4 if overlap else 7, 0 if overlap else (1 if k == 0 else 0), cs)
+                    if narrow:
+                        check(lib.dpt_narrow_ids_u16(_ptr(sl["ids"]), _ptr(sl["n_out"]), ids_cap, _ptr(sl["ids16"]),
+                                                     _ptr(sl["ovf"]), C.c_void_p(cs.cuda_stream)))
+                        sl["h_small"][12:13].copy_(sl["ovf"], non_blocking=True)
                     sl["h_small"][:8].copy_(sl["n_out"], non_blocking=True)
                     sl["h_small"][8:12].copy_(sl["counters"], non_blocking=True)
                     sl["h_doc_tok"][:hi - lo + 1].copy_(sl["doc_tok"][:hi - lo + 1], non_blocking=True)
@@ -338,6 +353,8 @@ class Engine:
                 ids_base = res.n_ids
                 if out_ids.numel() < ids_base:
                     out_ids = torch.empty(ids_base, dtype=torch.int32).pin_memory()
+                if narrow and ids_base and int(res.ids.max().item()) > 0xFFFF:
+                    raise _cabi.DptError(_cabi.EINVAL, "ids_dtype=uint16: token ids do not fit 16 bits")
                 out_ids[:ids_base].copy_(res.ids)
                 out_doc_tok[:] = res.doc_tok_offs.cpu().numpy()
                 out_doc_flags[:] = res.doc_flags.cpu().numpy()

@@ -279,6 +279,16 @@ int dpt_pad_batch(const int32_t* d_ids_a, const int64_t* d_doc_tok_offs_a,
                   int64_t doc_begin, int64_t n_rows, int64_t row_len, int64_t pad_id, int32_t pad_left,
                   int64_t* d_input_ids, int64_t* d_attention_mask, int64_t* d_row_lens, void* stream);
 
+/* ---- compact output: token ids as uint16 for vocabularies of at most 65,536 entries (Llama-2 32k, GPT-2 50k).
+ *      The ids of a corpus leave the GPU over PCIe; at 2 bytes per id the device-to-host copy of the adapters' result
+ *      (the flat List[int] of tokenizer_utils.py:76-80 / :170-174) is half as large.  Narrows the first
+ *      min(*d_n, cap) entries of d_ids into d_out; d_n is a DEVICE pointer (e.g. &n_out[DPT_NOUT_IDS] of an encode
+ *      call enqueued before on the same stream), so no host synchronisation is needed to learn the count.
+ *      Ids that do not fit 16 bits are written as 0xFFFF and counted in *d_overflow (device int64, may be NULL;
+ *      the caller zeroes it). */
+int dpt_narrow_ids_u16(const int32_t* d_ids, const int64_t* d_n, int64_t cap, uint16_t* d_out, int64_t* d_overflow,
+                       void* stream);
+
 const char* dpt_last_error(void);
 const char* dpt_version(void);
 /* number of kernel launches issued by this library in the calling process (bench "gpu_launches") */

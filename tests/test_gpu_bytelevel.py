@@ -148,6 +148,7 @@ def test_host_chunked_path_bytelevel(dev):
     h_text = torch.from_numpy(text.copy()).pin_memory()
     for rep in range(3):
         for chunk, ns in ((1 << 20, 3), (3_000_000, 2), (8 << 20, 4)):
-            hr = eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_LLAMA3, chunk_bytes=chunk, n_streams=ns)
+            hr = eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_LLAMA3, chunk_bytes=chunk, n_streams=ns,
+                                        overlap=bool(rep & 1))
             assert hr.n_ids == res.n_ids and hr.counters.tolist() == ctr
             assert np.array_equal(hr.ids.numpy(), ids) and np.array_equal(hr.doc_tok_offs, dto)

@@ -383,6 +383,31 @@ def test_host_chunked_path_equals_resident_path(dev):
         assert np.array_equal(hr.doc_tok_offs, res.doc_tok_offs.cpu().numpy())
         assert np.array_equal(hr.doc_flags, res.doc_flags.cpu().numpy()) and hr.doc_flags[7] == 1
         assert hr.counters.tolist() == res.counters.cpu().tolist()
+    # the three-stream variant (scan / DP / emit of neighbouring ranges overlapped) and the compact uint16 ids
+    ref_ids = res.ids.cpu().numpy()
+    for rep in range(2):
+        hr = eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_SPM_LLAMA, chunk_bytes=1 << 20, overlap=True)
+        assert np.array_equal(hr.ids.numpy(), ref_ids) and hr.counters.tolist() == res.counters.cpu().tolist()
+        assert np.array_equal(hr.doc_tok_offs, res.doc_tok_offs.cpu().numpy())
+    h16 = eng.encode_corpus_host(h_text, doc_offs, _cabi.RULE_SPM_LLAMA, chunk_bytes=3_500_000, ids_dtype=torch.uint16)
+    assert h16.ids.dtype == torch.uint16 and h16.n_ids == res.n_ids
+    assert np.array_equal(h16.ids.view(torch.int16).numpy().view(np.uint16).astype(np.int32), ref_ids)
+
+
+def test_narrow_ids_u16_overflow_is_reported(dev):
+    """dpt_narrow_ids_u16: ids beyond 16 bits become 0xFFFF and are counted; the count comes from device memory."""
+    import ctypes as C
+    from dptok import _cabi
+    ids = torch.tensor([1, 65535, 65536, 7, 200000, 3, 4, 5, 6, 9, 10], dtype=torch.int32, device=dev)
+    n = torch.tensor([9], dtype=torch.int64, device=dev)
+    out = torch.zeros(16, dtype=torch.uint16, device=dev)
+    ovf = torch.zeros(1, dtype=torch.int64, device=dev)
+    _cabi.check(_cabi.lib.dpt_narrow_ids_u16(C.c_void_p(ids.data_ptr()), C.c_void_p(n.data_ptr()), 11,
+                                             C.c_void_p(out.data_ptr()), C.c_void_p(ovf.data_ptr()),
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    got = out.cpu().view(torch.int16).numpy().view(np.uint16).astype(np.int64).tolist()
+    assert got[:9] == [1, 65535, 65535, 7, 65535, 3, 4, 5, 6] and got[9:] == [0] * 7
+    assert int(ovf.item()) == 2
 
 
 def test_pad_batch_on_device(dev):
