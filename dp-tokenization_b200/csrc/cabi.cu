@@ -399,9 +399,9 @@ int dpt_encode_corpus(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, i
                       int64_t word_cap, int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters,
                       int64_t* d_n_out, void* d_workspace, int64_t workspace_bytes, int32_t worst_case, void* stream) {
     if (int rc = check_ready(v, "dpt_encode_corpus")) return rc;
-    if (rule != DPT_RULE_SPM_LLAMA && rule != DPT_RULE_GPT2 && rule != DPT_RULE_LLAMA3)
-        return fail(DPT_EINVAL, "dpt_encode_corpus: rule not available on device in this build (SPM_LLAMA, GPT2, LLAMA3 "
-                                "are); pre-split on the host and call dpt_encode_words");
+    if (rule != DPT_RULE_SPM_LLAMA && rule != DPT_RULE_GPT2 && rule != DPT_RULE_LLAMA3 && rule != DPT_RULE_BLOOM)
+        return fail(DPT_EINVAL, "dpt_encode_corpus: unknown rule (SPM_LLAMA, GPT2, LLAMA3, BLOOM run on the device; "
+                                "pre-split anything else on the host and call dpt_encode_words)");
     std::string err;
     const int rc = dpt::encode_corpus_pipe(v, rule, d_text, n_bytes, d_doc_offs, n_docs, d_ids, ids_cap, d_word_lens,
                                            d_word_flags, word_cap, d_doc_tok_offs, d_doc_flags, d_counters, d_n_out,
@@ -427,8 +427,8 @@ int dpt_encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_t
                             int64_t workspace_bytes, int32_t worst_case, int32_t phases, void* stream) {
     if (int rc = check_ready(v, "dpt_encode_corpus_range")) return rc;
     if (phases < 0 || phases > 7) return fail(DPT_EINVAL, "dpt_encode_corpus_range: phases must be 0..7");
-    if (rule != DPT_RULE_SPM_LLAMA && rule != DPT_RULE_GPT2 && rule != DPT_RULE_LLAMA3)
-        return fail(DPT_EINVAL, "dpt_encode_corpus_range: rule not available on device in this build");
+    if (rule != DPT_RULE_SPM_LLAMA && rule != DPT_RULE_GPT2 && rule != DPT_RULE_LLAMA3 && rule != DPT_RULE_BLOOM)
+        return fail(DPT_EINVAL, "dpt_encode_corpus_range: unknown rule");
     std::string err;
     const int rc = dpt::encode_corpus_range(v, rule, d_text, n_bytes_total, d_doc_offs, n_docs_total, byte_begin, byte_end,
                                             doc_begin, doc_end, reset_table, n_bytes_total, table_word_cap, d_ids, ids_cap,

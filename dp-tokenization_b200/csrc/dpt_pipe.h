@@ -527,7 +527,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                 // only a document start within the next character can matter here
                 const uint64_t near = (((uint64_t)S.mDS[w] | ((uint64_t)S.mDS[w + 1] << 32)) >> (r & 31)) >> 1;
                 const int dend = (near & 0x1Fu) ? r + 1 + pp_ctz((uint32_t)(near & 0x1Fu)) : r + 8;
-                if (dpt_is_sync_space(U, S.text, r, dend)) sy |= 1u << (r & 31);
+                if (dpt_is_sync_space(P.rule, U, S.text, r, dend)) sy |= 1u << (r & 31);
             }
             S.mSY[w] = sy;
             S.mCF[w] = S.mCS[w] | ds;
@@ -549,7 +549,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                 const int nd = next_ds(own_lo);
                 const int64_t dend = nd < PA_R ? g0 + nd : (int64_t)S.region_doc_end;
                 int64_t q = g0 - 1;
-                while (q > dstart && !dpt_is_sync_space(U, P.text, q, dend)) --q;
+                while (q > dstart && !dpt_is_sync_space(P.rule, U, P.text, q, dend)) --q;
                 S.first_sync_global = q < dstart ? dstart : q;
             }
         }
@@ -588,9 +588,10 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                 }
                 const int64_t stop = limit < dend ? limit : dend;
                 // Inside the region the scanner reads the shared-memory copy of the text (index g -> S.text[g - g0]).
-                // It looks at most one character past the end of a piece, so a piece end more than 4 bytes in front of
-                // the region end was decided on loaded bytes only; closer than that the scan stops and the word stays
-                // open (its end is then found from global memory by the probe loop).
+                // It looks at most two characters past the end of a piece (BLOOM: a space and the character after it),
+                // so a piece end more than 8 bytes in front of the region end was decided on loaded bytes only; closer
+                // than that the scan stops and the word stays open (its end is then found from global memory by the
+                // probe loop).
                 const int64_t rend = g0 + PA_R;
                 const int64_t send = dend < rend ? dend : rend;
                 const uint8_t* tsm = S.text - g0;
@@ -599,7 +600,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                     int64_t pe;
                     if (p >= g0) {
                         pe = dpt_piece_end(P.rule, U, tsm, p, send);
-                        if (send < dend && pe + 4 > rend) {
+                        if (send < dend && pe + 8 > rend) {
                             undecided = true;
                             const int64_t r = p - g0;
                             blk.atomic_or(&S.mWS[r >> 5], 1u << (r & 31));

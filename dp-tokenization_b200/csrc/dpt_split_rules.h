@@ -1,4 +1,4 @@
-// Byte-level split rules (GPT-2, Llama-3), host/device.
+// Byte-level split rules (GPT-2, Llama-3, BLOOM), host/device.
 //
 // The reference obtains its pieces from the tokenizer object: `pre_tokenize_str` (tokenizer_utils.py:157-159) runs
 // the tokenizer's split regex over the text; each piece is then solved by the DP on its own (:165-168).  These
@@ -7,6 +7,10 @@
 //
 //   GPT-2    's|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+
 //   Llama-3  (?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+
+//   BLOOM    Split( ?[^(\s|[.,!?…。，、।۔،])]+, isolated): the bracket expression is ONE negated class (the inner
+//            [...] is a nested class), i.e. "not whitespace and none of ( ) | . , ! ? U+2026 U+3002 U+FF0C U+3001
+//            U+0964 U+06D4 U+060C"; the regex does not cover the text, and `isolated` turns every maximal
+//            uncovered stretch into a piece of its own (probed with tokenizers 0.22.2: "a. .b" -> a | ". ." | b)
 //
 // dpt_piece_end(rule, ...) returns where the piece that starts at p ends.  Code-point classes come from the table
 // generated out of the installed `tokenizers` itself (tools/gen_unicode_tables.py), so \p{L}, \p{N} and \s mean what
@@ -14,9 +18,11 @@
 // probed the same way.  The oracle for these rules is `tokenizers`' pre_tokenize_str (tests).
 //
 // Parallelisation (kernel A): a space followed by a non-whitespace character of the same document is ALWAYS a
-// piece start under both regexes (whitespace alternatives never consume the last whitespace character in front of
-// a non-space; only a piece that starts AT that space can take it as its optional prefix), so those positions and
-// the document starts are synchronisation points: each thread scans the stretch between two consecutive ones.
+// piece start under the GPT-2 and Llama-3 regexes (whitespace alternatives never consume the last whitespace
+// character in front of a non-space; only a piece that starts AT that space can take it as its optional prefix), so
+// those positions and the document starts are synchronisation points: each thread scans the stretch between two
+// consecutive ones.  BLOOM: the same holds for a space followed by a character of the regex's class (a match never
+// runs through a space, and an uncovered stretch ends where the next match begins).
 #pragma once
 #include "dpt_common.h"
 
@@ -167,13 +173,56 @@ DPT_HD int64_t dpt_piece_end_llama3(const DptUniView& U, const uint8_t* text, in
     return dpt_ws_piece_end(U, text, p, end, true);
 }
 
-DPT_HD int64_t dpt_piece_end(int32_t rule, const DptUniView& U, const uint8_t* text, int64_t p, int64_t end) {
-    return rule == 3 /* DPT_RULE_LLAMA3 */ ? dpt_piece_end_llama3(U, text, p, end) : dpt_piece_end_gpt2(U, text, p, end);
+// BLOOM: characters the split regex's class excludes
+DPT_HD bool dpt_bloom_excluded(const DptChar& c) {
+    if (c.cls == DPT_CLS_S) return true;
+    switch (c.cp) {
+        case '(': case ')': case '|': case '.': case ',': case '!': case '?':
+        case 0x2026u: case 0x3002u: case 0xFF0Cu: case 0x3001u: case 0x0964u: case 0x06D4u: case 0x060Cu:
+            return true;
+        default:
+            return false;
+    }
 }
 
-// Is p (doc_start < p < end, text[p] == ' ') a synchronisation point: a space whose next character is a
-// non-whitespace character of the same document?
-DPT_HD bool dpt_is_sync_space(const DptUniView& U, const uint8_t* text, int64_t p, int64_t end) {
+DPT_HD int64_t dpt_piece_end_bloom(const DptUniView& U, const uint8_t* text, int64_t p, int64_t end) {
+    const DptChar c0 = dpt_char_at(U, text, p, end);
+    int64_t e = -1;  // first byte after the first class character of a match that starts at p
+    if (!dpt_bloom_excluded(c0)) {
+        e = p + c0.len;
+    } else if (c0.cp == 0x20u && p + 1 < end) {  // the optional space
+        const DptChar c1 = dpt_char_at(U, text, p + 1, end);
+        if (!dpt_bloom_excluded(c1)) e = p + 1 + c1.len;
+    }
+    if (e >= 0) {  // a match: the run of class characters
+        while (e < end) {
+            const DptChar c = dpt_char_at(U, text, e, end);
+            if (dpt_bloom_excluded(c)) break;
+            e += c.len;
+        }
+        return e;
+    }
+    // no match starts here: the uncovered stretch runs to where the next match begins
+    e = p + c0.len;
+    while (e < end) {
+        const DptChar c = dpt_char_at(U, text, e, end);
+        if (!dpt_bloom_excluded(c)) break;
+        if (c.cp == 0x20u && e + 1 < end && !dpt_bloom_excluded(dpt_char_at(U, text, e + 1, end))) break;
+        e += c.len;
+    }
+    return e;
+}
+
+DPT_HD int64_t dpt_piece_end(int32_t rule, const DptUniView& U, const uint8_t* text, int64_t p, int64_t end) {
+    return rule == 3 /* DPT_RULE_LLAMA3 */  ? dpt_piece_end_llama3(U, text, p, end)
+           : rule == 4 /* DPT_RULE_BLOOM */ ? dpt_piece_end_bloom(U, text, p, end)
+                                            : dpt_piece_end_gpt2(U, text, p, end);
+}
+
+// Is p (doc_start < p < end, text[p] == ' ') a synchronisation point: a space whose next character, in the same
+// document, is a non-whitespace character (GPT-2, Llama-3) / a character of the regex's class (BLOOM)?
+DPT_HD bool dpt_is_sync_space(int32_t rule, const DptUniView& U, const uint8_t* text, int64_t p, int64_t end) {
     if (text[p] != 0x20u || p + 1 >= end) return false;
-    return dpt_char_at(U, text, p + 1, end).cls != DPT_CLS_S;
+    const DptChar c = dpt_char_at(U, text, p + 1, end);
+    return rule == 4 /* DPT_RULE_BLOOM */ ? !dpt_bloom_excluded(c) : c.cls != DPT_CLS_S;
 }

@@ -206,9 +206,13 @@ _LLAMA3_SPLIT = (r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1
                  r"|\s*[\r\n]+|\s+(?!\S)|\s+")
 
 
+_BLOOM_SPLIT = r" ?[^(\s|[.,!?…。，、।۔،])]+"
+
+
 def _device_split_rule(tokenizer):
     """DPT_RULE_* of the tokenizer's pre-tokenizer if the device implements exactly that split (GPT-2 ByteLevel regex,
-    Llama-3 Split regex + ByteLevel) and nothing rewrites the text before it; None -> pre_tokenize_str on the host."""
+    Llama-3 or BLOOM Split regex + ByteLevel) and nothing rewrites the text before it; None -> pre_tokenize_str on the
+    host."""
     try:
         backend = getattr(tokenizer, "backend_tokenizer", None) or tokenizer._tokenizer
         spec = json.loads(backend.to_str())
@@ -227,9 +231,12 @@ def _device_split_rule(tokenizer):
     if pt.get("type") == "Sequence":
         steps = pt.get("pretokenizers", [])
         if (len(steps) == 2 and steps[0].get("type") == "Split" and steps[0].get("behavior") == "Isolated" and
-                not steps[0].get("invert", False) and steps[0].get("pattern", {}).get("Regex") == _LLAMA3_SPLIT and
-                is_bytelevel(steps[1], False)):
-            return _cabi.RULE_LLAMA3
+                not steps[0].get("invert", False) and is_bytelevel(steps[1], False)):
+            rx = steps[0].get("pattern", {}).get("Regex")
+            if rx == _LLAMA3_SPLIT:
+                return _cabi.RULE_LLAMA3
+            if rx == _BLOOM_SPLIT:
+                return _cabi.RULE_BLOOM
     return None
 
 

@@ -1,4 +1,4 @@
-"""GPU parity of the byte-level split rules (GPT-2, Llama-3) running inside the corpus pipeline, through the C ABI:
+"""GPU parity of the byte-level split rules (GPT-2, Llama-3, BLOOM) running inside the corpus pipeline, through the C ABI:
 pieces must equal the installed `tokenizers` pre-tokenizer's (tokenizer_utils.py:157-159), ids/lengths the oracle's."""
 import random
 
@@ -58,7 +58,8 @@ def _check(eng, tok, vb, rule, docs, dev):
     return res
 
 
-@pytest.mark.parametrize("name,rule_name", [("gpt2_50k", "RULE_GPT2"), ("llama3_128k", "RULE_LLAMA3")])
+@pytest.mark.parametrize("name,rule_name", [("gpt2_50k", "RULE_GPT2"), ("llama3_128k", "RULE_LLAMA3"),
+                                            ("bloom_8k", "RULE_BLOOM")])
 def test_device_split_rules_vs_tokenizers(dev, name, rule_name):
     """configs[2]/[3]-shaped input: en/de sentence pairs (GPT-2 50k) and long mixed documents incl. Arabic with
     diacritics (Llama-3 128k), plus a soup of contractions, digit runs, newline runs, tabs, multi-byte whitespace and
@@ -77,11 +78,13 @@ def test_device_split_rules_vs_tokenizers(dev, name, rule_name):
     soup = ["Hello", " ", "  ", "world", "'s", "'S", "'re", "'LL", "'", "''", "12345", "3", "٣٤", "é", "naïve", "日本",
             "\n", "\n\n", "\t", "\r\n", ".", ",", "!!", "(x)", "—", "…", " ", "　", "ſ", "'ſ", "x", "İ", "ǅ",
             "قُدَّام", "البيت", "%", "a1b2", " ", "+=", "'t", "'d", "'m", "'ve", "'VE"]
+    soup += ["(", ")", "|", "?", "!", "[w]", "。", "，", "、", "।", "۔", "،", "؟", ". .", " .", " (", "a)b"]
     for trial in range(6):
         docs = ["".join(rng.choice(soup) for _ in range(rng.randint(1, 80))).encode()
                 for _ in range(rng.choice([1, 50, 3000]))]
         _check(eng, tok, vb, rule, docs, dev)
-    big = [("x" * 20000 + " y").encode(), ("7" * 9000 + "a").encode(), (" " * 6000 + "z\n" * 3000).encode()]
+    big = [("x" * 20000 + " y").encode(), ("7" * 9000 + "a").encode(), (" " * 6000 + "z\n" * 3000).encode(),
+           ("." * 5000 + " " + "," * 4200 + " q").encode(), ("\u3002" * 1500 + " \u3000" * 700 + "w").encode()]
     _check(eng, tok, vb, rule, big, dev)
 
 
@@ -90,7 +93,7 @@ def test_bytelevel_adapter_batch_uses_device_rule(dev):
     equals the per-string path that pre-tokenizes on the host like the reference (tokenizer_utils.py:161-174)."""
     from dptok import _cabi, assets, synth
     from packages.tokenizer_utils import dp_tokenize_bloom
-    for name, rule in (("gpt2_3k", _cabi.RULE_GPT2), ("llama3_128k", _cabi.RULE_LLAMA3), ("bloom_8k", None)):
+    for name, rule in (("gpt2_3k", _cabi.RULE_GPT2), ("llama3_128k", _cabi.RULE_LLAMA3), ("bloom_8k", _cabi.RULE_BLOOM)):
         tok = assets.load_hf(name)
         enc, dec = dp_tokenize_bloom(tok, None)
         assert enc.device_rule == rule

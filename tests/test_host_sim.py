@@ -354,7 +354,7 @@ def _check_bytelevel(host_sim, h, tok, vb, rule, docs, **kw):
 
 
 def test_pipeline_code_bytelevel_rules(host_sim):
-    """GPT-2 and Llama-3 split regexes as the device scanner: English/German sentence pairs, Arabic with combining
+    """GPT-2, Llama-3 and BLOOM split regexes as the device scanner: English/German sentence pairs, Arabic with combining
     marks, contractions (incl. case-insensitive and U+017F), digit groups, newline runs, tabs, ideographic space,
     multi-byte digits, document boundaries every few bytes."""
     from dptok import assets, synth
@@ -362,7 +362,8 @@ def test_pipeline_code_bytelevel_rules(host_sim):
     soup = ["Hello", " ", "  ", "world", "'s", "'S", "'re", "'LL", "'", "''", "12345", "3", "٣٤", "é", "naïve", "日本",
             "\n", "\n\n", "\t", "\r\n", ".", ",", "!!", "(x)", "—", "…", " ", "　", "ſ", "'ſ", "x", "İ", "ǅ",
             "قُدَّام", "البيت", "%", "a1b2", " ", "+=", "'t", "'d", "'m", "'ve", "'VE"]
-    for name, rule in (("gpt2_3k", 2), ("llama3_128k", 3)):
+    soup += ["(", ")", "|", "?", "!", "[w]", "。", "，", "、", "।", "۔", "،", "؟", ". .", " .", " (", "a)b"]
+    for name, rule in (("gpt2_3k", 2), ("llama3_128k", 3), ("bloom_8k", 4)):
         tok = assets.load_tokenizer(name)
         v2i = {t: k for k, t in enumerate(assets.load_spec(name)["model"]["vocab"])}
         vb = vocab_bytes(v2i, "bytelevel")
@@ -379,6 +380,7 @@ def test_pipeline_code_bytelevel_rules(host_sim):
             _check_bytelevel(host_sim, h, tok, vb, rule, docs, nthreads=rng.choice([1, 3, 8]), n_slots=rng.choice([0, 64]),
                              n_ranges=rng.choice([1, 1, 3]))
         # pieces far longer than a tile / its look-behind: one 20 KB letter run, 9 KB of digits, 6 KB of spaces
-        big = [("x" * 20000 + " y").encode(), ("7" * 9000 + "a").encode(), (" " * 6000 + "z\n" * 3000).encode()]
+        big = [("x" * 20000 + " y").encode(), ("7" * 9000 + "a").encode(), (" " * 6000 + "z\n" * 3000).encode(),
+               ("." * 5000 + " " + "," * 4200 + " q").encode(), ("\u3002" * 1500 + " \u3000" * 700 + "w").encode()]
         _check_bytelevel(host_sim, h, tok, vb, rule, big, nthreads=4)
         host_sim.sim_vocab_destroy(ctypes.c_void_p(h))
