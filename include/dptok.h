@@ -61,7 +61,7 @@ enum dpt_unit_mode { DPT_UNIT_BYTES = 0, DPT_UNIT_CODEPOINTS = 1 };
  *               a word starts at every U+2581 (tokenizer_utils.py:12-17,24-31)
  *   GPT2      - ByteLevel(use_regex=True) split
  *   LLAMA3    - Llama-3 split regex
- *   BLOOM     - BLOOM split regex ' ?[^(\\s|[.,!?...])]+' + isolated gaps
+ *   BLOOM     - BLOOM split regex ' ?[^(\s|[.,!?...])]+' + isolated gaps
  *               (the pre-tokenizer tokenizer_utils.py:157-159 was written for)    */
 enum dpt_rule {
     DPT_RULE_PRESPLIT = 0,
