@@ -838,7 +838,9 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
         for (uint32_t i = tid; i < npend; i += nt) {
             const uint32_t v = S.pend[i], cls = v >> 29;
             const uint32_t r = blk.atomic_add_ret(&S.cur_c[cls], 1u);
-            P.pending[(size_t)cls * (size_t)P.pend_stride + S.base_c[cls] + r] = v & REF_INDEX;
+            // (a queue only overflows when the corpus holds more words than word_cap: reported, the caller retries)
+            if ((int64_t)(S.base_c[cls] + r) < P.pend_stride)
+                P.pending[(size_t)cls * (size_t)P.pend_stride + S.base_c[cls] + r] = v & REF_INDEX;
         }
         blk.sync();
         if (tid == 0) {
@@ -939,6 +941,11 @@ DPT_PIPE_FN int32_t pb_normalise(const PipeParams& P, int64_t p, int64_t e_end, 
     return n;
 }
 
+// entries of length class c that kernel A could store (see the enqueue at the end of pa_run_tile)
+DPT_PIPE_FN uint32_t pb_queue_len(const PipeParams& P, int c) {
+    const uint32_t n = P.ctl->n_pending[c];
+    return (int64_t)n < P.pend_stride ? n : (uint32_t)P.pend_stride;
+}
 // item i of the DP work list: i < n_pending -> table slot pending[i]; else odd word i - n_pending
 struct PbItem {
     int64_t pos, end;
@@ -1007,7 +1014,7 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
     uint32_t npc[PB_CLASSES];
     uint64_t total = 0;
     for (int c = 0; c < PB_CLASSES; ++c) {
-        npc[c] = P.ctl->n_pending[c];
+        npc[c] = pb_queue_len(P, c);
         total += npc[c];
     }
     const uint32_t n_odd = P.ctl->n_odd < (uint32_t)P.odd_cap ? P.ctl->n_odd : (uint32_t)P.odd_cap;
@@ -1082,7 +1089,7 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
 template <class Blk>
 DPT_PIPE_FN void pb_long_thread(Blk& blk, const PipeParams& P, int64_t gtid, int64_t gthreads) {
     uint32_t npc[PB_CLASSES];
-    for (int c = 0; c < PB_CLASSES; ++c) npc[c] = P.ctl->n_pending[c];
+    for (int c = 0; c < PB_CLASSES; ++c) npc[c] = pb_queue_len(P, c);
     const uint32_t n_odd = P.ctl->n_odd < (uint32_t)P.odd_cap ? P.ctl->n_odd : (uint32_t)P.odd_cap;
     const uint32_t n_long = P.ctl->n_long;
     for (uint64_t k = (uint64_t)gtid; k < n_long; k += (uint64_t)gthreads) {

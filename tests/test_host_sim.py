@@ -138,14 +138,15 @@ def test_spm_rule_matches_reference_pretokenizer(host_sim):
 # by a std::thread emulation of CUDA blocks, against (a) the general path's rule + the C oracle and (b) the
 # reference-shaped normaliser.
 # ------------------------------------------------------------------------------------------------
-def _run_fused(host_sim, h, spm, docs, nthreads=4, n_slots=0, ids_cap=None, odd_cap=0, pool_cap=0, lp_cap=0, n_ranges=1):
+def _run_fused(host_sim, h, spm, docs, nthreads=4, n_slots=0, ids_cap=None, odd_cap=0, pool_cap=0, lp_cap=0, n_ranges=1,
+               word_cap=None):
     raw = b"".join(docs)
     text = np.frombuffer(raw + b"\0" * 64, np.uint8).copy()
     offs = np.zeros(len(docs) + 1, np.int64)
     offs[1:] = np.cumsum([len(d) for d in docs])
     n = len(raw)
     cap = 3 * n + 3 * len(docs) + 16 if ids_cap is None else ids_cap
-    wcap = n + 2 * len(docs) + 16
+    wcap = n + 2 * len(docs) + 16 if word_cap is None else word_cap
     ids = np.full(cap, -7, np.int32)
     wl = np.full(wcap, -7, np.int32)
     wf = np.full(wcap, 99, np.uint8)
@@ -156,7 +157,8 @@ def _run_fused(host_sim, h, spm, docs, nthreads=4, n_slots=0, ids_cap=None, odd_
     host_sim.sim_encode_corpus_pipe(h, spm, text.ctypes.data, n, offs.ctypes.data, len(docs), ids.ctypes.data, cap,
                                     wl.ctypes.data, wf.ctypes.data, wcap, dto.ctypes.data, dfl.ctypes.data,
                                     ctr.ctypes.data, nout.ctypes.data, nthreads, n_slots, odd_cap, pool_cap, lp_cap, n_ranges)
-    return dict(ids=ids[:min(nout[0], cap)], wl=wl[:nout[1]], wf=wf[:nout[1]], dto=dto, dfl=dfl, ctr=ctr, nout=nout)
+    return dict(ids=ids[:min(nout[0], cap)], wl=wl[:min(nout[1], wcap)], wf=wf[:min(nout[1], wcap)], dto=dto, dfl=dfl, ctr=ctr,
+                nout=nout)
 
 
 def _general_expected(host_sim, h, vb, docs):
@@ -236,6 +238,10 @@ def test_pipeline_code_s2orc_shaped_text(host_sim):
     # capacities of the internal lists are reported, never silently exceeded
     r4 = _run_fused(host_sim, h, 1, docs, nthreads=4, n_slots=256, odd_cap=100, pool_cap=10, lp_cap=50)
     assert r4["nout"][6] > r4["nout"][7]
+    # word_cap far below the word count (and below the number of distinct words, so the DP queues fill up): the
+    # requirement is reported, nothing is written beyond a capacity, the words that fit are right
+    r5 = _run_fused(host_sim, h, 1, docs, nthreads=4, word_cap=700)
+    assert r5["nout"][1] == len(r["wl"]) and np.array_equal(r5["wl"], r["wl"][:700])
     # capacity: ids beyond ids_cap are dropped, the requirement is still reported
     r3 = _run_fused(host_sim, h, 1, docs, nthreads=4, ids_cap=1000)
     assert r3["nout"][0] == len(r["ids"]) and np.array_equal(r3["ids"], r["ids"][:1000])
