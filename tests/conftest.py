@@ -46,9 +46,12 @@ def host_sim():
     out = os.path.join(out_dir, "libsim.so")
     srcs = [os.path.join(ROOT, "tests", "host_sim", "sim.cpp"), os.path.join(PKG, "csrc", "vocab.cpp")]
     deps = srcs + [os.path.join(PKG, "csrc", h) for h in os.listdir(os.path.join(PKG, "csrc")) if h.endswith(".h")]
-    if not os.path.isfile(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+    extra = os.environ.get("DPT_SIM_EXTRA", "").split()  # development: the kernels' tuning macros (-DDPT_PA_T=...)
+    if extra:
+        out = os.path.join(out_dir, "libsim_variant.so")
+    if extra or not os.path.isfile(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", "-I", os.path.join(PKG, "csrc"),
-                               "-o", out] + srcs)
+                               "-o", out] + extra + srcs)
     lib = C.CDLL(out)
     lib.sim_vocab_create.restype = C.c_void_p
     lib.sim_vocab_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
