@@ -852,6 +852,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
         if (lo < ne) blk.sync();
     } while (lo < ne);
     if (tid == 0 && tile == P.n_tiles - 1) P.ctl->n_words = (unsigned long long)((int64_t)S.base_w + ne);
+    if (tid == 0 && tile == 0) P.counters[3] = 0;  // untokenizable words: kernel C adds to it tile by tile
     blk.sync();
 }
 
@@ -1178,6 +1179,25 @@ DPT_PIPE_FN uint32_t pc_meta(const PipeParams& P, uint32_t ref) {
 #endif
 }
 
+// Final counters and the capacity report, written by thread 0 of kernel C's LAST tile, which knows the grand total of
+// tokens from its own look-back.  Everything else here was final before kernel C started; counters[3] (untokenizable
+// words) is zeroed by kernel A and added to by every tile of kernel C.
+DPT_PIPE_FN void pd_finish(const PipeParams& P, unsigned long long tot) {
+    const int64_t n_words_true = (int64_t)P.ctl->n_words;
+    P.counters[0] = (unsigned long long)(P.byte_end - P.byte_begin);
+    P.counters[1] = (unsigned long long)n_words_true;
+    P.counters[2] = tot;
+    P.n_out[0] = (int64_t)tot;             // DPT_NOUT_IDS
+    P.n_out[1] = n_words_true;             // DPT_NOUT_WORDS
+    P.n_out[2] = (int64_t)P.ctl->lp_used;  // DPT_NOUT_POOL_REQ  (long-word scratch positions)
+    P.n_out[3] = P.lp_cap;                 // DPT_NOUT_POOL_CAP
+    P.n_out[4] = (int64_t)P.persist->pool_used;  // ids pool required
+    P.n_out[5] = P.pool_cap;
+    P.n_out[6] = (int64_t)P.ctl->n_odd;    // odd words required
+    P.n_out[7] = P.odd_cap;
+    P.doc_tok_offs[P.n_docs_local] = (int64_t)tot;
+}
+
 template <class Blk>
 DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int tile) {
     const int tid = blk.tid();
@@ -1308,7 +1328,10 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
         }
     }
     if (tid == 0) {
-        if (S.n_untok) blk.atomic_add_u64_ret(&P.ctl->n_untok, (unsigned long long)S.n_untok);
+        if (S.n_untok) blk.atomic_add_u64_ret(&P.counters[3], (unsigned long long)S.n_untok);
+        // the last tile knows the grand total from its own look-back: it writes the counters and the capacity report
+        // (everything else in them was final before this kernel started)
+        if ((int64_t)(tile + 1) * PC_TILE >= n_words) pd_finish(P, (unsigned long long)S.base_t + total);
     }
     blk.sync();
 }
@@ -1319,6 +1342,7 @@ DPT_PIPE_FN void pc_kernel(Blk& blk, const PipeParams& P, CSmem& S) {
         const int tile = blk.block_index();
         const int64_t n_words = (int64_t)P.ctl->n_words < P.word_cap ? (int64_t)P.ctl->n_words : P.word_cap;
         if (tile < P.n_ctiles && (int64_t)tile * PC_TILE < n_words) pc_run_tile(blk, P, S, tile);
+        else if (tile == 0 && blk.tid() == 0) pd_finish(P, 0ull);  // no words (cannot happen: documents are non-empty)
         return;
     }
     for (;;) {
@@ -1326,31 +1350,13 @@ DPT_PIPE_FN void pc_kernel(Blk& blk, const PipeParams& P, CSmem& S) {
         blk.sync();
         const int tile = S.tile;
         const int64_t n_words = (int64_t)P.ctl->n_words < P.word_cap ? (int64_t)P.ctl->n_words : P.word_cap;
-        if (tile >= P.n_ctiles || (int64_t)tile * PC_TILE >= n_words) break;
+        if (tile >= P.n_ctiles || (int64_t)tile * PC_TILE >= n_words) {
+            if (tile == 0 && blk.tid() == 0) pd_finish(P, 0ull);
+            break;
+        }
         pc_run_tile(blk, P, S, tile);
         if (!blk.persistent()) break;
     }
-}
-
-// final counters, written by one thread after kernel C (stream order)
-DPT_PIPE_FN void pd_finish(const PipeParams& P) {
-    const int64_t n_words_true = (int64_t)P.ctl->n_words;
-    const int64_t n_words = n_words_true < P.word_cap ? n_words_true : P.word_cap;
-    const int64_t n_ctiles = (n_words + PC_TILE - 1) / PC_TILE;
-    const unsigned long long tot = n_ctiles > 0 ? (P.desc_t[n_ctiles - 1] & PD_MASK) : 0ull;
-    P.counters[0] = (unsigned long long)(P.byte_end - P.byte_begin);
-    P.counters[1] = (unsigned long long)n_words_true;
-    P.counters[2] = tot;
-    P.counters[3] = P.ctl->n_untok;
-    P.n_out[0] = (int64_t)tot;             // DPT_NOUT_IDS
-    P.n_out[1] = n_words_true;             // DPT_NOUT_WORDS
-    P.n_out[2] = (int64_t)P.ctl->lp_used;  // DPT_NOUT_POOL_REQ  (long-word scratch positions)
-    P.n_out[3] = P.lp_cap;                 // DPT_NOUT_POOL_CAP
-    P.n_out[4] = (int64_t)P.persist->pool_used;  // ids pool required
-    P.n_out[5] = P.pool_cap;
-    P.n_out[6] = (int64_t)P.ctl->n_odd;    // odd words required
-    P.n_out[7] = P.odd_cap;
-    P.doc_tok_offs[P.n_docs_local] = (int64_t)tot;
 }
 
 }  // namespace dpt

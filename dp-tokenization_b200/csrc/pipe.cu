@@ -49,6 +49,7 @@ struct DevBlk {
         return atomicAdd(p, v);
     }
     __device__ __forceinline__ unsigned long long load_relaxed(const unsigned long long* p) const { return ld_relaxed_gpu(p); }
+    __device__ __forceinline__ void fence() const { __threadfence(); }
     __device__ __forceinline__ unsigned long long cas_u64(unsigned long long* p, unsigned long long expect,
                                                           unsigned long long desired) const {
         return atomicCAS(p, expect, desired);
@@ -202,8 +203,22 @@ __global__ void __launch_bounds__(PC_THREADS, DPT_PC_CTAS) k_emit(const __grid_c
     pc_kernel(blk, P, S);
 }
 
-__global__ void k_pipe_finish(const __grid_constant__ PipeParams P) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) pd_finish(P);
+// Everything a launch sequence needs zeroed, in ONE launch (three cudaMemsetAsync calls before: each is a launch of its
+// own with its own gap on the stream): up to three 16-byte-aligned regions, sizes in 16-byte units.
+struct ClearJob {
+    uint4* p[2];
+    unsigned long long n16[2];
+    uint8_t* bytes;  // a region of any alignment and size (the caller's doc_flags)
+    unsigned long long n_bytes;
+};
+__global__ void __launch_bounds__(256) k_pipe_clear(const ClearJob J) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+        for (unsigned long long i = t; i < J.n16[r]; i += stride) J.p[r][i] = z;
+    for (unsigned long long i = t; i < J.n_bytes; i += stride) J.bytes[i] = 0;
 }
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -309,6 +324,7 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
         if (sm_count <= 0) sm_count = 148;
     }
+    ClearJob clear{};
     PipeParams P{};
     P.V = v->d_view;
     P.text = d_text;
@@ -344,7 +360,10 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
         P.pool = (int32_t*)take(tz.pool_cap * 4);
         P.pool_cap = tz.pool_cap;
         P.slot_mask = (uint32_t)(tz.n_slots - 1);
-        if (reset_table) cudaMemsetAsync(base, 0, (size_t)zero_bytes, st);
+        if (reset_table) {
+            clear.p[0] = (uint4*)base;
+            clear.n16[0] = (unsigned long long)((zero_bytes + 15) / 16);  // (the region ends on a 256-byte boundary)
+        }
     }
     const bool do_scan = (phases & 1) != 0, do_dp = (phases & 2) != 0, do_emit = (phases & 4) != 0;
     {   // range part: everything that must start zeroed is contiguous
@@ -373,7 +392,10 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
         P.lp_b = (uint16_t*)take(z.lp_cap * 2);
         P.odd_cap = z.odd_cap;
         P.lp_cap = z.lp_cap;
-        if (do_scan) cudaMemsetAsync(base, 0, (size_t)zero_bytes, st);
+        if (do_scan) {
+            clear.p[1] = (uint4*)base;
+            clear.n16[1] = (unsigned long long)((zero_bytes + 15) / 16);  // (up to 8 bytes of the padding in front of refs)
+        }
     }
     P.tile_first = (int32_t)(byte_begin / PA_T);
     P.n_tiles = (int32_t)((byte_end + PA_T - 1) / PA_T - byte_begin / PA_T);
@@ -381,8 +403,22 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
     P.spm = rule == DPT_RULE_SPM_LLAMA ? 1 : 0;
     P.rule = rule;
     P.vec_ok = ((((uintptr_t)d_word_lens) & 15u) == 0 && (((uintptr_t)d_word_flags) & 7u) == 0) ? 1 : 0;
+    if (do_scan && d_doc_flags) {
+        clear.bytes = d_doc_flags;
+        clear.n_bytes = (unsigned long long)range_docs;
+    }
+    if (clear.n16[0] || clear.n16[1] || clear.n_bytes) {
+        if (((uintptr_t)clear.p[0] | (uintptr_t)clear.p[1]) & 15u) {  // a workspace that is not 16-byte aligned
+            if (clear.n16[0]) cudaMemsetAsync(clear.p[0], 0, (size_t)clear.n16[0] * 16, st);
+            if (clear.n16[1]) cudaMemsetAsync(clear.p[1], 0, (size_t)clear.n16[1] * 16, st);
+            if (clear.n_bytes) cudaMemsetAsync(clear.bytes, 0, (size_t)clear.n_bytes, st);
+        } else {
+            ProfScope prof("k_pipe_clear", st);
+            k_pipe_clear<<<(unsigned)(sm_count * 8), 256, 0, st>>>(clear);
+            ++g_launches;
+        }
+    }
     if (do_scan) {
-    if (d_doc_flags) cudaMemsetAsync(d_doc_flags, 0, (size_t)range_docs, st);
     {
         ProfScope prof(P.spm ? "k_scan_dedup" : "k_scan_dedup_bl", st);
         if (P.spm)
@@ -413,11 +449,6 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
     {
         ProfScope prof("k_emit", st);
         k_emit<<<(unsigned)z.n_ctiles, PC_THREADS, 0, st>>>(P);
-        ++g_launches;
-    }
-    {
-        ProfScope prof("k_pipe_finish", st);
-        k_pipe_finish<<<1, 32, 0, st>>>(P);
         ++g_launches;
     }
     }

@@ -37,6 +37,7 @@ struct HostBlk {
         return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
     }
     unsigned long long load_relaxed(const unsigned long long* p) const { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+    void fence() const { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
     unsigned long long cas_u64(unsigned long long* p, unsigned long long expect, unsigned long long desired) const {
         __atomic_compare_exchange_n(p, &expect, desired, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
         return expect;  // old value, like atomicCAS
@@ -287,7 +288,7 @@ int32_t sim_encode_corpus_pipe(void* vv, int32_t rule, const uint8_t* text, int6
                 });
             for (auto& x : th) x.join();
         }
-        pd_finish(P);
+        // (the counters and the capacity report were written by the thread that finished kernel C's last tile)
         // stitch
         const int64_t nid = r_nout[0] < r_ids_cap ? r_nout[0] : r_ids_cap, nw = r_nout[1] < r_word_cap ? r_nout[1] : r_word_cap;
         for (int64_t k = 0; k < nid; ++k) ids[ids_base + k] = r_ids[k];
