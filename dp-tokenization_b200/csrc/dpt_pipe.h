@@ -172,6 +172,7 @@ struct ASmemT {
     uint32_t mWS[PA_NW + 2];  // word starts
     uint32_t mCX[PA_NW + 2];  // positions that make their word "odd" (solved from the raw text, not deduplicated)
     uint32_t mSY[PA_NW + 2];  // byte-level rules: synchronisation points of the split scanner
+    uint32_t mAL[kSpm ? 2 : PA_NW + 2];  // byte-level rules: ASCII letters (the split scanner skips over their runs)
     uint32_t cnt[PA_NW + 2];
     uint32_t dsn[PA_NW + 2];  // byte-level rules: document starts in front of each mask word
     uint16_t wlist[WL_CAP];   // region index of the words of the current window (| 0x8000: a document's '<s>' word)
@@ -344,6 +345,33 @@ DPT_HD uint32_t pp_eq4(uint32_t x, uint32_t c4) {
     t = ~(t | z | 0x7F7F7F7Fu);                 // 0x80 in every byte of z that is zero
     return ((t >> 7) * 0x01020408u) >> 24;      // gather the four flag bits
 }
+// 4-bit mask of the bytes of x that are ASCII letters (same test as dpt_char_at: ((b | 0x20) - 'a') < 26, b < 0x80)
+DPT_HD uint32_t pp_letters4(uint32_t x) {
+    const uint32_t y = (x | 0x20202020u) & 0x7F7F7F7Fu;
+    const uint32_t ge = y + 0x1F1F1F1Fu;  // bit 7 of a byte: y >= 'a'
+    const uint32_t gt = y + 0x05050505u;  // bit 7 of a byte: y > 'z'
+    const uint32_t t = ge & ~gt & ~x & 0x80808080u;
+    return ((t >> 7) * 0x01020408u) >> 24;
+}
+// the split scanners' accelerator (dpt_split_rules.h: DptNoSkip) over a tile's ASCII-letter mask; region index = p - g0
+struct PaLetterSkip {
+    const uint32_t* mask;
+    int64_t g0;
+    DPT_HD int64_t ascii_letters(int64_t p, int64_t end) const {
+        int64_t r = p - g0;
+        if (r < 0) return p;  // in front of the region: the scanner reads global memory character by character
+        while (p < end) {
+            const int sh = (int)(r & 31), avail = 32 - sh;
+            const uint32_t inv = ~(mask[r >> 5] >> sh);  // the bits shifted in from the top read as "not a letter"
+            int n = inv ? pp_ctz(inv) : 32;
+            if (n > avail) n = avail;
+            p += n;
+            r += n;
+            if (n < avail) break;
+        }
+        return p < end ? p : end;
+    }
+};
 // length class of a word body: lanes of a warp of kernel B get words of one class, i.e. of similar DP cost
 DPT_HD int pp_len_class(int len) {
     return len <= 6 ? 0 : len <= 10 ? 1 : len <= 16 ? 2 : 3;
@@ -477,6 +505,9 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
         reinterpret_cast<uint16_t*>(S.mCS)[hw] = (uint16_t)cs;
         reinterpret_cast<uint16_t*>(S.mSP)[hw] = (uint16_t)sp;
         reinterpret_cast<uint16_t*>(S.mM3)[hw] = (uint16_t)(spm ? m3 : 0u);
+        if (!spm)
+            reinterpret_cast<uint16_t*>(S.mAL)[hw] = (uint16_t)(pp_letters4(x.x) | (pp_letters4(x.y) << 4) |
+                                                                (pp_letters4(x.z) << 8) | (pp_letters4(x.w) << 12));
     }
     blk.sync();
 
@@ -600,7 +631,11 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                 while (p < stop) {
                     int64_t pe;
                     if (p >= g0) {
+#if defined(DPT_NO_LETTER_SKIP)  // tuning variant: the scanner walks letter runs character by character
                         pe = dpt_piece_end(P.rule, U, tsm, p, send);
+#else
+                        pe = dpt_piece_end(P.rule, U, tsm, p, send, PaLetterSkip{S.mAL, g0});
+#endif
                         if (send < dend && pe + 8 > rend) {
                             undecided = true;
                             const int64_t r = p - g0;

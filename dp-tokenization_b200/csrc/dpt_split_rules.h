@@ -80,8 +80,17 @@ DPT_HD DptChar dpt_char_at(const DptUniView& U, const uint8_t* text, int64_t p, 
     return c;
 }
 
+// Optional accelerator of the scanners: ascii_letters(p, end) returns the end of the run of ASCII letters that starts
+// at p (p itself if there is none), never beyond `end`.  Kernel A answers it from a one-bit-per-byte mask of its tile
+// (dpt_pipe.h: PaLetterSkip); the default does nothing and the scanner walks the run character by character.
+struct DptNoSkip {
+    DPT_HD int64_t ascii_letters(int64_t p, int64_t) const { return p; }
+};
+
 // end of the maximal run of characters of class `cls` starting at p
-DPT_HD int64_t dpt_run_end(const DptUniView& U, const uint8_t* text, int64_t p, int64_t end, uint32_t cls) {
+template <class Skip>
+DPT_HD int64_t dpt_run_end(const DptUniView& U, const uint8_t* text, int64_t p, int64_t end, uint32_t cls, const Skip& skip) {
+    if (cls == DPT_CLS_L) p = skip.ascii_letters(p, end);  // (an ASCII letter is always a character of class L on its own)
     while (p < end) {
         const DptChar c = dpt_char_at(U, text, p, end);
         if (c.cls != cls) break;
@@ -108,7 +117,8 @@ DPT_HD int64_t dpt_ws_piece_end(const DptUniView& U, const uint8_t* text, int64_
     return last > p ? last : e;
 }
 
-DPT_HD int64_t dpt_piece_end_gpt2(const DptUniView& U, const uint8_t* text, int64_t p, int64_t end) {
+template <class Skip>
+DPT_HD int64_t dpt_piece_end_gpt2(const DptUniView& U, const uint8_t* text, int64_t p, int64_t end, const Skip& skip) {
     const uint32_t c0 = text[p];
     if (c0 == '\'' && p + 1 < end) {  // 's|'t|'re|'ve|'m|'ll|'d  (case-sensitive)
         const uint32_t c1 = text[p + 1];
@@ -121,13 +131,14 @@ DPT_HD int64_t dpt_piece_end_gpt2(const DptUniView& U, const uint8_t* text, int6
     int64_t q = p;
     if (c0 == 0x20u && p + 1 < end) q = p + 1;  // the optional space of  ' ?X+'
     const DptChar c = dpt_char_at(U, text, q, end);
-    if (c.cls != DPT_CLS_S) return dpt_run_end(U, text, q + c.len, end, c.cls);
+    if (c.cls != DPT_CLS_S) return dpt_run_end(U, text, q + c.len, end, c.cls, skip);
     return dpt_ws_piece_end(U, text, p, end, false);
 }
 
 DPT_HD bool dpt_is_newline(uint32_t b) { return b == 0x0Au || b == 0x0Du; }
 
-DPT_HD int64_t dpt_piece_end_llama3(const DptUniView& U, const uint8_t* text, int64_t p, int64_t end) {
+template <class Skip>
+DPT_HD int64_t dpt_piece_end_llama3(const DptUniView& U, const uint8_t* text, int64_t p, int64_t end, const Skip& skip) {
     const uint32_t c0 = text[p];
     if (c0 == '\'' && p + 1 < end) {  // (?i:'s|'t|'re|'ve|'m|'ll|'d); U+017F (C5 BF) folds to 's'
         const uint32_t c1 = text[p + 1] | 0x20u;
@@ -141,10 +152,10 @@ DPT_HD int64_t dpt_piece_end_llama3(const DptUniView& U, const uint8_t* text, in
     }
     const DptChar k0 = dpt_char_at(U, text, p, end);
     // [^\r\n\p{L}\p{N}]?\p{L}+
-    if (k0.cls == DPT_CLS_L) return dpt_run_end(U, text, p + k0.len, end, DPT_CLS_L);
+    if (k0.cls == DPT_CLS_L) return dpt_run_end(U, text, p + k0.len, end, DPT_CLS_L, skip);
     if (k0.cls != DPT_CLS_N && !dpt_is_newline(k0.cp) && p + k0.len < end) {
         const DptChar k1 = dpt_char_at(U, text, p + k0.len, end);
-        if (k1.cls == DPT_CLS_L) return dpt_run_end(U, text, p + k0.len + k1.len, end, DPT_CLS_L);
+        if (k1.cls == DPT_CLS_L) return dpt_run_end(U, text, p + k0.len + k1.len, end, DPT_CLS_L, skip);
     }
     // \p{N}{1,3}
     if (k0.cls == DPT_CLS_N) {
@@ -165,7 +176,7 @@ DPT_HD int64_t dpt_piece_end_llama3(const DptUniView& U, const uint8_t* text, in
         if (k1.cls == DPT_CLS_O) q = p + 1;
     }
     if (q >= 0) {
-        int64_t e = dpt_run_end(U, text, q, end, DPT_CLS_O);
+        int64_t e = dpt_run_end(U, text, q, end, DPT_CLS_O, skip);
         while (e < end && dpt_is_newline(text[e])) ++e;
         return e;
     }
@@ -185,7 +196,8 @@ DPT_HD bool dpt_bloom_excluded(const DptChar& c) {
     }
 }
 
-DPT_HD int64_t dpt_piece_end_bloom(const DptUniView& U, const uint8_t* text, int64_t p, int64_t end) {
+template <class Skip>
+DPT_HD int64_t dpt_piece_end_bloom(const DptUniView& U, const uint8_t* text, int64_t p, int64_t end, const Skip& skip) {
     const DptChar c0 = dpt_char_at(U, text, p, end);
     int64_t e = -1;  // first byte after the first class character of a match that starts at p
     if (!dpt_bloom_excluded(c0)) {
@@ -194,11 +206,13 @@ DPT_HD int64_t dpt_piece_end_bloom(const DptUniView& U, const uint8_t* text, int
         const DptChar c1 = dpt_char_at(U, text, p + 1, end);
         if (!dpt_bloom_excluded(c1)) e = p + 1 + c1.len;
     }
-    if (e >= 0) {  // a match: the run of class characters
+    if (e >= 0) {  // a match: the run of class characters (letters are in the class: ASCII letter runs are skipped over)
         while (e < end) {
-            const DptChar c = dpt_char_at(U, text, e, end);
-            if (dpt_bloom_excluded(c)) break;
-            e += c.len;
+            const int64_t e2 = skip.ascii_letters(e, end);
+            if (e2 >= end) return end;
+            const DptChar c = dpt_char_at(U, text, e2, end);
+            if (dpt_bloom_excluded(c)) return e2;
+            e = e2 + c.len;
         }
         return e;
     }
@@ -213,10 +227,14 @@ DPT_HD int64_t dpt_piece_end_bloom(const DptUniView& U, const uint8_t* text, int
     return e;
 }
 
+template <class Skip>
+DPT_HD int64_t dpt_piece_end(int32_t rule, const DptUniView& U, const uint8_t* text, int64_t p, int64_t end, const Skip& skip) {
+    return rule == 3 /* DPT_RULE_LLAMA3 */  ? dpt_piece_end_llama3(U, text, p, end, skip)
+           : rule == 4 /* DPT_RULE_BLOOM */ ? dpt_piece_end_bloom(U, text, p, end, skip)
+                                            : dpt_piece_end_gpt2(U, text, p, end, skip);
+}
 DPT_HD int64_t dpt_piece_end(int32_t rule, const DptUniView& U, const uint8_t* text, int64_t p, int64_t end) {
-    return rule == 3 /* DPT_RULE_LLAMA3 */  ? dpt_piece_end_llama3(U, text, p, end)
-           : rule == 4 /* DPT_RULE_BLOOM */ ? dpt_piece_end_bloom(U, text, p, end)
-                                            : dpt_piece_end_gpt2(U, text, p, end);
+    return dpt_piece_end(rule, U, text, p, end, DptNoSkip{});
 }
 
 // Is p (doc_start < p < end, text[p] == ' ') a synchronisation point: a space whose next character, in the same

@@ -14,6 +14,9 @@
 #ifndef DPT_PA_CTAS
 #define DPT_PA_CTAS 8
 #endif
+#ifndef DPT_PABL_CTAS
+#define DPT_PABL_CTAS 4  // byte-level kernel A: 55 registers; 5 and 6 CTAs measured slower over the two byte-level workloads
+#endif
 #ifndef DPT_PB_CTAS
 #define DPT_PB_CTAS 12
 #endif
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(PA_THREADS, DPT_PA_CTAS) k_scan_dedup(const __
     pa_kernel<DevBlk, true>(blk, P, S);
 }
 // byte-level rules (GPT-2, Llama-3): the split scanner needs more registers and the sync-point list more memory
-__global__ void __launch_bounds__(PA_THREADS) k_scan_dedup_bl(const __grid_constant__ PipeParams P) {
+__global__ void __launch_bounds__(PA_THREADS, DPT_PABL_CTAS) k_scan_dedup_bl(const __grid_constant__ PipeParams P) {
     __shared__ ASmemT<false> S;
     DevBlk blk;
     pa_kernel<DevBlk, false>(blk, P, S);

@@ -29,7 +29,7 @@ def run(args):
         env = dict(os.environ)
         if path:
             env["DPT_LIB_PATH"] = path
-        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "10", "--warmup", "3", "--no-cpu-baseline", "--no-e2e"] + args
+        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", os.environ.get("DPT_VARIANT_STEPS", "10"), "--warmup", "3", "--no-cpu-baseline", "--no-e2e"] + args
         p = subprocess.run(cmd, env=env, capture_output=True, text=True)
         try:
             line = json.loads(p.stdout.strip().splitlines()[-1])
