@@ -44,7 +44,7 @@ namespace dpt {
 #define DPT_PA_THREADS 256
 #endif
 #ifndef DPT_PA_WIN
-#define DPT_PA_WIN 512
+#define DPT_PA_WIN 768
 #endif
 constexpr int PA_T = DPT_PA_T;                // raw bytes per tile of kernel A
 constexpr int PA_HALO = 32;                   // look-behind (multiple of 32 keeps mask words aligned)
@@ -69,7 +69,9 @@ constexpr int PB_LOCAL = 72;                  // normalised bytes solved with pe
 constexpr int PB_REFILL = DPT_PB_REFILL;
 constexpr int PC_THREADS = 256;
 constexpr int PC_PER = 8;                     // words per thread in kernel C
-constexpr int PA_WIN = DPT_PA_WIN;                  // words of a tile handled per pass (a 4 KB tile holds ~520; more -> more passes)
+constexpr int PA_WIN = DPT_PA_WIN;                  // words of a tile handled per pass.  A tile holds ~500-540 words: with 512 most
+                                              // byte-level tiles needed a second, nearly empty pass and resolved their look-back
+                                              // BEFORE probing (768: k_scan_dedup_bl 1.44 -> 1.38 / 1.46 -> 1.31 ms, SPM unchanged)
 constexpr int PC_TILE = PC_THREADS * PC_PER;
 constexpr int PC_STAGE = 6144;                // ids of one kernel-C tile staged in shared memory (more -> direct writes)
 
@@ -193,6 +195,8 @@ struct CSmem {
     uint32_t scan[40];
     int32_t tile;
     uint32_t tile_tot, n_untok;
+    uint32_t n_docfirst;       // byte-level rules: documents that start in this tile
+    long long doc0;            // ... and the index (in the range) of the first of them
     unsigned long long base_t;
 };
 
@@ -862,7 +866,9 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
             const uint32_t ref = S.stage[k];
             if (base + k < P.word_cap) P.refs[base + k] = ref;
             if (!spm && (ref & REF_DOCFIRST)) {
-                const int64_t d = pp_lower_bound(P.doc_offs, P.n_docs + 1, g0 + (int)(S.wlist[k] & 0x7FFFu));
+                // index of this document = first document of the region + document starts in front of the word
+                const int r = (int)(S.wlist[k] & 0x7FFFu);
+                const int64_t d = (int64_t)S.d_first + S.dsn[r >> 5] + pp_popc(S.mDS[r >> 5] & ((1u << (r & 31)) - 1u));
                 if (d >= P.doc_begin && d < P.doc_begin + P.n_docs_local) P.doc_first_word[d - P.doc_begin] = base + k;
             }
         }
@@ -1277,11 +1283,19 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
             if (meta[k] & RES_UNTOK) ++untok; else mine += meta[k] & 0xFFFFFFu;
         }
     }
-    if (tid == 0) S.n_untok = 0;
+    // byte-level rules: first words of documents among this thread's words (a '<s>' ref carries its document index)
+    uint32_t my_docfirst = 0;
+    if (!P.spm) {
+#pragma unroll
+        for (int k = 0; k < PC_PER; ++k)
+            if (w0 + k < n_words && (ref[k] & REF_KIND) != REF_BOS && (ref[k] & REF_DOCFIRST)) ++my_docfirst;
+    }
+    if (tid == 0) S.n_untok = S.n_docfirst = 0;
     uint32_t total;
     const uint32_t off = blk.exclusive_scan(mine, S.scan, total);
     blk.lookback_publish(P.desc_t, tile, (unsigned long long)total);
     if (untok) blk.atomic_add(&S.n_untok, untok);
+    if (my_docfirst) blk.atomic_add(&S.n_docfirst, my_docfirst);
     // per-word outputs that do not need the token offset
     if (w0 + PC_PER <= n_words && P.vec_ok) {
         uint4 l0, l1;
@@ -1346,7 +1360,17 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
         if (staged)
             for (uint32_t q = (uint32_t)tid; q < total; q += (uint32_t)blk.nthreads())
                 if (base_t + q < P.ids_cap) pc_st_stream(P.ids + base_t + q, S.ids[q]);
-        // document token offsets
+        // document token offsets.  Byte-level rules: documents are numbered by their first words, so the index of a
+        // first word = documents that start in front of this tile (ONE search of doc_first_word per tile; a search
+        // per document made kernel C twice as slow on short documents) + first words in front of it within the tile.
+        int64_t d_next = 0;
+        if (!P.spm && S.n_docfirst) {  // block-uniform
+            uint32_t tile_docs;
+            const uint32_t before = blk.exclusive_scan(my_docfirst, S.scan, tile_docs);
+            if (tid == 0) S.doc0 = (long long)pp_lower_bound(P.doc_first_word, P.n_docs_local, (int64_t)tile * PC_TILE);
+            blk.sync();
+            d_next = (int64_t)S.doc0 + before;
+        }
         int64_t gt = base_t + off;
 #pragma unroll
         for (int k = 0; k < PC_PER; ++k) {
@@ -1356,7 +1380,7 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
                 const int64_t d = (int64_t)(ref[k] & REF_INDEX);
                 if (d < P.n_docs_local) P.doc_tok_offs[d] = gt;
             } else if (ref[k] & REF_DOCFIRST) {  // byte-level rules: first word of a document
-                const int64_t d = pp_lower_bound(P.doc_first_word, P.n_docs_local, w0 + k);
+                const int64_t d = d_next++;
                 if (d < P.n_docs_local) P.doc_tok_offs[d] = gt;
             }
             if (!(meta[k] & RES_UNTOK)) gt += meta[k] & 0xFFFFFFu;
