@@ -86,3 +86,30 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "liboracle" not in src and "host_sim" not in src.replace("tests/host_sim", ""), f
+
+
+def test_adapter_recognises_device_split_rules(product_lib):
+    """`dp_tokenize_bloom` picks the DPT_RULE_* of a tokenizer from its JSON (GPT-2 ByteLevel regex, Llama-3 / BLOOM
+    Split regex + ByteLevel) and falls back to `pre_tokenize_str` on the host for anything else
+    (tokenizer_utils.py:157-159)."""
+    import json
+    from tokenizers import Regex, Tokenizer, pre_tokenizers
+    from dptok import _cabi, assets
+    from packages.tokenizer_utils import _device_split_rule
+    for name, rule in (("gpt2_3k", _cabi.RULE_GPT2), ("llama3_128k", _cabi.RULE_LLAMA3), ("bloom_8k", _cabi.RULE_BLOOM)):
+        assert _device_split_rule(assets.load_hf(name)) == rule
+
+    class Wrapped:  # what the adapter looks at: `_tokenizer` of a HF fast tokenizer
+        def __init__(self, backend):
+            self._tokenizer = backend
+
+    base = assets.load_tokenizer("bloom_8k")
+    spec = json.loads(base.to_str())
+    spec["pre_tokenizer"]["pretokenizers"][0]["pattern"]["Regex"] = r" ?[^\s]+"   # some other split regex
+    assert _device_split_rule(Wrapped(Tokenizer.from_str(json.dumps(spec)))) is None
+    spec = json.loads(base.to_str())
+    spec["pre_tokenizer"]["pretokenizers"][1]["add_prefix_space"] = True             # rewrites the text first
+    assert _device_split_rule(Wrapped(Tokenizer.from_str(json.dumps(spec)))) is None
+    spec = json.loads(base.to_str())
+    spec["normalizer"] = {"type": "NFC"}                                             # a normaliser in front
+    assert _device_split_rule(Wrapped(Tokenizer.from_str(json.dumps(spec)))) is None
