@@ -80,9 +80,11 @@ DPT_HD DptChar dpt_char_at(const DptUniView& U, const uint8_t* text, int64_t p, 
     return c;
 }
 
-// Optional accelerator of the scanners: ascii_letters(p, end) returns the end of the run of ASCII letters that starts
-// at p (p itself if there is none), never beyond `end`.  Kernel A answers it from a one-bit-per-byte mask of its tile
-// (dpt_pipe.h: PaLetterSkip); the default does nothing and the scanner walks the run character by character.
+// Optional accelerator of the scanners: ascii_letters(p, end), p a character start, returns the end of a run of whole
+// characters of class L that starts at p (p itself if it knows of none), never beyond `end`; it need not be the
+// maximal run.  Kernel A answers it from a one-bit-per-byte mask of its tile (dpt_pipe.h: PaLetterSkip - ASCII letters
+// and the multi-byte letters the tile could classify); the default does nothing and the scanner walks the run character
+// by character.
 struct DptNoSkip {
     DPT_HD int64_t ascii_letters(int64_t p, int64_t) const { return p; }
 };
@@ -90,7 +92,7 @@ struct DptNoSkip {
 // end of the maximal run of characters of class `cls` starting at p
 template <class Skip>
 DPT_HD int64_t dpt_run_end(const DptUniView& U, const uint8_t* text, int64_t p, int64_t end, uint32_t cls, const Skip& skip) {
-    if (cls == DPT_CLS_L) p = skip.ascii_letters(p, end);  // (an ASCII letter is always a character of class L on its own)
+    if (cls == DPT_CLS_L) p = skip.ascii_letters(p, end);
     while (p < end) {
         const DptChar c = dpt_char_at(U, text, p, end);
         if (c.cls != cls) break;

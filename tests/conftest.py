@@ -37,19 +37,16 @@ def product_lib():
     return lib
 
 
-@pytest.fixture(scope="session")
-def host_sim():
-    """TEST-ONLY g++ build of the device headers (tests/host_sim/sim.cpp)."""
+def build_host_sim(extra=(), name="libsim.so"):
+    """TEST-ONLY g++ build of the device headers (tests/host_sim/sim.cpp); `extra`: the kernels' tuning macros."""
     import ctypes as C
     out_dir = os.path.join(ROOT, "tests", "host_sim", "_build")
     os.makedirs(out_dir, exist_ok=True)
-    out = os.path.join(out_dir, "libsim.so")
+    out = os.path.join(out_dir, name)
     srcs = [os.path.join(ROOT, "tests", "host_sim", "sim.cpp"), os.path.join(PKG, "csrc", "vocab.cpp")]
     deps = srcs + [os.path.join(PKG, "csrc", h) for h in os.listdir(os.path.join(PKG, "csrc")) if h.endswith(".h")]
-    extra = os.environ.get("DPT_SIM_EXTRA", "").split()  # development: the kernels' tuning macros (-DDPT_PA_T=...)
-    if extra:
-        out = os.path.join(out_dir, "libsim_variant.so")
-    if extra or not os.path.isfile(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+    extra = list(extra)
+    if not os.path.isfile(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", "-I", os.path.join(PKG, "csrc"),
                                "-o", out] + extra + srcs)
     lib = C.CDLL(out)
@@ -68,3 +65,21 @@ def host_sim():
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64,
                                            C.c_int64, C.c_int64, C.c_int32]
     return lib
+
+
+@pytest.fixture(scope="session")
+def host_sim():
+    extra = os.environ.get("DPT_SIM_EXTRA", "").split()  # development: -DDPT_PA_T=... etc.
+    return build_host_sim(extra, "libsim_variant.so" if extra else "libsim.so")
+
+
+@pytest.fixture(scope="session")
+def host_sim_noskip():
+    """The same kernels with the split scanner walking letter runs character by character (no letter mask)."""
+    return build_host_sim(["-DDPT_NO_LETTER_SKIP"], "libsim_noskip.so")
+
+
+@pytest.fixture(scope="session")
+def host_sim_mb_letters():
+    """The same kernels with multi-byte letters in the tile's letter mask too (DPT_MB_LETTERS; measured slower, off)."""
+    return build_host_sim(["-DDPT_MB_LETTERS"], "libsim_mbletters.so")

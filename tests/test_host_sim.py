@@ -390,3 +390,35 @@ def test_pipeline_code_bytelevel_rules(host_sim):
                ("." * 5000 + " " + "," * 4200 + " q").encode(), ("\u3002" * 1500 + " \u3000" * 700 + "w").encode()]
         _check_bytelevel(host_sim, h, tok, vb, rule, big, nthreads=4)
         host_sim.sim_vocab_destroy(ctypes.c_void_p(h))
+
+
+def test_letter_mask_agrees_with_scanner_on_arbitrary_bytes(host_sim, host_sim_noskip, host_sim_mb_letters):
+    """The tile's letter mask (ASCII letters by SWAR; with DPT_MB_LETTERS also multi-byte letters classified in the mask
+    pass) only lets the split scanner skip ahead: on ANY bytes - truncated and invalid UTF-8, lead bytes cut by document boundaries, runs
+    across tile borders - the pieces, ids and offsets equal those of the scanner walking character by character."""
+    from dptok import assets
+    rng = random.Random(11)
+    frags = [b"abc", b"Z", b" ", b"  ", b"\n", b"1", b"'s", b".", "é".encode(), "ß".encode(), "قُدَّام".encode(),
+             "日本".encode(), "𝒜".encode(), "ǅ".encode(), b"\xc3", b"\xa9", b"\xe6\x97", b"\xf0\x9d\x92", b"\xff", b"\xc0\x80",
+             b"\xed\xa0\x80", "ſ".encode(), "İ".encode(), "　".encode()]
+    for name, rule in (("gpt2_3k", 2), ("llama3_128k", 3), ("bloom_8k", 4)):
+        v2i = {t: k for k, t in enumerate(assets.load_spec(name)["model"]["vocab"])}
+        vb = vocab_bytes(v2i, "bytelevel")
+        h1, h2 = make_sim_vocab(host_sim, vb, 0), make_sim_vocab(host_sim_noskip, vb, 0)
+        h3 = make_sim_vocab(host_sim_mb_letters, vb, 0)
+        for trial in range(12):
+            n_docs = rng.choice([1, 7, 300])
+            docs = [b"".join(rng.choice(frags) for _ in range(rng.randint(1, 120 if n_docs < 300 else 12))) for _ in range(n_docs)]
+            if trial % 3 == 0:  # long letter runs across tile borders, a multi-byte letter right at a border
+                docs.append(b"x" * 3960 + "é".encode() * 40 + b" y" + "ب".encode() * 5000)
+            a = _run_fused(host_sim, h1, rule, docs, nthreads=rng.choice([1, 4, 8]))
+            b = _run_fused(host_sim_noskip, h2, rule, docs, nthreads=4)
+            assert a["nout"].tolist() == b["nout"].tolist() and a["ctr"].tolist() == b["ctr"].tolist()
+            assert np.array_equal(a["wl"], b["wl"]) and np.array_equal(a["ids"], b["ids"])
+            assert np.array_equal(a["dto"], b["dto"]) and np.array_equal(a["wf"], b["wf"])
+            c = _run_fused(host_sim_mb_letters, h3, rule, docs, nthreads=3)
+            assert c["nout"].tolist() == b["nout"].tolist() and np.array_equal(c["wl"], b["wl"])
+            assert np.array_equal(c["ids"], b["ids"]) and np.array_equal(c["dto"], b["dto"])
+        host_sim_mb_letters.sim_vocab_destroy(ctypes.c_void_p(h3))
+        host_sim.sim_vocab_destroy(ctypes.c_void_p(h1))
+        host_sim_noskip.sim_vocab_destroy(ctypes.c_void_p(h2))
