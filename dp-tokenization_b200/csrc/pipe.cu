@@ -52,7 +52,6 @@ struct DevBlk {
         return atomicAdd(p, v);
     }
     __device__ __forceinline__ unsigned long long load_relaxed(const unsigned long long* p) const { return ld_relaxed_gpu(p); }
-    __device__ __forceinline__ void fence() const { __threadfence(); }
     __device__ __forceinline__ unsigned long long cas_u64(unsigned long long* p, unsigned long long expect,
                                                           unsigned long long desired) const {
         return atomicCAS(p, expect, desired);

@@ -37,7 +37,6 @@ struct HostBlk {
         return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
     }
     unsigned long long load_relaxed(const unsigned long long* p) const { return __atomic_load_n(p, __ATOMIC_RELAXED); }
-    void fence() const { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
     unsigned long long cas_u64(unsigned long long* p, unsigned long long expect, unsigned long long desired) const {
         __atomic_compare_exchange_n(p, &expect, desired, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
         return expect;  // old value, like atomicCAS
