@@ -1,5 +1,6 @@
-// CUDA kernels (sm_100a) of the corpus pipeline in dpt_pipe.h:  A scan+dedup -> B DP per distinct word ->
-// C scan+emit -> D counters.  Five launches per corpus, no host synchronisation in between.
+// CUDA kernels (sm_100a) of the corpus pipeline in dpt_pipe.h:  clear -> A scan+dedup -> B DP per distinct word (+ B'
+// long words) -> C scan+emit (its last tile writes the counters).  Five launches per corpus, no host synchronisation
+// in between.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -346,7 +347,7 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
     P.doc_flags = d_doc_flags;
     P.counters = (unsigned long long*)d_counters;
     P.n_out = d_n_out;
-    {   // table part: PipePersist + tags first, so a reset is one memset
+    {   // table part: PipePersist + tags first, so a reset is one contiguous region of k_pipe_clear
         char* base = (char*)d_table_ws;
         int64_t used = 0;
         auto take = [&](int64_t bytes) {
