@@ -513,41 +513,6 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
         if (!spm) {
             // bytes of letter characters: ASCII letters (SWAR)
             uint32_t al = pp_letters4(x.x) | (pp_letters4(x.y) << 4) | (pp_letters4(x.z) << 8) | (pp_letters4(x.w) << 12);
-            // (DPT_MB_LETTERS also classifies the multi-byte characters of the 16 bytes here and marks the letters among
-            // them, so that the scanner skips Arabic or accented runs too.  Exact - the emulation tests compare both
-            // ways with the plain scanner - but measured slower on the B200: the look-ups in this pass cost more than
-            // the scanner saves, k_scan_dedup_bl 1.354 -> 1.433 ms (40 % Arabic), 1.116 -> 1.181 ms (en/de).  Off.)
-#if defined(DPT_MB_LETTERS)
-            if ((x.x | x.y | x.z | x.w) & 0x80808080u) {
-                const DptUniView U{P.V.uni1, P.V.uni2};
-                const int base = 16 * hw;
-                int q = base >= 3 ? base - 3 : 0;  // a character that reaches into these 16 bytes starts at most 3 in front
-                while (q < base + 16) {
-                    const uint32_t b0 = S.text[q];
-                    const int need = (b0 & 0xE0u) == 0xC0u ? 2 : (b0 & 0xF0u) == 0xE0u ? 3 : (b0 & 0xF8u) == 0xF0u ? 4 : 0;
-                    if (need == 0) {  // ASCII, a continuation byte or an invalid lead byte: no multi-byte character starts here
-                        ++q;
-                        continue;
-                    }
-                    bool ok = q + need <= PA_R && !pp_any_in_range(S.mDS, q + 1, q + need);
-                    uint32_t cp = need == 2 ? (b0 & 0x1Fu) : need == 3 ? (b0 & 0x0Fu) : (b0 & 0x07u);  // as dpt_char_at
-                    for (int k = 1; ok && k < need; ++k) {
-                        const uint32_t bk = S.text[q + k];
-                        ok = (bk & 0xC0u) == 0x80u;
-                        cp = (cp << 6) | (bk & 0x3Fu);
-                    }
-                    if (!ok) {  // malformed or not decidable here: left to the scanner
-                        ++q;
-                        continue;
-                    }
-                    if (dpt_cp_class(U, cp) == DPT_CLS_L) {
-                        const int lo = q > base ? q - base : 0, hi = q + need - base < 16 ? q + need - base : 16;
-                        if (hi > lo) al |= ((1u << (hi - lo)) - 1u) << lo;
-                    }
-                    q += need;
-                }
-            }
-#endif
             reinterpret_cast<uint16_t*>(S.mAL)[hw] = (uint16_t)al;
         }
     }

@@ -78,8 +78,3 @@ def host_sim_noskip():
     """The same kernels with the split scanner walking letter runs character by character (no letter mask)."""
     return build_host_sim(["-DDPT_NO_LETTER_SKIP"], "libsim_noskip.so")
 
-
-@pytest.fixture(scope="session")
-def host_sim_mb_letters():
-    """The same kernels with multi-byte letters in the tile's letter mask too (DPT_MB_LETTERS; measured slower, off)."""
-    return build_host_sim(["-DDPT_MB_LETTERS"], "libsim_mbletters.so")
