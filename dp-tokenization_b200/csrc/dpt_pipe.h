@@ -87,10 +87,13 @@ constexpr unsigned long long PD_MASK = (1ull << 62) - 1;
 
 constexpr uint32_t RES_UNTOK = 1u << 24;      // result meta: word_len (24 bits) | flags
 constexpr uint32_t RES_POOLED = 1u << 25;     // more than RES_INLINE ids: they live in the pool at ids[0] | ids[1] << 32
-constexpr int RES_INLINE = 7;
+constexpr int RES_INLINE = 3;
 constexpr uint32_t RES_LONG = 1u << 26;       // solved by the long-word kernel
 
-struct alignas(32) ResRec {  // result of one distinct word: exactly one 32-byte sector
+// Result of one distinct word: 16 bytes, indexed by the word's table slot.  Nine of ten word OCCURRENCES have at most
+// three tokens, so kernel C's one 16-byte gather per word brings everything it needs; the 32-byte records of round 1
+// (7 ids inline) made the table a sparse 67 MB that fought the streaming refs/ids for L2 (hit rate 47 %).
+struct alignas(16) ResRec {
     uint32_t meta;           // word_len (len_dp[n], 24 bits) | RES_* flags
     int32_t ids[RES_INLINE];
 };
@@ -105,6 +108,7 @@ struct PipeCtl {  // device-side counters, zeroed by the launcher
     unsigned int ticket_a, ticket_c;
     unsigned int n_pending[PB_CLASSES];  // distinct words queued for the DP, by length class (keeps a warp's lanes alike)
     unsigned int n_odd, n_long;
+    unsigned int n_defer, pad0;          // words the cooperative DP kernel handed to the thread-per-word kernel
     unsigned long long lp_used, n_words, n_untok, n_too_long;
     unsigned long long b_cursor;  // next unclaimed item of kernel B's work list
 };
@@ -143,6 +147,8 @@ struct PipeParams {
     ResRec* odd_res;              // odd_cap
     int32_t* pool;                // pool_cap ids of words with more than 7 tokens (persistent, like the table)
     uint32_t* longq;              // n_slots + odd_cap
+    uint32_t* defer;              // pend_stride table slots (cooperative DP kernel -> thread-per-word kernel)
+    int32_t coop;                 // 1: length classes 0..2 are solved by the cooperative kernel (device); 0: host emulation
     uint8_t* lp_norm;             // long-word scratch: lp_cap positions
     uint64_t* lp_best;
     uint16_t* lp_a;
@@ -377,9 +383,11 @@ struct PaLetterSkip {
         return p < end ? p : end;
     }
 };
-// length class of a word body: lanes of a warp of kernel B get words of one class, i.e. of similar DP cost
-DPT_HD int pp_len_class(int len) {
-    return len <= 6 ? 0 : len <= 10 ? 1 : len <= 16 ? 2 : 3;
+// Length class of a word = the tile width of the cooperative DP kernel that solves it: `units` = lanes the word needs
+// (body bytes, + 1 for the SPM marker).  0: 8-lane tiles (4 words per warp), 1: 16 lanes, 2: 32 lanes, 3: longer than a
+// warp -> the thread-per-word kernel.
+DPT_HD int pp_len_class(int units) {
+    return units <= 8 ? 0 : units <= 16 ? 1 : units <= 31 ? 2 : 3;
 }
 DPT_HD uint32_t pp_tail_mask(int nbytes) { return nbytes >= 4 ? ~0u : ((1u << (8 * nbytes)) - 1u); }
 
@@ -804,7 +812,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                             t = blk.cas_u64(&P.tags[slot], 0ull, mine);
                             if (t == 0) {  // first occurrence of this word: claim the slot, queue the DP
                                 const uint32_t li = blk.atomic_add_ret(&S.n_pend, 1u);
-                                const uint32_t cls = (uint32_t)pp_len_class(len);
+                                const uint32_t cls = (uint32_t)pp_len_class(len + (spm ? 1 : 0));
                                 S.pend[li] = slot | (cls << 29);
                                 blk.atomic_add(&S.n_pend_c[cls], 1u);
                                 ref = slot;
@@ -998,8 +1006,15 @@ struct PbItem {
     bool marker;
     ResRec* out;
 };
-// Work list order: odd words, then the length classes from longest to shortest, so the expensive words are
-// claimed first and the kernel's tail is made of the cheapest ones.
+// Work list of the thread-per-word kernel.  With the cooperative kernel in front (P.coop, the device): odd words, the
+// words longer than a warp (class 3), then the words the cooperative kernel deferred (out-of-vocabulary characters that
+// expand to "<0xHH>" text).  Without it (host emulation): odd words, then every length class from longest to shortest.
+DPT_PIPE_FN uint64_t pb_list_len(const PipeParams& P, const uint32_t* npc, uint32_t n_odd, uint32_t n_defer) {
+    uint64_t total = n_odd;
+    if (P.coop) return total + npc[PB_CLASSES - 1] + n_defer;
+    for (int c = 0; c < PB_CLASSES; ++c) total += npc[c];
+    return total;
+}
 DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint64_t i, const uint32_t* npc, uint32_t n_odd) {
     PbItem it;
     if (i < n_odd) {
@@ -1011,12 +1026,18 @@ DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint64_t i, const uint32_t* npc,
         return it;
     }
     i -= n_odd;
-    uint32_t cls = PB_CLASSES - 1;
-    while (cls > 0 && i >= npc[cls]) {
-        i -= npc[cls];
-        --cls;
+    uint32_t slot;
+    if (P.coop) {
+        slot = i < npc[PB_CLASSES - 1] ? P.pending[(size_t)(PB_CLASSES - 1) * (size_t)P.pend_stride + i]
+                                       : P.defer[i - npc[PB_CLASSES - 1]];
+    } else {
+        uint32_t cls = PB_CLASSES - 1;
+        while (cls > 0 && i >= npc[cls]) {
+            i -= npc[cls];
+            --cls;
+        }
+        slot = P.pending[(size_t)cls * (size_t)P.pend_stride + i];
     }
-    const uint32_t slot = P.pending[(size_t)cls * (size_t)P.pend_stride + i];
     const unsigned long long t = P.tags[slot];
     it.pos = pp_tag_pos(t);
     it.end = it.pos + pp_tag_len(t);
@@ -1058,13 +1079,9 @@ DPT_PIPE_FN void pb_finish_word(Blk& blk, const PipeParams& P, const uint8_t* no
 template <class Blk>
 DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
     uint32_t npc[PB_CLASSES];
-    uint64_t total = 0;
-    for (int c = 0; c < PB_CLASSES; ++c) {
-        npc[c] = pb_queue_len(P, c);
-        total += npc[c];
-    }
+    for (int c = 0; c < PB_CLASSES; ++c) npc[c] = pb_queue_len(P, c);
     const uint32_t n_odd = P.ctl->n_odd < (uint32_t)P.odd_cap ? P.ctl->n_odd : (uint32_t)P.odd_cap;
-    total += n_odd;
+    const uint64_t total = pb_list_len(P, npc, n_odd, P.ctl->n_defer);
     uint8_t norm[PB_LOCAL + 8];
     uint32_t best[PB_LOCAL + 1], Ap[PB_LOCAL + 1], Bp[PB_LOCAL + 1];
     uint8_t upos[PB_LOCAL + 8];
@@ -1248,7 +1265,7 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
     const int64_t n_words = (int64_t)P.ctl->n_words < P.word_cap ? (int64_t)P.ctl->n_words : P.word_cap;
     const int64_t w0 = (int64_t)tile * PC_TILE + (int64_t)tid * PC_PER;
     uint32_t ref[PC_PER], meta[PC_PER];
-    uint4 head[PC_PER];  // first half of every word's result record: meta + ids[0..2] (pooled: meta + pool offset)
+    uint4 head[PC_PER];  // every word's result record: meta + ids[0..2] (pooled: meta + pool offset)
     uint32_t mine = 0, untok = 0;
     if (w0 + PC_PER <= n_words) {  // two 16-byte loads of 8 refs
         const uint4 r0 = pc_ld_stream(reinterpret_cast<const uint4*>(P.refs + w0));
@@ -1345,13 +1362,6 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
                 if (gt < cap) dst[gt] = (int32_t)head[k].y;
                 if (nk > 1 && gt + 1 < cap) dst[gt + 1] = (int32_t)head[k].z;
                 if (nk > 2 && gt + 2 < cap) dst[gt + 2] = (int32_t)head[k].w;
-                if (nk > 3 && (ref[k] & REF_KIND) != REF_BOS) {  // '<s>' contributes at most three ids
-                    const uint4 c = *(reinterpret_cast<const uint4*>(pc_record_ptr(P, ref[k])) + 1);   // ids[3..6]
-                    if (gt + 3 < cap) dst[gt + 3] = (int32_t)c.x;
-                    if (nk > 4 && gt + 4 < cap) dst[gt + 4] = (int32_t)c.y;
-                    if (nk > 5 && gt + 5 < cap) dst[gt + 5] = (int32_t)c.z;
-                    if (nk > 6 && gt + 6 < cap) dst[gt + 6] = (int32_t)c.w;
-                }
             }
             gt += nk;
         }

@@ -8,6 +8,7 @@
 
 #include "../../include/dptok.h"
 #include "dpt_pipe.h"
+#include "dpt_dp_coop.cuh"
 #include "kernels.h"
 #include "vocab.h"
 
@@ -20,6 +21,9 @@
 #endif
 #ifndef DPT_PB_CTAS
 #define DPT_PB_CTAS 12
+#endif
+#ifndef DPT_PBC_CTAS
+#define DPT_PBC_CTAS 8
 #endif
 #ifndef DPT_PC_CTAS
 #define DPT_PC_CTAS 4
@@ -190,6 +194,13 @@ __global__ void __launch_bounds__(PA_THREADS, DPT_PABL_CTAS) k_scan_dedup_bl(con
     pa_kernel<DevBlk, false>(blk, P, S);
 }
 
+// the cooperative DP (dpt_dp_coop.cuh): length classes 0..2, i.e. every word that fits a warp
+__global__ void __launch_bounds__(PBC_THREADS, DPT_PBC_CTAS) k_dp_coop(const __grid_constant__ PipeParams P) {
+    __shared__ uint32_t slot_smem[(PBC_THREADS / 32) * 32 * 32];
+    pbc_kernel(P, slot_smem);
+}
+
+// thread-per-word DP with local-memory state: odd words, words longer than a warp, words the cooperative kernel deferred
 __global__ void __launch_bounds__(PB_THREADS, DPT_PB_CTAS) k_dp_distinct(const __grid_constant__ PipeParams P) {
     DevBlk blk;
     pb_thread(blk, P);
@@ -259,7 +270,7 @@ int64_t corpus_table_workspace(int64_t n_bytes_total, int64_t word_cap_total, in
     int64_t b = 0;
     b += align_up(sizeof(PipePersist), 256);
     b += align_up(z.n_slots * 8, 256);    // tags
-    b += align_up(z.n_slots * 32, 256);   // res
+    b += align_up(z.n_slots * (int64_t)sizeof(ResRec), 256);   // res
     b += align_up(z.pool_cap * 4, 256);   // pool
     return b + 1024;
 }
@@ -272,8 +283,9 @@ int64_t corpus_range_workspace(int64_t range_bytes, int64_t range_docs, int64_t 
     b += align_up(word_cap * 4 + 64, 256);                   // refs
     b += align_up(word_cap * 4 * PB_CLASSES + 64, 256);      // pending (length classes x min(word_cap, n_slots); upper bound)
     b += align_up((range_docs + 1) * 8, 256);                // doc_first_word
-    b += align_up(z.odd_cap * 16, 256) + align_up(z.odd_cap * 32, 256);  // odd, odd_res
+    b += align_up(z.odd_cap * 16, 256) + align_up(z.odd_cap * (int64_t)sizeof(ResRec), 256);  // odd, odd_res
     b += align_up((word_cap + z.odd_cap) * 4, 256);          // longq
+    b += align_up(word_cap * 4 + 64, 256);                   // defer (upper bound of pend_stride entries)
     b += align_up(z.lp_cap, 256) + align_up(z.lp_cap * 8, 256) + 2 * align_up(z.lp_cap * 2, 256);
     return b + 4096;
 }
@@ -359,7 +371,7 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
         P.persist = (PipePersist*)take(sizeof(PipePersist));
         P.tags = (unsigned long long*)take(tz.n_slots * 8);
         const int64_t zero_bytes = used;
-        P.res = (ResRec*)take(tz.n_slots * 32);
+        P.res = (ResRec*)take(tz.n_slots * (int64_t)sizeof(ResRec));
         P.pool = (int32_t*)take(tz.pool_cap * 4);
         P.pool_cap = tz.pool_cap;
         P.slot_mask = (uint32_t)(tz.n_slots - 1);
@@ -387,8 +399,10 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
         P.pending = (uint32_t*)take(P.pend_stride * 4 * PB_CLASSES + 64);
         P.doc_first_word = (int64_t*)take((range_docs + 1) * 8);
         P.odd = (OddWord*)take(z.odd_cap * 16);
-        P.odd_res = (ResRec*)take(z.odd_cap * 32);
+        P.odd_res = (ResRec*)take(z.odd_cap * (int64_t)sizeof(ResRec));
         P.longq = (uint32_t*)take((word_cap + z.odd_cap) * 4);
+        P.defer = (uint32_t*)take(P.pend_stride * 4 + 64);
+        P.coop = 1;
         P.lp_norm = (uint8_t*)take(z.lp_cap);
         P.lp_best = (uint64_t*)take(z.lp_cap * 8);
         P.lp_a = (uint16_t*)take(z.lp_cap * 2);
@@ -433,11 +447,21 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
     }
     if (do_dp) {
     {
+        ProfScope prof("k_dp_coop", st);
+        static int bc_ctas = 0;  // CTAs per SM of the cooperative kernel's grid (development knob: DPT_BC_GRID)
+        if (!bc_ctas) {
+            const char* e = getenv("DPT_BC_GRID");
+            bc_ctas = e && atoi(e) > 0 ? atoi(e) : DPT_PBC_CTAS;
+        }
+        k_dp_coop<<<(unsigned)(sm_count * bc_ctas), PBC_THREADS, 0, st>>>(P);
+        ++g_launches;
+    }
+    {
         ProfScope prof("k_dp_distinct", st);
         static int b_ctas = 0;  // CTAs per SM of kernel B's grid (development knob: DPT_B_GRID)
         if (!b_ctas) {
             const char* e = getenv("DPT_B_GRID");
-            b_ctas = e && atoi(e) > 0 ? atoi(e) : 16;
+            b_ctas = e && atoi(e) > 0 ? atoi(e) : 4;
         }
         k_dp_distinct<<<(unsigned)(sm_count * b_ctas), PB_THREADS, 0, st>>>(P);
         ++g_launches;
