@@ -481,4 +481,16 @@ int dpt_roundtrip_check(const dpt_vocab* v, const int32_t* d_ids, const int64_t*
     return rc ? fail(rc, "dpt_roundtrip_check: launch failed") : DPT_OK;
 }
 
+int dpt_synth_corpus(const uint8_t* d_lex_a_bytes, const int64_t* d_lex_a_offs, const uint32_t* d_lex_a_cdf, int32_t n_a,
+                     const uint8_t* d_lex_b_bytes, const int64_t* d_lex_b_offs, const uint32_t* d_lex_b_cdf, int32_t n_b,
+                     const dpt_synth_params* params, int64_t doc_base, int64_t n_docs, int64_t* d_doc_len,
+                     const int64_t* d_doc_offs, uint8_t* d_text, void* stream) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return fail(DPT_ECUDA, "dpt_synth_corpus: no CUDA device");
+    std::string err;
+    const int rc = dpt::synth_run(d_lex_a_bytes, d_lex_a_offs, d_lex_a_cdf, n_a, d_lex_b_bytes, d_lex_b_offs, d_lex_b_cdf, n_b,
+                                  params, doc_base, n_docs, d_doc_len, d_doc_offs, d_text, (cudaStream_t)stream, err);
+    return rc ? fail(rc, err.c_str()) : DPT_OK;
+}
+
 }  // extern "C"

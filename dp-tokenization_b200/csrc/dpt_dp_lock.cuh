@@ -1,0 +1,301 @@
+// Kernel B of the corpus pipeline: the shortest-tokenization DP (dp_tokenize.py:24-84 in the closed form of
+// dpt_dp_core.h) for every distinct word of at most 31 units - one THREAD per word, the 32 words of a warp in LOCK STEP.
+//
+// Why this shape (measured, profiles/README.md):
+//   * round 1's kernel stepped a per-lane state machine (one trie step of the lane's own (start, end) pair per
+//     iteration) with its DP state in 1 KB of local memory per thread: ~110 instructions per trie step, 417 MB of
+//     DRAM traffic for the spilled state.
+//   * a sub-warp-cooperative kernel (lane j walks from start j, redux.min relaxation, ballot/clz selection; kept as
+//     profiles/rejected/r2_dp_coop.patch) has no local memory but runs dense n x T lane-slots per word:
+//     512 M warp-instructions, 0.73 ms against 0.28 ms.
+//   * here the loops are warp-uniform - every lane is at start position s of its own word, the walk loop runs until
+//     no lane's walk is alive - so the lanes never diverge, the word's bytes sit in a REGISTER window that shifts by one
+//     byte per start (static byte extraction, no indexed loads), and the state of a position is ONE 32-bit word
+//     (16-bit ordered key | A distance | B distance) in shared memory laid out [position][thread]: conflict-free,
+//     16 KB per CTA, nothing spills.  A trie step costs ~25 instructions for 32 words.
+//
+// Ordered 16-bit key of a position (words of at most 31 units):  len << 7 | notreach << 6 | (63 - longest token);
+// relaxing an edge is one unsigned min, exactly like the 32/64-bit keys of dpt_dp_core.h.  A = distance to the largest
+// predecessor with minimal (len, notreach), B = distance to the largest predecessor with the minimal key: the backward
+// pass follows B until a token of the target length has been taken, then A (dp_tokenize.py:57-69,82-84), and turns every
+// chosen edge into an id by re-walking its bytes (trie lines are L1-hot by then).
+//
+// SPM rule: the word-initial U+2581 is one unit in front of the body (start 0 begins at the marker's trie node); a word
+// with a character that is no vocabulary entry (its normalised text is the "<0xHH>" spelling, tokenizer_utils.py:26-29)
+// is handed to the thread-per-word kernel through the `defer` list, as are words of more than 31 units (class 3) and the
+// odd words.
+#pragma once
+#include "dpt_pipe.h"
+
+namespace dpt {
+
+constexpr int PBL_THREADS = 128;
+constexpr int PBL_ROWS = 32;          // positions 0..31
+constexpr uint32_t PBL_NONE = 0xFFFFu;
+
+__device__ __forceinline__ uint32_t pbl_byte(const uint32_t (&wb)[8], const int k) {  // byte k of the window (k static)
+    return (wb[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+}
+
+template <bool kSpm>
+__device__ __forceinline__ void pbl_batch(const PipeParams& P, uint32_t* __restrict__ st, const int cls, const uint32_t nq,
+                                          const uint32_t batch, const int lane) {
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    constexpr int m = kSpm ? 1 : 0;
+    const uint32_t idx = batch * 32u + (uint32_t)lane;
+    bool valid = idx < nq;
+    uint32_t slot_item = 0;
+    int64_t pos = 0;
+    int len = 0;
+    if (valid) {
+        slot_item = P.pending[(size_t)cls * (size_t)P.pend_stride + idx];
+        const unsigned long long tag = P.tags[slot_item];
+        pos = pp_tag_pos(tag);
+        len = pp_tag_len(tag);
+        if (len + m > PBL_ROWS - 1) {  // cannot happen (the class says so); never index out of the rows
+            valid = false;
+            len = 0;
+        }
+    }
+    const int n = valid ? len + m : 0;  // units of the word = DP positions 0..n
+
+    // ---- the body bytes, zero-padded to 32, in eight registers --------------------------------------------------
+    uint32_t wb[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) wb[q] = 0;
+    if (valid) {
+        if (pos + 48 <= P.n_bytes) {
+            const uint8_t* base4 = P.text - ((uintptr_t)P.text & 3u);
+            const int64_t ro = pos + (int64_t)((uintptr_t)P.text & 3u);
+            uint32_t v[4];
+            pp_load16_raw(base4, ro, v);
+            wb[0] = v[0]; wb[1] = v[1]; wb[2] = v[2]; wb[3] = v[3];
+            if (len > 16) {
+                pp_load16_raw(base4, ro + 16, v);
+                wb[4] = v[0]; wb[5] = v[1]; wb[6] = v[2]; wb[7] = v[3];
+            }
+        } else {
+#pragma unroll
+            for (int qw = 0; qw < 8; ++qw) {  // (static indices: the window stays in registers)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (4 * qw + b < len) wb[qw] |= (uint32_t)P.text[pos + 4 * qw + b] << (8 * b);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {  // zero the bytes behind the word
+            const int rem = len - 4 * q;
+            if (rem < 4) wb[q] = rem <= 0 ? 0u : (wb[q] & ((1u << (8 * rem)) - 1u));
+        }
+    }
+    const int nmax = __reduce_max_sync(FULL, n);
+    uint32_t* const col = st + threadIdx.x;  // this thread's column: row p at col[p * PBL_THREADS]
+
+    // ---- rows: phantom keys (len_dp[i] = i, dp_tokenize.py:28; not reachable), NONE inside a character ---------------
+    {
+        uint32_t u = 0;  // unit index of the row being written
+#pragma unroll
+        for (int p = 0; p < PBL_ROWS; ++p) {
+            bool bnd;
+            if (!kSpm) {
+                bnd = true;
+            } else if (p <= 1 || p == n) {
+                bnd = true;  // in front of the marker, in front of the body (a stray continuation byte starts a character there), end
+            } else {
+                bnd = (pbl_byte(wb, p >= 1 ? p - 1 : 0) & 0xC0u) != 0x80u;
+            }
+            uint32_t key = PBL_NONE;
+            if (p <= n && bnd) key = p == 0 ? 63u : ((u << 7) | 0x7Fu);
+            if (p <= nmax) col[p * PBL_THREADS] = key;
+            if (p <= n && bnd) ++u;
+        }
+    }
+
+    // ---- forward: warp-uniform loop over the start positions ----------------------------------------------------
+    const uint32_t* __restrict__ da = P.V.da;
+    uint32_t Eprev = 0;     // SPM: end positions relaxed from the previous active start (out-of-vocabulary test)
+    bool have_prev = false, oov = false;
+#pragma unroll 1
+    for (int s = 0; s < nmax; ++s) {
+        const uint32_t rs = s < n ? col[s * PBL_THREADS] : PBL_NONE;
+        const uint32_t kj = rs & 0xFFFFu;
+        const bool active = kj != PBL_NONE;  // a unit boundary of this lane's word
+        if (kSpm && active) {
+            // the previous character [prev start, s) must itself be a vocabulary entry (else the normalised text spells it "<0xHH>")
+            if (have_prev && !((Eprev >> s) & 1u)) oov = true;
+            Eprev = 0;
+            have_prev = s >= 1;  // the marker (start 0) is always there (rule precondition)
+        }
+        const uint32_t hi1 = (kj & 0xFFC0u) + 0x80u, low = kj & 0x3Fu;
+        uint32_t entry = DPT_DA_ROOT_ENTRY, cl = 0;
+        int p = s;
+        bool alive = active;
+        // relax the edge s -> p with `cl` units
+        auto relax = [&](const bool term) {
+            if (__any_sync(FULL, term)) {
+                if (term) {
+                    const uint32_t row = col[p * PBL_THREADS];
+                    uint32_t bi = row & 0xFFFFu;
+                    if (bi != PBL_NONE) {
+                        const uint32_t lowe = 63u - cl;
+                        const uint32_t k = hi1 + (low < lowe ? low : lowe);
+                        uint32_t ab = row >> 16;
+                        const uint32_t d = (uint32_t)(p - s);
+                        if ((k >> 6) <= (bi >> 6)) ab = (ab & 0xFF00u) | d;
+                        if (k <= bi) {
+                            bi = k;
+                            ab = (ab & 0x00FFu) | (d << 8);
+                        }
+                        col[p * PBL_THREADS] = bi | (ab << 16);
+                        if (kSpm) Eprev |= 1u << p;
+                    }
+                }
+            }
+        };
+        if (kSpm && s == 0) {  // start 0 begins behind U+2581 (its trie node is part of the compiled vocabulary)
+            entry = P.V.marker_entry;
+            cl = 1;
+            p = 1;
+            relax(alive && (entry & DPT_DA_TERMINAL));
+        }
+#pragma unroll
+        for (int k = 0; k < PBL_ROWS - 1; ++k) {
+            const uint32_t c = pbl_byte(wb, k);
+            const uint32_t base = entry >> DPT_DA_BASE_SHIFT;
+            alive = alive && p < n && base != 0;
+            uint32_t e = 0;
+            if (alive) e = __ldg(da + base + c);
+            alive = alive && (e & DPT_DA_MATCH_MASK) == (DPT_DA_OCCUPIED | c);
+            if (!__any_sync(FULL, alive)) break;
+            if (alive) {
+                entry = e;
+                ++p;
+                cl += (!kSpm || (c & 0xC0u) != 0x80u) ? 1u : 0u;
+            }
+            relax(alive && (e & DPT_DA_TERMINAL));
+        }
+        if (!(kSpm && s == 0)) {  // the window moves on by one byte (start 0 of an SPM word reads the body from its first byte, like start 1)
+#pragma unroll
+            for (int q = 0; q < 7; ++q) wb[q] = __funnelshift_r(wb[q], wb[q + 1], 8);
+            wb[7] >>= 8;
+        }
+    }
+    if (kSpm && valid && have_prev && !((Eprev >> n) & 1u)) oov = true;
+    if (kSpm) {  // hand the words with out-of-vocabulary characters to the thread-per-word kernel
+        oov = oov && valid;
+        const uint32_t mo = __ballot_sync(FULL, oov);
+        if (mo) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&P.ctl->n_defer, (uint32_t)__popc(mo));
+            base = __shfl_sync(FULL, base, 0);
+            if (oov) P.defer[base + (uint32_t)__popc(mo & ((1u << lane) - 1u))] = slot_item;
+        }
+        if (oov) valid = false;
+    }
+
+    // ---- result: length, flags, ids ------------------------------------------------------------------------------------
+    const uint32_t kn = valid ? (col[n * PBL_THREADS] & 0xFFFFu) : PBL_NONE;
+    const uint32_t wl = kn >> 7;
+    const bool reach = valid && !(kn & 0x40u);
+    const uint32_t target = 63u - (kn & 0x3Fu);
+    const bool pooled = reach && wl > (uint32_t)RES_INLINE;
+    unsigned long long poff = 0;
+    {   // one pool allocation per warp
+        uint32_t inc = pooled ? wl : 0u;
+        const uint32_t mine = inc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d) inc += o;
+        }
+        const uint32_t total = __shfl_sync(FULL, inc, 31);
+        if (total) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&P.persist->pool_used, (unsigned long long)total);
+            base = __shfl_sync(FULL, base, 0);
+            poff = base + (inc - mine);
+        }
+    }
+    ResRec* const rec = &P.res[slot_item];
+    int i = reach ? n : 0, o = (int)wl;
+    bool got = false;
+    const uint8_t* __restrict__ body = P.text + pos;
+#pragma unroll 1
+    while (__any_sync(FULL, i > 0)) {
+        uint32_t d = 0;
+        if (i > 0) {
+            const uint32_t ab = col[i * PBL_THREADS] >> 16;
+            d = got ? (ab & 0xFFu) : (ab >> 8);
+            if (d == 0 || (int)d > i) {  // cannot happen on a reachable path; never spin on corrupt state
+                i = 0;
+                d = 0;
+            }
+        }
+        const int j = i - (int)d;
+        // re-walk the token [j, i): its trie slot gives the id
+        uint32_t entry = DPT_DA_ROOT_ENTRY, slot = 0, cl = 0;
+        int q = j - m, qe = i - m;  // body byte range
+        if (kSpm && j == 0 && d) {
+            entry = P.V.marker_entry;
+            slot = P.V.marker_slot;
+            cl = 1;
+            q = 0;
+        }
+        const int steps = d ? qe - q : 0;
+        const int smax = __reduce_max_sync(FULL, steps);
+        for (int r = 0; r < smax; ++r) {
+            if (r < steps) {
+                const uint32_t c = body[q + r];
+                slot = (entry >> DPT_DA_BASE_SHIFT) + c;
+                entry = __ldg(da + slot);
+                cl += (!kSpm || (c & 0xC0u) != 0x80u) ? 1u : 0u;
+            }
+        }
+        if (d) {
+            const int32_t id = __ldg(P.V.slot_id + slot);
+            --o;
+            if (pooled) {
+                if ((int64_t)(poff + (unsigned long long)o) < P.pool_cap) P.pool[poff + (unsigned long long)o] = id;
+            } else if (o >= 0 && o < RES_INLINE) {
+                rec->ids[o] = id;
+            }
+            if (!got && cl == target) got = true;
+            i = j;
+        }
+    }
+    if (valid) {
+        rec->meta = (wl & 0xFFFFFFu) | (reach ? 0u : RES_UNTOK) | (pooled ? RES_POOLED : 0u);
+        if (pooled) {
+            rec->ids[0] = (int32_t)(uint32_t)(poff & 0xFFFFFFFFull);
+            rec->ids[1] = (int32_t)(uint32_t)(poff >> 32);
+        }
+    }
+}
+
+// Persistent warps over batches of 32 words of one length class, longest class first (static striding: the words of a
+// class cost about the same).
+template <bool kSpm>
+__device__ __forceinline__ void pbl_kernel(const PipeParams& P, uint32_t* st) {
+    const int lane = (int)(threadIdx.x & 31);
+    const uint32_t nq2 = pb_queue_len(P, 2), nq1 = pb_queue_len(P, 1), nq0 = pb_queue_len(P, 0);
+    const uint32_t nb2 = (nq2 + 31) / 32, nb1 = (nq1 + 31) / 32, nb0 = (nq0 + 31) / 32;
+    const uint32_t total = nb2 + nb1 + nb0;
+    const uint32_t nw = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < total; g += nw) {
+        int cls = 2;
+        uint32_t nq = nq2, b = g;
+        if (g >= nb2 + nb1) {
+            cls = 0;
+            nq = nq0;
+            b = g - nb2 - nb1;
+        } else if (g >= nb2) {
+            cls = 1;
+            nq = nq1;
+            b = g - nb2;
+        }
+        pbl_batch<kSpm>(P, st, cls, nq, b, lane);  // (one call site: the unrolled walk is ~1.5 k instructions)
+        __syncwarp();
+    }
+}
+
+}  // namespace dpt

@@ -7,6 +7,7 @@
 #include <string>
 
 struct dpt_vocab;
+struct dpt_synth_params;
 
 namespace dpt {
 
@@ -70,5 +71,11 @@ int pad_batch(const int32_t* d_ids_a, const int64_t* d_offs_a, const int32_t* d_
 int lattice_word(const dpt_vocab* v, const uint8_t* d_text, int32_t n_bytes, const uint8_t* d_unit_starts,
                  int32_t* d_len_dp, int32_t* d_pred_offs, int32_t* d_pred, int32_t pred_cap, int32_t* d_n_out,
                  int32_t* d_unit_of, cudaStream_t st);
+
+// synthetic corpus generator on the device (synth.cu; measurement support, not on the tokenization path)
+int synth_run(const uint8_t* a_bytes, const int64_t* a_offs, const uint32_t* a_cdf, int32_t a_n, const uint8_t* b_bytes,
+              const int64_t* b_offs, const uint32_t* b_cdf, int32_t b_n, const dpt_synth_params* sp, int64_t doc_base,
+              int64_t n_docs, int64_t* d_doc_len, const int64_t* d_doc_offs, uint8_t* d_text, cudaStream_t st,
+              std::string& err);
 
 }  // namespace dpt

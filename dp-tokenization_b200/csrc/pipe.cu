@@ -8,7 +8,7 @@
 
 #include "../../include/dptok.h"
 #include "dpt_pipe.h"
-#include "dpt_dp_coop.cuh"
+#include "dpt_dp_lock.cuh"
 #include "kernels.h"
 #include "vocab.h"
 
@@ -22,8 +22,8 @@
 #ifndef DPT_PB_CTAS
 #define DPT_PB_CTAS 12
 #endif
-#ifndef DPT_PBC_CTAS
-#define DPT_PBC_CTAS 8
+#ifndef DPT_PBL_CTAS
+#define DPT_PBL_CTAS 8
 #endif
 #ifndef DPT_PC_CTAS
 #define DPT_PC_CTAS 4
@@ -95,6 +95,7 @@ struct DevBlk {
     __device__ __forceinline__ bool in_first_warp() const { return threadIdx.x < 32; }
     __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31); }
     __device__ __forceinline__ int warp_width() const { return 32; }
+    __device__ __forceinline__ unsigned grid_warps() const { return gridDim.x * (blockDim.x >> 5); }
     // first i in [0, n] with a[i] >= x (a sorted), by the 32 lanes of one warp: every round probes 32 split points
     __device__ __forceinline__ int64_t warp_lower_bound(const int64_t* a, int64_t n, int64_t x) const {
         const int lane = (int)(threadIdx.x & 31);
@@ -194,10 +195,14 @@ __global__ void __launch_bounds__(PA_THREADS, DPT_PABL_CTAS) k_scan_dedup_bl(con
     pa_kernel<DevBlk, false>(blk, P, S);
 }
 
-// the cooperative DP (dpt_dp_coop.cuh): length classes 0..2, i.e. every word that fits a warp
-__global__ void __launch_bounds__(PBC_THREADS, DPT_PBC_CTAS) k_dp_coop(const __grid_constant__ PipeParams P) {
-    __shared__ uint32_t slot_smem[(PBC_THREADS / 32) * 32 * 32];
-    pbc_kernel(P, slot_smem);
+// the lock-step DP (dpt_dp_lock.cuh): length classes 0..2, i.e. every word of at most 31 units
+__global__ void __launch_bounds__(PBL_THREADS, DPT_PBL_CTAS) k_dp_lock_spm(const __grid_constant__ PipeParams P) {
+    __shared__ uint32_t st[PBL_ROWS * PBL_THREADS];
+    pbl_kernel<true>(P, st);
+}
+__global__ void __launch_bounds__(PBL_THREADS, DPT_PBL_CTAS) k_dp_lock_bl(const __grid_constant__ PipeParams P) {
+    __shared__ uint32_t st[PBL_ROWS * PBL_THREADS];
+    pbl_kernel<false>(P, st);
 }
 
 // thread-per-word DP with local-memory state: odd words, words longer than a warp, words the cooperative kernel deferred
@@ -253,7 +258,7 @@ static TableSizes table_sizes(int64_t n_bytes_total, int64_t word_cap_total, int
     int64_t s = 4096;
     while (s < want) s <<= 1;
     z.n_slots = s;
-    z.pool_cap = worst ? 6 * n_bytes_total + 3 * word_cap_total + 64 : n_bytes_total / 4 + 65536;
+    z.pool_cap = worst ? 8 * n_bytes_total + 5 * word_cap_total + 64 : n_bytes_total / 4 + 65536;
     return z;
 }
 static RangeSizes range_sizes(int64_t range_bytes, int64_t word_cap, int worst) {
@@ -447,13 +452,16 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
     }
     if (do_dp) {
     {
-        ProfScope prof("k_dp_coop", st);
-        static int bc_ctas = 0;  // CTAs per SM of the cooperative kernel's grid (development knob: DPT_BC_GRID)
-        if (!bc_ctas) {
-            const char* e = getenv("DPT_BC_GRID");
-            bc_ctas = e && atoi(e) > 0 ? atoi(e) : DPT_PBC_CTAS;
+        ProfScope prof(P.spm ? "k_dp_lock_spm" : "k_dp_lock_bl", st);
+        static int bl_ctas = 0;  // CTAs per SM of the lock-step kernel's grid (development knob: DPT_BL_GRID)
+        if (!bl_ctas) {
+            const char* e = getenv("DPT_BL_GRID");
+            bl_ctas = e && atoi(e) > 0 ? atoi(e) : DPT_PBL_CTAS;
         }
-        k_dp_coop<<<(unsigned)(sm_count * bc_ctas), PBC_THREADS, 0, st>>>(P);
+        if (P.spm)
+            k_dp_lock_spm<<<(unsigned)(sm_count * bl_ctas), PBL_THREADS, 0, st>>>(P);
+        else
+            k_dp_lock_bl<<<(unsigned)(sm_count * bl_ctas), PBL_THREADS, 0, st>>>(P);
         ++g_launches;
     }
     {
@@ -461,7 +469,7 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
         static int b_ctas = 0;  // CTAs per SM of kernel B's grid (development knob: DPT_B_GRID)
         if (!b_ctas) {
             const char* e = getenv("DPT_B_GRID");
-            b_ctas = e && atoi(e) > 0 ? atoi(e) : 4;
+            b_ctas = e && atoi(e) > 0 ? atoi(e) : 8;
         }
         k_dp_distinct<<<(unsigned)(sm_count * b_ctas), PB_THREADS, 0, st>>>(P);
         ++g_launches;

@@ -36,6 +36,11 @@ class VocabInfo(C.Structure):
                 ("device", C.c_int32), ("blob_bytes", C.c_int64)]
 
 
+class SynthParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("words_lo", C.c_int32), ("words_hi", C.c_int32), ("sentence_mean", C.c_int32),
+                ("flags", C.c_int32), ("frac_b", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 if not os.path.isfile(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} not found: build the CUDA extension first "
@@ -73,6 +78,7 @@ SIGNATURES = {
     "dpt_roundtrip_check": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _p, _p]),
     "dpt_narrow_ids_u16": (C.c_int, [_p, _p, _i64, _p, _p, _p]),
     "dpt_pad_batch": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _p, _p, _p, _p]),
+    "dpt_synth_corpus": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _i32, _p, _i64, _i64, _p, _p, _p, _p]),
     "dpt_last_error": (C.c_char_p, []),
     "dpt_version": (C.c_char_p, []),
     "dpt_launch_count": (_i64, []),

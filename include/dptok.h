@@ -290,6 +290,29 @@ int dpt_pad_batch(const int32_t* d_ids_a, const int64_t* d_doc_tok_offs_a,
 int dpt_narrow_ids_u16(const int32_t* d_ids, const int64_t* d_n, int64_t cap, uint16_t* d_out, int64_t* d_overflow,
                        void* stream);
 
+/* ---- measurement support (BASELINE.json configs[3] / configs[4]): synthetic corpora generated
+ *      ON THE DEVICE from a counter-based RNG, so a 1 GB corpus of long documents or 1.25 GB of Arabic-script text per
+ *      GPU never crosses PCIe.  Not part of the tokenization path (the reference reads its inputs from datasets:
+ *      main_analyze_s2orc.py:253-255, main_biomed_translation.py:71-73, dialect_arabic.py:24); a document is a pure
+ *      function of (seed, global document index), so every rank can generate the same corpus or its own range of it.
+ *      Lexicon = word strings (d_lex_bytes / d_lex_offs[n_types+1]) + d_lex_cdf[n_types], the cumulative word
+ *      probabilities scaled to 32 bits; an optional second lexicon B is used for a document with probability
+ *      frac_b / 2^32 (e.g. Arabic-script documents among English ones).
+ *      Two passes: d_doc_offs == NULL writes the byte length of each document to d_doc_len[n_docs]; the caller forms
+ *      the offsets (exclusive prefix sum) and calls again with d_doc_offs[n_docs] and d_text to fill the bytes. */
+typedef struct dpt_synth_params {
+    uint64_t seed;
+    int32_t words_lo, words_hi;  /* words per document, uniform                                            */
+    int32_t sentence_mean;       /* a sentence ends after each word with probability 1 / sentence_mean     */
+    int32_t flags;               /* bit 0: lexicon A is ASCII (capitalise sentence starts), bit 1: B is    */
+    uint32_t frac_b;             /* P(document uses lexicon B) * 2^32                                      */
+    uint32_t reserved;
+} dpt_synth_params;
+int dpt_synth_corpus(const uint8_t* d_lex_a_bytes, const int64_t* d_lex_a_offs, const uint32_t* d_lex_a_cdf, int32_t n_a,
+                     const uint8_t* d_lex_b_bytes, const int64_t* d_lex_b_offs, const uint32_t* d_lex_b_cdf, int32_t n_b,
+                     const dpt_synth_params* params, int64_t doc_base, int64_t n_docs,
+                     int64_t* d_doc_len, const int64_t* d_doc_offs, uint8_t* d_text, void* stream);
+
 const char* dpt_last_error(void);
 const char* dpt_version(void);
 /* number of kernel launches issued by this library in the calling process (bench "gpu_launches") */

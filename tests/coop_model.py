@@ -29,7 +29,7 @@ def solve(body: bytes, vocab: Dict[bytes, int], spm: bool) -> Optional[Tuple[Lis
     assert 1 <= n <= 31
     # lane t: the byte string it owns
     own = [MARK if (spm and t == 0) else bytes([body[t - m]]) for t in range(n)]
-    isstart = [True if (spm and t == 0) else (not spm or (body[t - m] & 0xC0) != 0x80) for t in range(n)]
+    isstart = [True if t <= m else (not spm or (body[t - m] & 0xC0) != 0x80) for t in range(n)]
     Bm = sum(1 << t for t in range(n) if isstart[t]) | (1 << n)
     # walks: E_t = ends of vocabulary entries that start at t (the kernel finds them by walking the trie)
     E = [0] * n

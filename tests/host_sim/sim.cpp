@@ -57,6 +57,7 @@ struct HostBlk {
     bool in_first_warp() const { return tid_ == 0; }  // an emulated warp is one thread
     int lane() const { return 0; }
     int warp_width() const { return 1; }
+    unsigned grid_warps() const { return 0; }
     int64_t warp_lower_bound(const int64_t* a, int64_t n, int64_t x) const { return dpt::pp_lower_bound(a, n, x); }
     unsigned long long warp_take(unsigned long long* cursor) const { return __atomic_fetch_add(cursor, 1ull, __ATOMIC_RELAXED); }
     bool warp_any(bool p) const { return p; }
