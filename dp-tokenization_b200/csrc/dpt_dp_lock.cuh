@@ -12,13 +12,16 @@
 //     no lane's walk is alive - so the lanes never diverge, the word's bytes sit in a REGISTER window that shifts by one
 //     byte per start (static byte extraction, no indexed loads), and the state of a position is ONE 32-bit word
 //     (16-bit ordered key | A distance | B distance) in shared memory laid out [position][thread]: conflict-free,
-//     16 KB per CTA, nothing spills.  A trie step costs ~25 instructions for 32 words.
+//     16 KB per CTA, nothing spills.
+//   * a CTA takes chunks of PBL_CHUNK words from a ticket and counting-sorts each chunk by word length in shared
+//     memory before its warps solve it: the outer loop of a warp runs to the LONGEST of its 32 words.
 //
 // Ordered 16-bit key of a position (words of at most 31 units):  len << 7 | notreach << 6 | (63 - longest token);
-// relaxing an edge is one unsigned min, exactly like the 32/64-bit keys of dpt_dp_core.h.  A = distance to the largest
-// predecessor with minimal (len, notreach), B = distance to the largest predecessor with the minimal key: the backward
-// pass follows B until a token of the target length has been taken, then A (dp_tokenize.py:57-69,82-84), and turns every
-// chosen edge into an id by re-walking its bytes (trie lines are L1-hot by then).
+// relaxing an edge is one unsigned min, exactly like the 32/64-bit keys of dpt_dp_core.h.  Key 0 = "inside a
+// character" (no real key is 0: the origin is 63): such a row never wins a comparison, so the relaxation needs no test
+// for it.  A = distance to the largest predecessor with minimal (len, notreach), B = distance to the largest
+// predecessor with the minimal key: the backward pass follows B until a token of the target length has been taken, then A
+// (dp_tokenize.py:57-69,82-84), and turns every chosen edge into an id by re-walking its bytes (trie lines are L1-hot).
 //
 // SPM rule: the word-initial U+2581 is one unit in front of the body (start 0 begins at the marker's trie node); a word
 // with a character that is no vocabulary entry (its normalised text is the "<0xHH>" spelling, tokenizer_utils.py:26-29)
@@ -30,26 +33,45 @@
 namespace dpt {
 
 constexpr int PBL_THREADS = 128;
-constexpr int PBL_ROWS = 32;          // positions 0..31
-constexpr uint32_t PBL_NONE = 0xFFFFu;
+constexpr int PBL_ROWS = 32;   // positions 0..31
+#ifndef DPT_PBL_CHUNK
+#define DPT_PBL_CHUNK 256
+#endif
+constexpr int PBL_CHUNK = DPT_PBL_CHUNK;  // words a CTA sorts and solves at a time (a multiple of PBL_THREADS)
+
+struct PblSmem {
+    uint32_t st[PBL_ROWS * PBL_THREADS];    // DP state, [position][thread]
+    unsigned long long tag[PBL_CHUNK];      // the chunk's words sorted by length: table tag (position, length) ...
+    uint32_t slot[PBL_CHUNK];               // ... and table slot
+    uint32_t hist[PBL_ROWS + 1];            // words per length, then the bins' start offsets
+    uint32_t chunk;
+};
 
 __device__ __forceinline__ uint32_t pbl_byte(const uint32_t (&wb)[8], const int k) {  // byte k of the window (k static)
     return (wb[k >> 2] >> (8 * (k & 3))) & 0xFFu;
 }
+// e = pred ? *p : 0 as ONE predicated load (the compiler turns the C form into a divergent branch: BSSY / BRA / BSYNC)
+__device__ __forceinline__ uint32_t pbl_ldg_if(const uint32_t* p, bool pred) {
+    uint32_t e;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.u32 %0, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}"
+        : "=r"(e)
+        : "l"(p), "r"((uint32_t)pred));
+    return e;
+}
 
+// One batch: 32 words (one per lane) of the sorted chunk.
 template <bool kSpm>
-__device__ __forceinline__ void pbl_batch(const PipeParams& P, uint32_t* __restrict__ st, const int cls, const uint32_t nq,
-                                          const uint32_t batch, const int lane) {
+__device__ __forceinline__ void pbl_batch(const PipeParams& P, PblSmem& S, const int first, const int count, const int lane) {
     constexpr uint32_t FULL = 0xFFFFFFFFu;
     constexpr int m = kSpm ? 1 : 0;
-    const uint32_t idx = batch * 32u + (uint32_t)lane;
-    bool valid = idx < nq;
+    bool valid = first + lane < count;
     uint32_t slot_item = 0;
     int64_t pos = 0;
     int len = 0;
     if (valid) {
-        slot_item = P.pending[(size_t)cls * (size_t)P.pend_stride + idx];
-        const unsigned long long tag = P.tags[slot_item];
+        slot_item = S.slot[first + lane];
+        const unsigned long long tag = S.tag[first + lane];
         pos = pp_tag_pos(tag);
         len = pp_tag_len(tag);
         if (len + m > PBL_ROWS - 1) {  // cannot happen (the class says so); never index out of the rows
@@ -89,9 +111,9 @@ __device__ __forceinline__ void pbl_batch(const PipeParams& P, uint32_t* __restr
         }
     }
     const int nmax = __reduce_max_sync(FULL, n);
-    uint32_t* const col = st + threadIdx.x;  // this thread's column: row p at col[p * PBL_THREADS]
+    uint32_t* const col = S.st + threadIdx.x;  // this thread's column: row p at col[p * PBL_THREADS]
 
-    // ---- rows: phantom keys (len_dp[i] = i, dp_tokenize.py:28; not reachable), NONE inside a character ---------------
+    // ---- rows: phantom keys (len_dp[i] = i, dp_tokenize.py:28; not reachable), 0 inside a character ------------------
     {
         uint32_t u = 0;  // unit index of the row being written
 #pragma unroll
@@ -104,7 +126,7 @@ __device__ __forceinline__ void pbl_batch(const PipeParams& P, uint32_t* __restr
             } else {
                 bnd = (pbl_byte(wb, p >= 1 ? p - 1 : 0) & 0xC0u) != 0x80u;
             }
-            uint32_t key = PBL_NONE;
+            uint32_t key = 0;
             if (p <= n && bnd) key = p == 0 ? 63u : ((u << 7) | 0x7Fu);
             if (p <= nmax) col[p * PBL_THREADS] = key;
             if (p <= n && bnd) ++u;
@@ -117,9 +139,8 @@ __device__ __forceinline__ void pbl_batch(const PipeParams& P, uint32_t* __restr
     bool have_prev = false, oov = false;
 #pragma unroll 1
     for (int s = 0; s < nmax; ++s) {
-        const uint32_t rs = s < n ? col[s * PBL_THREADS] : PBL_NONE;
-        const uint32_t kj = rs & 0xFFFFu;
-        const bool active = kj != PBL_NONE;  // a unit boundary of this lane's word
+        const uint32_t kj = (s < n ? col[s * PBL_THREADS] : 0u) & 0xFFFFu;
+        const bool active = kj != 0u;  // a unit boundary of this lane's word
         if (kSpm && active) {
             // the previous character [prev start, s) must itself be a vocabulary entry (else the normalised text spells it "<0xHH>")
             if (have_prev && !((Eprev >> s) & 1u)) oov = true;
@@ -130,25 +151,22 @@ __device__ __forceinline__ void pbl_batch(const PipeParams& P, uint32_t* __restr
         uint32_t entry = DPT_DA_ROOT_ENTRY, cl = 0;
         int p = s;
         bool alive = active;
-        // relax the edge s -> p with `cl` units
+        // relax the edge s -> p (cl units) for the lanes with `term`; rows inside a character hold key 0 and never lose
         auto relax = [&](const bool term) {
             if (__any_sync(FULL, term)) {
-                if (term) {
-                    const uint32_t row = col[p * PBL_THREADS];
-                    uint32_t bi = row & 0xFFFFu;
-                    if (bi != PBL_NONE) {
-                        const uint32_t lowe = 63u - cl;
-                        const uint32_t k = hi1 + (low < lowe ? low : lowe);
-                        uint32_t ab = row >> 16;
-                        const uint32_t d = (uint32_t)(p - s);
-                        if ((k >> 6) <= (bi >> 6)) ab = (ab & 0xFF00u) | d;
-                        if (k <= bi) {
-                            bi = k;
-                            ab = (ab & 0x00FFu) | (d << 8);
-                        }
-                        col[p * PBL_THREADS] = bi | (ab << 16);
-                        if (kSpm) Eprev |= 1u << p;
-                    }
+                uint32_t* const rp = col + p * PBL_THREADS;
+                const uint32_t row = *rp;
+                const uint32_t bi = row & 0xFFFFu;
+                const uint32_t lowe = cl ^ 0x3Fu;  // 63 - cl
+                const uint32_t k = hi1 + (low < lowe ? low : lowe);
+                const uint32_t d = (uint32_t)(p - s);
+                const bool pa = term && k <= (bi | 0x3Fu);  // (k >> 6) <= (bi >> 6)
+                const bool pb = term && k <= bi;
+                uint32_t nr = (row & 0xFF00FFFFu) | (d << 16);          // A = d
+                if (pb) nr = (nr & 0x00FF0000u) | k | (d << 24);       // key = k, B = d
+                if (pa) {
+                    *rp = nr;
+                    if (kSpm) Eprev |= 1u << p;
                 }
             }
         };
@@ -158,21 +176,38 @@ __device__ __forceinline__ void pbl_batch(const PipeParams& P, uint32_t* __restr
             p = 1;
             relax(alive && (entry & DPT_DA_TERMINAL));
         }
+        // The walk: groups of four steps peel the bytes off a running copy of the window (a fully unrolled 31-step walk let
+        // the compiler keep every step's derived values live at once: > 128 registers).
+        uint32_t ww[8];
 #pragma unroll
-        for (int k = 0; k < PBL_ROWS - 1; ++k) {
-            const uint32_t c = pbl_byte(wb, k);
-            const uint32_t base = entry >> DPT_DA_BASE_SHIFT;
-            alive = alive && p < n && base != 0;
-            uint32_t e = 0;
-            if (alive) e = __ldg(da + base + c);
-            alive = alive && (e & DPT_DA_MATCH_MASK) == (DPT_DA_OCCUPIED | c);
-            if (!__any_sync(FULL, alive)) break;
-            if (alive) {
-                entry = e;
-                ++p;
-                cl += (!kSpm || (c & 0xC0u) != 0x80u) ? 1u : 0u;
+        for (int q = 0; q < 8; ++q) ww[q] = wb[q];
+        bool open = true;
+#pragma unroll 1
+        for (int g = 0; g < 8 && open; ++g) {
+            uint32_t wcur = ww[0];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t c = wcur & 0xFFu;
+                wcur >>= 8;
+                const uint32_t base = entry >> DPT_DA_BASE_SHIFT;
+                alive = alive && p < n && base != 0;
+                const uint32_t e = pbl_ldg_if(da + base + c, alive);
+                alive = alive && (e & DPT_DA_MATCH_MASK) == (DPT_DA_OCCUPIED | c);
+                if (!__any_sync(FULL, alive)) {
+                    open = false;
+                    break;
+                }
+                if (alive) {
+                    entry = e;
+                    ++p;
+                    if (kSpm) cl += (c & 0xC0u) != 0x80u ? 1u : 0u;
+                }
+                if (!kSpm) cl = (uint32_t)(p - s);
+                relax(alive && (e & DPT_DA_TERMINAL));
             }
-            relax(alive && (e & DPT_DA_TERMINAL));
+#pragma unroll
+            for (int q = 0; q < 7; ++q) ww[q] = ww[q + 1];
+            ww[7] = 0;
         }
         if (!(kSpm && s == 0)) {  // the window moves on by one byte (start 0 of an SPM word reads the body from its first byte, like start 1)
 #pragma unroll
@@ -194,7 +229,7 @@ __device__ __forceinline__ void pbl_batch(const PipeParams& P, uint32_t* __restr
     }
 
     // ---- result: length, flags, ids ------------------------------------------------------------------------------------
-    const uint32_t kn = valid ? (col[n * PBL_THREADS] & 0xFFFFu) : PBL_NONE;
+    const uint32_t kn = valid ? (col[n * PBL_THREADS] & 0xFFFFu) : 0xFFFFu;
     const uint32_t wl = kn >> 7;
     const bool reach = valid && !(kn & 0x40u);
     const uint32_t target = 63u - (kn & 0x3Fu);
@@ -272,29 +307,80 @@ __device__ __forceinline__ void pbl_batch(const PipeParams& P, uint32_t* __restr
     }
 }
 
-// Persistent warps over batches of 32 words of one length class, longest class first (static striding: the words of a
-// class cost about the same).
+// Persistent CTAs: a chunk of PBL_CHUNK words of the concatenated queues (classes 2, 1, 0) from a ticket -> counting
+// sort by length in shared memory -> the warps solve its batches of 32, interleaved so every warp gets long and short ones.
 template <bool kSpm>
-__device__ __forceinline__ void pbl_kernel(const PipeParams& P, uint32_t* st) {
-    const int lane = (int)(threadIdx.x & 31);
+__device__ __forceinline__ void pbl_kernel(const PipeParams& P, PblSmem& S) {
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nq2 = pb_queue_len(P, 2), nq1 = pb_queue_len(P, 1), nq0 = pb_queue_len(P, 0);
-    const uint32_t nb2 = (nq2 + 31) / 32, nb1 = (nq1 + 31) / 32, nb0 = (nq0 + 31) / 32;
-    const uint32_t total = nb2 + nb1 + nb0;
-    const uint32_t nw = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < total; g += nw) {
-        int cls = 2;
-        uint32_t nq = nq2, b = g;
-        if (g >= nb2 + nb1) {
-            cls = 0;
-            nq = nq0;
-            b = g - nb2 - nb1;
-        } else if (g >= nb2) {
-            cls = 1;
-            nq = nq1;
-            b = g - nb2;
+    const uint32_t total = nq2 + nq1 + nq0;
+    const uint32_t n_chunks = (total + PBL_CHUNK - 1) / PBL_CHUNK;
+    for (;;) {
+        if (tid == 0) S.chunk = atomicAdd(&P.ctl->lock_ticket, 1u);
+        if (tid <= PBL_ROWS) S.hist[tid] = 0;
+        __syncthreads();
+        const uint32_t chunk = S.chunk;
+        if (chunk >= n_chunks) break;
+        const uint32_t c0 = chunk * PBL_CHUNK;
+        const int count = (int)(total - c0 < (uint32_t)PBL_CHUNK ? total - c0 : (uint32_t)PBL_CHUNK);
+        // this thread's words of the chunk
+        uint32_t slot[PBL_CHUNK / PBL_THREADS];
+        unsigned long long tag[PBL_CHUNK / PBL_THREADS];
+        uint32_t rank[PBL_CHUNK / PBL_THREADS];
+#pragma unroll
+        for (int r = 0; r < PBL_CHUNK / PBL_THREADS; ++r) {
+            const int k = tid + r * PBL_THREADS;
+            slot[r] = 0;
+            tag[r] = 0;
+            rank[r] = 0;
+            if (k < count) {
+                uint32_t g = c0 + (uint32_t)k;
+                int cls = 2;
+                if (g >= nq2 + nq1) {
+                    cls = 0;
+                    g -= nq2 + nq1;
+                } else if (g >= nq2) {
+                    cls = 1;
+                    g -= nq2;
+                }
+                slot[r] = P.pending[(size_t)cls * (size_t)P.pend_stride + g];
+            }
         }
-        pbl_batch<kSpm>(P, st, cls, nq, b, lane);  // (one call site: the unrolled walk is ~1.5 k instructions)
-        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < PBL_CHUNK / PBL_THREADS; ++r)
+            if (tid + r * PBL_THREADS < count) tag[r] = P.tags[slot[r]];
+#pragma unroll
+        for (int r = 0; r < PBL_CHUNK / PBL_THREADS; ++r)
+            if (tid + r * PBL_THREADS < count) {
+                const int len = pp_tag_len(tag[r]);
+                rank[r] = atomicAdd(&S.hist[len < PBL_ROWS ? len : PBL_ROWS], 1u);
+            }
+        __syncthreads();
+        if (warp == 0) {  // bins -> start offsets, longest words first: lane l owns length 31 - l, the bin of length >= 32 stays empty
+            const uint32_t h = S.hist[PBL_ROWS - 1 - lane];
+            uint32_t inc = h;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            S.hist[PBL_ROWS - 1 - lane] = inc - h;
+            if (lane == 31) S.hist[PBL_ROWS] = inc;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < PBL_CHUNK / PBL_THREADS; ++r)
+            if (tid + r * PBL_THREADS < count) {
+                const int len = pp_tag_len(tag[r]);
+                const uint32_t at = S.hist[len < PBL_ROWS ? len : PBL_ROWS] + rank[r];
+                if (at < (uint32_t)PBL_CHUNK) {
+                    S.slot[at] = slot[r];
+                    S.tag[at] = tag[r];
+                }
+            }
+        __syncthreads();
+        for (int b = warp; b * 32 < count; b += PBL_THREADS / 32) pbl_batch<kSpm>(P, S, b * 32, count, lane);
+        __syncthreads();
     }
 }
 

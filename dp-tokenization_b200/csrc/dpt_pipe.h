@@ -110,7 +110,9 @@ struct PipeCtl {  // device-side counters, zeroed by the launcher
     unsigned int n_odd, n_long;
     unsigned int n_defer, pad0;          // words the cooperative DP kernel handed to the thread-per-word kernel
     unsigned long long lp_used, n_words, n_untok, n_too_long;
-    unsigned long long b_cursor;  // next unclaimed item of kernel B's work list
+    unsigned long long b_cursor;  // next unclaimed item of kernel B's work list (thread-per-word kernel, first launch)
+    unsigned long long b_cursor2; // ... second launch (the words the lock-step kernel deferred)
+    unsigned int lock_ticket, pad1;  // next unclaimed chunk of the lock-step kernel
 };
 
 struct PipePersist {  // survives the launches of one chunked call (same lifetime as the word table)
@@ -148,7 +150,8 @@ struct PipeParams {
     int32_t* pool;                // pool_cap ids of words with more than 7 tokens (persistent, like the table)
     uint32_t* longq;              // n_slots + odd_cap
     uint32_t* defer;              // pend_stride table slots (cooperative DP kernel -> thread-per-word kernel)
-    int32_t coop;                 // 1: length classes 0..2 are solved by the cooperative kernel (device); 0: host emulation
+    int32_t coop;                 // work list of the thread-per-word kernel: 0 = everything (host emulation); 1 = odd words + words
+                                  // of more than 31 units (beside the lock-step kernel); 2 = the words the lock-step kernel deferred
     uint8_t* lp_norm;             // long-word scratch: lp_cap positions
     uint64_t* lp_best;
     uint16_t* lp_a;
@@ -1006,18 +1009,23 @@ struct PbItem {
     bool marker;
     ResRec* out;
 };
-// Work list of the thread-per-word kernel.  With the cooperative kernel in front (P.coop, the device): odd words, the
-// words longer than a warp (class 3), then the words the cooperative kernel deferred (out-of-vocabulary characters that
-// expand to "<0xHH>" text).  Without it (host emulation): odd words, then every length class from longest to shortest.
+// Work list of the thread-per-word kernel.  On the device the lock-step kernel (dpt_dp_lock.cuh) solves the length
+// classes 0..2; this kernel runs twice: P.coop == 1, BESIDE the lock-step kernel on a side stream: the odd words and the
+// words of more than 31 units (class 3); P.coop == 2, after it: the words the lock-step kernel deferred
+// (out-of-vocabulary characters that expand to "<0xHH>" text).  P.coop == 0 (host emulation): odd words, then every
+// length class from longest to shortest.
 DPT_PIPE_FN uint64_t pb_list_len(const PipeParams& P, const uint32_t* npc, uint32_t n_odd, uint32_t n_defer) {
+    if (P.coop == 2) return n_defer;
     uint64_t total = n_odd;
-    if (P.coop) return total + npc[PB_CLASSES - 1] + n_defer;
+    if (P.coop == 1) return total + npc[PB_CLASSES - 1];
     for (int c = 0; c < PB_CLASSES; ++c) total += npc[c];
     return total;
 }
-DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint64_t i, const uint32_t* npc, uint32_t n_odd) {
+// a word of the long-word queue: bit 31 = odd word index, else table slot
+DPT_PIPE_FN PbItem pb_item_tagged(const PipeParams& P, uint32_t v) {
     PbItem it;
-    if (i < n_odd) {
+    if (v & 0x80000000u) {
+        const uint32_t i = v & 0x7FFFFFFFu;
         const OddWord o = P.odd[i];
         it.pos = o.pos;
         it.end = o.pos + o.len;
@@ -1025,11 +1033,26 @@ DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint64_t i, const uint32_t* npc,
         it.out = &P.odd_res[i];
         return it;
     }
-    i -= n_odd;
+    const unsigned long long t = P.tags[v];
+    it.pos = pp_tag_pos(t);
+    it.end = it.pos + pp_tag_len(t);
+    it.marker = P.spm != 0;
+    it.out = &P.res[v];
+    return it;
+}
+// item i of the work list; *tagged = its long-word-queue form
+DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint64_t i, const uint32_t* npc, uint32_t n_odd, uint32_t* tagged) {
+    PbItem it;
+    if (P.coop != 2 && i < n_odd) {
+        *tagged = 0x80000000u | (uint32_t)i;
+        return pb_item_tagged(P, *tagged);
+    }
+    if (P.coop != 2) i -= n_odd;
     uint32_t slot;
-    if (P.coop) {
-        slot = i < npc[PB_CLASSES - 1] ? P.pending[(size_t)(PB_CLASSES - 1) * (size_t)P.pend_stride + i]
-                                       : P.defer[i - npc[PB_CLASSES - 1]];
+    if (P.coop == 2) {
+        slot = P.defer[i];
+    } else if (P.coop == 1) {
+        slot = P.pending[(size_t)(PB_CLASSES - 1) * (size_t)P.pend_stride + i];
     } else {
         uint32_t cls = PB_CLASSES - 1;
         while (cls > 0 && i >= npc[cls]) {
@@ -1038,12 +1061,8 @@ DPT_PIPE_FN PbItem pb_item(const PipeParams& P, uint64_t i, const uint32_t* npc,
         }
         slot = P.pending[(size_t)cls * (size_t)P.pend_stride + i];
     }
-    const unsigned long long t = P.tags[slot];
-    it.pos = pp_tag_pos(t);
-    it.end = it.pos + pp_tag_len(t);
-    it.marker = P.spm != 0;
-    it.out = &P.res[slot];
-    return it;
+    *tagged = slot;
+    return pb_item_tagged(P, slot);
 }
 
 // One thread per distinct word, DP state in local memory; the forward pass is the resumable state machine of
@@ -1100,16 +1119,17 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
         if (more) {
             // lanes without a word take the next items of the list (one atomic per warp)
             const bool ask = !have && (!spread || blk.lane() == 0);
-            const uint64_t idx = blk.warp_take_n(&P.ctl->b_cursor, ask);
+            const uint64_t idx = blk.warp_take_n(P.coop == 2 ? &P.ctl->b_cursor2 : &P.ctl->b_cursor, ask);
             const bool got = ask && idx < total;
             more = !blk.warp_any(ask && !got);
             bool fresh = false;
             if (got) {
-                const PbItem it = pb_item(P, idx, npc, n_odd);
+                uint32_t tagged;
+                const PbItem it = pb_item(P, idx, npc, n_odd, &tagged);
                 const int32_t nlen = pb_normalise(P, it.pos, it.end, it.marker, norm, PB_LOCAL);
                 if (nlen < 0) {  // too long for the local state: the long-word kernel solves it
                     const uint32_t q = blk.atomic_add_ret(&P.ctl->n_long, 1u);
-                    P.longq[q] = (uint32_t)idx;
+                    P.longq[q] = tagged;
                 } else if (nlen == 0) {  // cannot happen (documents are non-empty); keep the record defined
                     ResRec rec;
                     for (int k = 0; k < RES_INLINE; ++k) rec.ids[k] = 0;
@@ -1155,12 +1175,9 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
 // long words: one thread each, state in a global scratch pool (13 bytes per normalised position)
 template <class Blk>
 DPT_PIPE_FN void pb_long_thread(Blk& blk, const PipeParams& P, int64_t gtid, int64_t gthreads) {
-    uint32_t npc[PB_CLASSES];
-    for (int c = 0; c < PB_CLASSES; ++c) npc[c] = pb_queue_len(P, c);
-    const uint32_t n_odd = P.ctl->n_odd < (uint32_t)P.odd_cap ? P.ctl->n_odd : (uint32_t)P.odd_cap;
     const uint32_t n_long = P.ctl->n_long;
     for (uint64_t k = (uint64_t)gtid; k < n_long; k += (uint64_t)gthreads) {
-        const PbItem it = pb_item(P, (uint64_t)P.longq[k], npc, n_odd);
+        const PbItem it = pb_item_tagged(P, P.longq[k]);
         const int64_t raw = it.end - it.pos;
         const int64_t need = (P.spm ? 6 * raw + 3 : raw) + 2;
         const unsigned long long off = blk.atomic_add_u64_ret(&P.ctl->lp_used, (unsigned long long)need);

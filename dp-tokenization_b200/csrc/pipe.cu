@@ -197,12 +197,12 @@ __global__ void __launch_bounds__(PA_THREADS, DPT_PABL_CTAS) k_scan_dedup_bl(con
 
 // the lock-step DP (dpt_dp_lock.cuh): length classes 0..2, i.e. every word of at most 31 units
 __global__ void __launch_bounds__(PBL_THREADS, DPT_PBL_CTAS) k_dp_lock_spm(const __grid_constant__ PipeParams P) {
-    __shared__ uint32_t st[PBL_ROWS * PBL_THREADS];
-    pbl_kernel<true>(P, st);
+    __shared__ PblSmem S;
+    pbl_kernel<true>(P, S);
 }
 __global__ void __launch_bounds__(PBL_THREADS, DPT_PBL_CTAS) k_dp_lock_bl(const __grid_constant__ PipeParams P) {
-    __shared__ uint32_t st[PBL_ROWS * PBL_THREADS];
-    pbl_kernel<false>(P, st);
+    __shared__ PblSmem S;
+    pbl_kernel<false>(P, S);
 }
 
 // thread-per-word DP with local-memory state: odd words, words longer than a warp, words the cooperative kernel deferred
@@ -241,6 +241,34 @@ __global__ void __launch_bounds__(256) k_pipe_clear(const ClearJob J) {
 }
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// One side stream + fork/join events per host thread and device (created on first use, kept for the life of the thread).
+struct SideStream {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool ok() const { return stream != nullptr; }
+};
+static SideStream& side_stream() {
+    static thread_local SideStream cache[16];
+    static SideStream none;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return none;
+    SideStream& s = cache[dev];
+    if (s.device != dev) {
+        const char* off = getenv("DPT_NO_SIDE_STREAM");
+        s.device = dev;
+        if (!(off && off[0] == '1')) {
+            if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) s.stream = nullptr;
+            if (s.stream && (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+                             cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess)) {
+                cudaStreamDestroy(s.stream);
+                s.stream = nullptr;
+            }
+        }
+    }
+    return s;
+}
 
 // Workspace = a TABLE part (word table, result records, id pool, DP queues: lives as long as the table, i.e. one
 // call or the chunks of one chunked call) + a RANGE part (everything private to one launch sequence).
@@ -451,34 +479,55 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
     }
     }
     if (do_dp) {
-    {
-        ProfScope prof(P.spm ? "k_dp_lock_spm" : "k_dp_lock_bl", st);
-        static int bl_ctas = 0;  // CTAs per SM of the lock-step kernel's grid (development knob: DPT_BL_GRID)
-        if (!bl_ctas) {
-            const char* e = getenv("DPT_BL_GRID");
-            bl_ctas = e && atoi(e) > 0 ? atoi(e) : DPT_PBL_CTAS;
+        // The thread-per-word kernel's first work list (odd words, words of more than 31 units: a few thousand, each a
+        // long serial chain - 0.13 ms however few they are) runs BESIDE the lock-step kernel on a side stream of the
+        // library (fork / join with events: from the caller's point of view everything is ordered on `st`).
+        SideStream& side = side_stream();
+        const bool forked = side.ok();
+        cudaStream_t s1 = forked ? side.stream : st;
+        if (forked) {
+            cudaEventRecord(side.fork, st);
+            cudaStreamWaitEvent(s1, side.fork, 0);
         }
-        if (P.spm)
-            k_dp_lock_spm<<<(unsigned)(sm_count * bl_ctas), PBL_THREADS, 0, st>>>(P);
-        else
-            k_dp_lock_bl<<<(unsigned)(sm_count * bl_ctas), PBL_THREADS, 0, st>>>(P);
-        ++g_launches;
-    }
-    {
-        ProfScope prof("k_dp_distinct", st);
-        static int b_ctas = 0;  // CTAs per SM of kernel B's grid (development knob: DPT_B_GRID)
+        static int b_ctas = 0;  // CTAs per SM of the thread-per-word kernel's grid (development knob: DPT_B_GRID)
         if (!b_ctas) {
             const char* e = getenv("DPT_B_GRID");
             b_ctas = e && atoi(e) > 0 ? atoi(e) : 8;
         }
-        k_dp_distinct<<<(unsigned)(sm_count * b_ctas), PB_THREADS, 0, st>>>(P);
-        ++g_launches;
-    }
-    {
-        ProfScope prof("k_dp_distinct_long", st);
-        k_dp_distinct_long<<<(unsigned)(sm_count * 2), PB_THREADS, 0, st>>>(P);
-        ++g_launches;
-    }
+        {
+            ProfScope prof("k_dp_distinct", s1);
+            PipeParams P1 = P;
+            P1.coop = 1;
+            k_dp_distinct<<<(unsigned)(sm_count * b_ctas), PB_THREADS, 0, s1>>>(P1);
+            ++g_launches;
+        }
+        if (forked) cudaEventRecord(side.join, s1);
+        {
+            ProfScope prof(P.spm ? "k_dp_lock_spm" : "k_dp_lock_bl", st);
+            static int bl_ctas = 0;  // CTAs per SM of the lock-step kernel's grid (development knob: DPT_BL_GRID)
+            if (!bl_ctas) {
+                const char* e = getenv("DPT_BL_GRID");
+                bl_ctas = e && atoi(e) > 0 ? atoi(e) : DPT_PBL_CTAS;
+            }
+            if (P.spm)
+                k_dp_lock_spm<<<(unsigned)(sm_count * bl_ctas), PBL_THREADS, 0, st>>>(P);
+            else
+                k_dp_lock_bl<<<(unsigned)(sm_count * bl_ctas), PBL_THREADS, 0, st>>>(P);
+            ++g_launches;
+        }
+        if (P.spm) {  // the words the lock-step kernel deferred (byte-level rules never defer)
+            ProfScope prof("k_dp_distinct_deferred", st);
+            PipeParams P2 = P;
+            P2.coop = 2;
+            k_dp_distinct<<<(unsigned)(sm_count * 2), PB_THREADS, 0, st>>>(P2);
+            ++g_launches;
+        }
+        if (forked) cudaStreamWaitEvent(st, side.join, 0);
+        {
+            ProfScope prof("k_dp_distinct_long", st);
+            k_dp_distinct_long<<<(unsigned)(sm_count * 2), PB_THREADS, 0, st>>>(P);
+            ++g_launches;
+        }
     }
     if (do_emit) {
     {

@@ -30,7 +30,8 @@ class DeviceLexicon:
         cdf32 = np.minimum(np.floor(cdf * 4294967296.0), 4294967295.0).astype(np.uint32)
         cdf32[-1] = 0xFFFFFFFF
         self.n = len(enc)
-        self.ascii = all(len(w) == len(s) for w, s in zip(enc[:2000], words[:2000]))
+        # Latin-script lexicon (sentence starts are capitalised; only an ASCII lowercase first letter is changed)
+        self.ascii = sum(1 for w in enc[:2000] if w[:1].isascii()) > 1800
         self.mean_len = float(np.sum(np.diff(offs) * p / p.sum()))  # frequency-weighted mean word length (bytes)
         self.bytes = torch.from_numpy(np.frombuffer(b"".join(enc), dtype=np.uint8).copy()).to(device)
         self.offs = torch.from_numpy(offs).to(device)

@@ -25,7 +25,7 @@ def test_device_generator_properties_and_parity(dev):
     from oracle.c_oracle import COracle
     en = synth_device.DeviceLexicon(synth.make_lexicon(20_000, seed=0), dev)
     ar = synth_device.DeviceLexicon(synth.make_arabic_lexicon(20_000, seed=0), dev)
-    assert en.ascii is False or en.ascii is True
+    assert en.ascii and not ar.ascii
     n_docs = 600
     text, offs = synth_device.generate(en, n_docs, seed=7, words_per_doc=(150, 900), device=dev, lex_b=ar, frac_b=0.4)
     text2, offs2 = synth_device.generate(en, n_docs, seed=7, words_per_doc=(150, 900), device=dev, lex_b=ar, frac_b=0.4)
