@@ -33,21 +33,25 @@
 namespace dpt {
 
 constexpr int PBL_THREADS = 128;
-constexpr int PBL_ROWS = 32;   // positions 0..31
-#ifndef DPT_PBL_CHUNK
-#define DPT_PBL_CHUNK 256
-#endif
-constexpr int PBL_CHUNK = DPT_PBL_CHUNK;  // words a CTA sorts and solves at a time (a multiple of PBL_THREADS)
+// Two instantiations: NW = 8 window registers (words of at most 31 units: length classes 0..2, nearly all words) and
+// NW = 16 (32..63 units: class 3, a few thousand words, on the side stream).  Rows = positions 0 .. 4 NW - 1.
+template <int NW>
+struct PblCfg {
+    static constexpr int ROWS = 4 * NW;            // DP positions 0 .. ROWS - 1: words of at most ROWS - 1 units
+    static constexpr int CHUNK = NW == 8 ? 256 : 128;  // words a CTA sorts and solves at a time (a multiple of PBL_THREADS)
+};
 
+template <int NW>
 struct PblSmem {
-    uint32_t st[PBL_ROWS * PBL_THREADS];    // DP state, [position][thread]
-    unsigned long long tag[PBL_CHUNK];      // the chunk's words sorted by length: table tag (position, length) ...
-    uint32_t slot[PBL_CHUNK];               // ... and table slot
-    uint32_t hist[PBL_ROWS + 1];            // words per length, then the bins' start offsets
+    uint32_t st[PblCfg<NW>::ROWS * PBL_THREADS];    // DP state, [position][thread]
+    unsigned long long tag[PblCfg<NW>::CHUNK];      // the chunk's words sorted by length: table tag (position, length) ...
+    uint32_t slot[PblCfg<NW>::CHUNK];               // ... and table slot
+    uint32_t hist[PblCfg<NW>::ROWS + 1];            // words per length, then the bins' start offsets
     uint32_t chunk;
 };
 
-__device__ __forceinline__ uint32_t pbl_byte(const uint32_t (&wb)[8], const int k) {  // byte k of the window (k static)
+template <int NW>
+__device__ __forceinline__ uint32_t pbl_byte(const uint32_t (&wb)[NW], const int k) {  // byte k of the window (k static)
     return (wb[k >> 2] >> (8 * (k & 3))) & 0xFFu;
 }
 // e = pred ? *p : 0 as ONE predicated load (the compiler turns the C form into a divergent branch: BSSY / BRA / BSYNC)
@@ -61,10 +65,11 @@ __device__ __forceinline__ uint32_t pbl_ldg_if(const uint32_t* p, bool pred) {
 }
 
 // One batch: 32 words (one per lane) of the sorted chunk.
-template <bool kSpm>
-__device__ __forceinline__ void pbl_batch(const PipeParams& P, PblSmem& S, const int first, const int count, const int lane) {
+template <bool kSpm, int NW>
+__device__ __forceinline__ void pbl_batch(const PipeParams& P, PblSmem<NW>& S, const int first, const int count, const int lane) {
     constexpr uint32_t FULL = 0xFFFFFFFFu;
     constexpr int m = kSpm ? 1 : 0;
+    constexpr int PBL_ROWS = PblCfg<NW>::ROWS;
     bool valid = first + lane < count;
     uint32_t slot_item = 0;
     int64_t pos = 0;
@@ -82,30 +87,31 @@ __device__ __forceinline__ void pbl_batch(const PipeParams& P, PblSmem& S, const
     const int n = valid ? len + m : 0;  // units of the word = DP positions 0..n
 
     // ---- the body bytes, zero-padded to 32, in eight registers --------------------------------------------------
-    uint32_t wb[8];
+    uint32_t wb[NW];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) wb[q] = 0;
+    for (int q = 0; q < NW; ++q) wb[q] = 0;
     if (valid) {
-        if (pos + 48 <= P.n_bytes) {
+        if (pos + 4 * NW + 16 <= P.n_bytes) {
             const uint8_t* base4 = P.text - ((uintptr_t)P.text & 3u);
             const int64_t ro = pos + (int64_t)((uintptr_t)P.text & 3u);
-            uint32_t v[4];
-            pp_load16_raw(base4, ro, v);
-            wb[0] = v[0]; wb[1] = v[1]; wb[2] = v[2]; wb[3] = v[3];
-            if (len > 16) {
-                pp_load16_raw(base4, ro + 16, v);
-                wb[4] = v[0]; wb[5] = v[1]; wb[6] = v[2]; wb[7] = v[3];
+#pragma unroll
+            for (int g = 0; g < NW / 4; ++g) {
+                if (g == 0 || len > 16 * g) {
+                    uint32_t v[4];
+                    pp_load16_raw(base4, ro + 16 * g, v);
+                    wb[4 * g] = v[0]; wb[4 * g + 1] = v[1]; wb[4 * g + 2] = v[2]; wb[4 * g + 3] = v[3];
+                }
             }
         } else {
 #pragma unroll
-            for (int qw = 0; qw < 8; ++qw) {  // (static indices: the window stays in registers)
+            for (int qw = 0; qw < NW; ++qw) {  // (static indices: the window stays in registers)
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
                     if (4 * qw + b < len) wb[qw] |= (uint32_t)P.text[pos + 4 * qw + b] << (8 * b);
             }
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {  // zero the bytes behind the word
+        for (int q = 0; q < NW; ++q) {  // zero the bytes behind the word
             const int rem = len - 4 * q;
             if (rem < 4) wb[q] = rem <= 0 ? 0u : (wb[q] & ((1u << (8 * rem)) - 1u));
         }
@@ -124,7 +130,7 @@ __device__ __forceinline__ void pbl_batch(const PipeParams& P, PblSmem& S, const
             } else if (p <= 1 || p == n) {
                 bnd = true;  // in front of the marker, in front of the body (a stray continuation byte starts a character there), end
             } else {
-                bnd = (pbl_byte(wb, p >= 1 ? p - 1 : 0) & 0xC0u) != 0x80u;
+                bnd = (pbl_byte<NW>(wb, p >= 1 ? p - 1 : 0) & 0xC0u) != 0x80u;
             }
             uint32_t key = 0;
             if (p <= n && bnd) key = p == 0 ? 63u : ((u << 7) | 0x7Fu);
@@ -136,6 +142,7 @@ __device__ __forceinline__ void pbl_batch(const PipeParams& P, PblSmem& S, const
     // ---- forward: warp-uniform loop over the start positions ----------------------------------------------------
     const uint32_t* __restrict__ da = P.V.da;
     uint32_t Eprev = 0;     // SPM: end positions relaxed from the previous active start (out-of-vocabulary test)
+    unsigned long long Eprev2 = 0;  // ... the same for the 64-position instantiation
     bool have_prev = false, oov = false;
 #pragma unroll 1
     for (int s = 0; s < nmax; ++s) {
@@ -143,8 +150,9 @@ __device__ __forceinline__ void pbl_batch(const PipeParams& P, PblSmem& S, const
         const bool active = kj != 0u;  // a unit boundary of this lane's word
         if (kSpm && active) {
             // the previous character [prev start, s) must itself be a vocabulary entry (else the normalised text spells it "<0xHH>")
-            if (have_prev && !((Eprev >> s) & 1u)) oov = true;
+            if (have_prev && !(NW == 8 ? (Eprev >> s) & 1u : (uint32_t)(Eprev2 >> s) & 1u)) oov = true;
             Eprev = 0;
+            Eprev2 = 0;
             have_prev = s >= 1;  // the marker (start 0) is always there (rule precondition)
         }
         const uint32_t hi1 = (kj & 0xFFC0u) + 0x80u, low = kj & 0x3Fu;
@@ -164,10 +172,10 @@ __device__ __forceinline__ void pbl_batch(const PipeParams& P, PblSmem& S, const
                 const bool pb = term && k <= bi;
                 uint32_t nr = (row & 0xFF00FFFFu) | (d << 16);          // A = d
                 if (pb) nr = (nr & 0x00FF0000u) | k | (d << 24);       // key = k, B = d
-                if (pa) {
-                    *rp = nr;
-                    if (kSpm) Eprev |= 1u << p;
-                }
+                if (pa) *rp = nr;
+                // (the edge exists whether or not it improves the row: the out-of-vocabulary test asks for existence)
+                if (kSpm && NW == 8 && term && bi != 0u) Eprev |= 1u << p;
+                if (kSpm && NW == 16 && term && bi != 0u) Eprev2 |= 1ull << p;
             }
         };
         if (kSpm && s == 0) {  // start 0 begins behind U+2581 (its trie node is part of the compiled vocabulary)
@@ -178,12 +186,12 @@ __device__ __forceinline__ void pbl_batch(const PipeParams& P, PblSmem& S, const
         }
         // The walk: groups of four steps peel the bytes off a running copy of the window (a fully unrolled 31-step walk let
         // the compiler keep every step's derived values live at once: > 128 registers).
-        uint32_t ww[8];
+        uint32_t ww[NW];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) ww[q] = wb[q];
+        for (int q = 0; q < NW; ++q) ww[q] = wb[q];
         bool open = true;
 #pragma unroll 1
-        for (int g = 0; g < 8 && open; ++g) {
+        for (int g = 0; g < NW && open; ++g) {
             uint32_t wcur = ww[0];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -206,16 +214,16 @@ __device__ __forceinline__ void pbl_batch(const PipeParams& P, PblSmem& S, const
                 relax(alive && (e & DPT_DA_TERMINAL));
             }
 #pragma unroll
-            for (int q = 0; q < 7; ++q) ww[q] = ww[q + 1];
-            ww[7] = 0;
+            for (int q = 0; q < NW - 1; ++q) ww[q] = ww[q + 1];
+            ww[NW - 1] = 0;
         }
         if (!(kSpm && s == 0)) {  // the window moves on by one byte (start 0 of an SPM word reads the body from its first byte, like start 1)
 #pragma unroll
-            for (int q = 0; q < 7; ++q) wb[q] = __funnelshift_r(wb[q], wb[q + 1], 8);
-            wb[7] >>= 8;
+            for (int q = 0; q < NW - 1; ++q) wb[q] = __funnelshift_r(wb[q], wb[q + 1], 8);
+            wb[NW - 1] >>= 8;
         }
     }
-    if (kSpm && valid && have_prev && !((Eprev >> n) & 1u)) oov = true;
+    if (kSpm && valid && have_prev && !(NW == 8 ? (Eprev >> n) & 1u : (uint32_t)(Eprev2 >> n) & 1u)) oov = true;
     if (kSpm) {  // hand the words with out-of-vocabulary characters to the thread-per-word kernel
         oov = oov && valid;
         const uint32_t mo = __ballot_sync(FULL, oov);
@@ -307,35 +315,40 @@ __device__ __forceinline__ void pbl_batch(const PipeParams& P, PblSmem& S, const
     }
 }
 
-// Persistent CTAs: a chunk of PBL_CHUNK words of the concatenated queues (classes 2, 1, 0) from a ticket -> counting
-// sort by length in shared memory -> the warps solve its batches of 32, interleaved so every warp gets long and short ones.
-template <bool kSpm>
-__device__ __forceinline__ void pbl_kernel(const PipeParams& P, PblSmem& S) {
+// Persistent CTAs: a chunk of CHUNK words of the concatenated queues (NW = 8: classes 2, 1, 0; NW = 16: class 3) from a
+// ticket -> counting sort by length in shared memory -> the warps solve its batches of 32, interleaved so every warp gets
+// long and short ones.
+template <bool kSpm, int NW>
+__device__ __forceinline__ void pbl_kernel(const PipeParams& P, PblSmem<NW>& S) {
+    constexpr int ROWS = PblCfg<NW>::ROWS, CHUNK = PblCfg<NW>::CHUNK, PER = CHUNK / PBL_THREADS, BINS_PER_LANE = ROWS / 32;
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t nq2 = pb_queue_len(P, 2), nq1 = pb_queue_len(P, 1), nq0 = pb_queue_len(P, 0);
+    const uint32_t nq2 = NW == 8 ? pb_queue_len(P, 2) : pb_queue_len(P, 3);
+    const uint32_t nq1 = NW == 8 ? pb_queue_len(P, 1) : 0u, nq0 = NW == 8 ? pb_queue_len(P, 0) : 0u;
+    const int cls_first = NW == 8 ? 2 : 3;
     const uint32_t total = nq2 + nq1 + nq0;
-    const uint32_t n_chunks = (total + PBL_CHUNK - 1) / PBL_CHUNK;
+    const uint32_t n_chunks = (total + CHUNK - 1) / CHUNK;
+    unsigned int* const ticket = NW == 8 ? &P.ctl->lock_ticket : &P.ctl->lock_ticket2;
     for (;;) {
-        if (tid == 0) S.chunk = atomicAdd(&P.ctl->lock_ticket, 1u);
-        if (tid <= PBL_ROWS) S.hist[tid] = 0;
+        if (tid == 0) S.chunk = atomicAdd(ticket, 1u);
+        if (tid <= ROWS) S.hist[tid] = 0;
         __syncthreads();
         const uint32_t chunk = S.chunk;
         if (chunk >= n_chunks) break;
-        const uint32_t c0 = chunk * PBL_CHUNK;
-        const int count = (int)(total - c0 < (uint32_t)PBL_CHUNK ? total - c0 : (uint32_t)PBL_CHUNK);
+        const uint32_t c0 = chunk * CHUNK;
+        const int count = (int)(total - c0 < (uint32_t)CHUNK ? total - c0 : (uint32_t)CHUNK);
         // this thread's words of the chunk
-        uint32_t slot[PBL_CHUNK / PBL_THREADS];
-        unsigned long long tag[PBL_CHUNK / PBL_THREADS];
-        uint32_t rank[PBL_CHUNK / PBL_THREADS];
+        uint32_t slot[PER];
+        unsigned long long tag[PER];
+        uint32_t rank[PER];
 #pragma unroll
-        for (int r = 0; r < PBL_CHUNK / PBL_THREADS; ++r) {
+        for (int r = 0; r < PER; ++r) {
             const int k = tid + r * PBL_THREADS;
             slot[r] = 0;
             tag[r] = 0;
             rank[r] = 0;
             if (k < count) {
                 uint32_t g = c0 + (uint32_t)k;
-                int cls = 2;
+                int cls = cls_first;
                 if (g >= nq2 + nq1) {
                     cls = 0;
                     g -= nq2 + nq1;
@@ -347,39 +360,49 @@ __device__ __forceinline__ void pbl_kernel(const PipeParams& P, PblSmem& S) {
             }
         }
 #pragma unroll
-        for (int r = 0; r < PBL_CHUNK / PBL_THREADS; ++r)
+        for (int r = 0; r < PER; ++r)
             if (tid + r * PBL_THREADS < count) tag[r] = P.tags[slot[r]];
 #pragma unroll
-        for (int r = 0; r < PBL_CHUNK / PBL_THREADS; ++r)
+        for (int r = 0; r < PER; ++r)
             if (tid + r * PBL_THREADS < count) {
                 const int len = pp_tag_len(tag[r]);
-                rank[r] = atomicAdd(&S.hist[len < PBL_ROWS ? len : PBL_ROWS], 1u);
+                rank[r] = atomicAdd(&S.hist[len < ROWS ? len : ROWS], 1u);
             }
         __syncthreads();
-        if (warp == 0) {  // bins -> start offsets, longest words first: lane l owns length 31 - l, the bin of length >= 32 stays empty
-            const uint32_t h = S.hist[PBL_ROWS - 1 - lane];
-            uint32_t inc = h;
+        if (warp == 0) {  // bins -> start offsets, longest words first: lane l owns the lengths ROWS-1 - BINS_PER_LANE l - q
+            uint32_t h[BINS_PER_LANE], mine = 0;
+#pragma unroll
+            for (int q = 0; q < BINS_PER_LANE; ++q) {
+                h[q] = S.hist[ROWS - 1 - (lane * BINS_PER_LANE + q)];
+                mine += h[q];
+            }
+            uint32_t inc = mine;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
                 if (lane >= d) inc += o;
             }
-            S.hist[PBL_ROWS - 1 - lane] = inc - h;
-            if (lane == 31) S.hist[PBL_ROWS] = inc;
+            uint32_t at = inc - mine;
+#pragma unroll
+            for (int q = 0; q < BINS_PER_LANE; ++q) {
+                S.hist[ROWS - 1 - (lane * BINS_PER_LANE + q)] = at;
+                at += h[q];
+            }
+            if (lane == 31) S.hist[ROWS] = inc;
         }
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < PBL_CHUNK / PBL_THREADS; ++r)
+        for (int r = 0; r < PER; ++r)
             if (tid + r * PBL_THREADS < count) {
                 const int len = pp_tag_len(tag[r]);
-                const uint32_t at = S.hist[len < PBL_ROWS ? len : PBL_ROWS] + rank[r];
-                if (at < (uint32_t)PBL_CHUNK) {
+                const uint32_t at = S.hist[len < ROWS ? len : ROWS] + rank[r];
+                if (at < (uint32_t)CHUNK) {
                     S.slot[at] = slot[r];
                     S.tag[at] = tag[r];
                 }
             }
         __syncthreads();
-        for (int b = warp; b * 32 < count; b += PBL_THREADS / 32) pbl_batch<kSpm>(P, S, b * 32, count, lane);
+        for (int b = warp; b * 32 < count; b += PBL_THREADS / 32) pbl_batch<kSpm, NW>(P, S, b * 32, count, lane);
         __syncthreads();
     }
 }

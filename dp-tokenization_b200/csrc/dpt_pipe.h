@@ -56,7 +56,7 @@ constexpr int PA_THREADS = DPT_PA_THREADS;
 constexpr int PA_MAXLEN = 63;                 // longest word body (bytes) that goes through the dedup table
 constexpr int PA_PROBES = 8;
 constexpr int PB_THREADS = 128;
-constexpr int PB_CLASSES = 4;                 // length classes of the DP work queues (8 measured no better: lane
+constexpr int PB_CLASSES = 5;                 // length classes of the DP work queues (8 measured no better: lane
                                               // imbalance comes from walk depths, not from word length)
 constexpr int PB_LOCAL = 72;                  // normalised bytes solved with per-thread local state in kernel B
 // kernel B: finished lanes take new words once fewer lanes than this are still walking.  1 = a warp finishes its 32
@@ -112,7 +112,7 @@ struct PipeCtl {  // device-side counters, zeroed by the launcher
     unsigned long long lp_used, n_words, n_untok, n_too_long;
     unsigned long long b_cursor;  // next unclaimed item of kernel B's work list (thread-per-word kernel, first launch)
     unsigned long long b_cursor2; // ... second launch (the words the lock-step kernel deferred)
-    unsigned int lock_ticket, pad1;  // next unclaimed chunk of the lock-step kernel
+    unsigned int lock_ticket, lock_ticket2;  // next unclaimed chunk of the lock-step kernels (<= 31 units / 32..63 units)
 };
 
 struct PipePersist {  // survives the launches of one chunked call (same lifetime as the word table)
@@ -386,11 +386,11 @@ struct PaLetterSkip {
         return p < end ? p : end;
     }
 };
-// Length class of a word = the tile width of the cooperative DP kernel that solves it: `units` = lanes the word needs
-// (body bytes, + 1 for the SPM marker).  0: 8-lane tiles (4 words per warp), 1: 16 lanes, 2: 32 lanes, 3: longer than a
-// warp -> the thread-per-word kernel.
+// Length class of a word by its `units` (body bytes, + 1 for the SPM marker): 0..2 -> the lock-step DP kernel with a
+// 32-byte register window (the CTA sorts its words by exact length anyway; the classes only keep A's queues apart),
+// 3 -> its 64-byte instantiation, 4 -> the thread-per-word kernel.
 DPT_HD int pp_len_class(int units) {
-    return units <= 8 ? 0 : units <= 16 ? 1 : units <= 31 ? 2 : 3;
+    return units <= 8 ? 0 : units <= 16 ? 1 : units <= 31 ? 2 : units <= 63 ? 3 : 4;
 }
 DPT_HD uint32_t pp_tail_mask(int nbytes) { return nbytes >= 4 ? ~0u : ((1u << (8 * nbytes)) - 1u); }
 
@@ -1010,8 +1010,8 @@ struct PbItem {
     ResRec* out;
 };
 // Work list of the thread-per-word kernel.  On the device the lock-step kernel (dpt_dp_lock.cuh) solves the length
-// classes 0..2; this kernel runs twice: P.coop == 1, BESIDE the lock-step kernel on a side stream: the odd words and the
-// words of more than 31 units (class 3); P.coop == 2, after it: the words the lock-step kernel deferred
+// classes 0..3; this kernel runs twice: P.coop == 1, BESIDE the lock-step kernel on a side stream: the odd words and the
+// words of more than 63 units (class 4); P.coop == 2, after it: the words the lock-step kernels deferred
 // (out-of-vocabulary characters that expand to "<0xHH>" text).  P.coop == 0 (host emulation): odd words, then every
 // length class from longest to shortest.
 DPT_PIPE_FN uint64_t pb_list_len(const PipeParams& P, const uint32_t* npc, uint32_t n_odd, uint32_t n_defer) {

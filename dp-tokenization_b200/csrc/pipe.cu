@@ -195,14 +195,23 @@ __global__ void __launch_bounds__(PA_THREADS, DPT_PABL_CTAS) k_scan_dedup_bl(con
     pa_kernel<DevBlk, false>(blk, P, S);
 }
 
-// the lock-step DP (dpt_dp_lock.cuh): length classes 0..2, i.e. every word of at most 31 units
+// the lock-step DP (dpt_dp_lock.cuh): words of at most 31 units (length classes 0..2) ...
 __global__ void __launch_bounds__(PBL_THREADS, DPT_PBL_CTAS) k_dp_lock_spm(const __grid_constant__ PipeParams P) {
-    __shared__ PblSmem S;
-    pbl_kernel<true>(P, S);
+    __shared__ PblSmem<8> S;
+    pbl_kernel<true, 8>(P, S);
 }
 __global__ void __launch_bounds__(PBL_THREADS, DPT_PBL_CTAS) k_dp_lock_bl(const __grid_constant__ PipeParams P) {
-    __shared__ PblSmem S;
-    pbl_kernel<false>(P, S);
+    __shared__ PblSmem<8> S;
+    pbl_kernel<false, 8>(P, S);
+}
+// ... and of 32..63 units (class 3: a few thousand words; 64-byte register window, 33 KB of state per CTA)
+__global__ void __launch_bounds__(PBL_THREADS, 4) k_dp_lock64_spm(const __grid_constant__ PipeParams P) {
+    __shared__ PblSmem<16> S;
+    pbl_kernel<true, 16>(P, S);
+}
+__global__ void __launch_bounds__(PBL_THREADS, 4) k_dp_lock64_bl(const __grid_constant__ PipeParams P) {
+    __shared__ PblSmem<16> S;
+    pbl_kernel<false, 16>(P, S);
 }
 
 // thread-per-word DP with local-memory state: odd words, words longer than a warp, words the cooperative kernel deferred
@@ -479,9 +488,10 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
     }
     }
     if (do_dp) {
-        // The thread-per-word kernel's first work list (odd words, words of more than 31 units: a few thousand, each a
-        // long serial chain - 0.13 ms however few they are) runs BESIDE the lock-step kernel on a side stream of the
-        // library (fork / join with events: from the caller's point of view everything is ordered on `st`).
+        // The few long words (32..63 units: the lock-step kernel's 64-byte instantiation; odd words and words of more
+        // than 63 units: the thread-per-word kernel - each a long serial chain, 0.13 ms however few they are) run BESIDE
+        // the lock-step kernel on a side stream of the library (fork / join with events: from the caller's point of view
+        // everything is ordered on `st`).
         SideStream& side = side_stream();
         const bool forked = side.ok();
         cudaStream_t s1 = forked ? side.stream : st;
@@ -489,16 +499,19 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
             cudaEventRecord(side.fork, st);
             cudaStreamWaitEvent(s1, side.fork, 0);
         }
-        static int b_ctas = 0;  // CTAs per SM of the thread-per-word kernel's grid (development knob: DPT_B_GRID)
-        if (!b_ctas) {
-            const char* e = getenv("DPT_B_GRID");
-            b_ctas = e && atoi(e) > 0 ? atoi(e) : 8;
+        {
+            ProfScope prof(P.spm ? "k_dp_lock64_spm" : "k_dp_lock64_bl", s1);
+            if (P.spm)
+                k_dp_lock64_spm<<<(unsigned)(sm_count * 2), PBL_THREADS, 0, s1>>>(P);
+            else
+                k_dp_lock64_bl<<<(unsigned)(sm_count * 2), PBL_THREADS, 0, s1>>>(P);
+            ++g_launches;
         }
         {
             ProfScope prof("k_dp_distinct", s1);
             PipeParams P1 = P;
             P1.coop = 1;
-            k_dp_distinct<<<(unsigned)(sm_count * b_ctas), PB_THREADS, 0, s1>>>(P1);
+            k_dp_distinct<<<(unsigned)(sm_count * 2), PB_THREADS, 0, s1>>>(P1);
             ++g_launches;
         }
         if (forked) cudaEventRecord(side.join, s1);
