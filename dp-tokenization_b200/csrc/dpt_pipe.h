@@ -54,7 +54,7 @@ constexpr int PA_R = PA_HALO + PA_T + PA_LA;  // region bytes = 4096 = 256 x 16:
 constexpr int PA_NW = PA_R / 32;
 constexpr int PA_THREADS = DPT_PA_THREADS;
 constexpr int PA_MAXLEN = 63;                 // longest word body (bytes) that goes through the dedup table
-constexpr int PA_PROBES = 8;
+constexpr int PA_PROBES = 16;                // (8: ~5e-4 of the distinct words found their neighbourhood full and became odd words)
 constexpr int PB_THREADS = 128;
 constexpr int PB_CLASSES = 5;                 // length classes of the DP work queues (8 measured no better: lane
                                               // imbalance comes from walk depths, not from word length)

@@ -9,6 +9,7 @@
 #include "../../include/dptok.h"
 #include "dpt_pipe.h"
 #include "dpt_dp_lock.cuh"
+#include "dpt_dp_warp.cuh"
 #include "kernels.h"
 #include "vocab.h"
 
@@ -204,15 +205,10 @@ __global__ void __launch_bounds__(PBL_THREADS, DPT_PBL_CTAS) k_dp_lock_bl(const 
     __shared__ PblSmem<8> S;
     pbl_kernel<false, 8>(P, S);
 }
-// ... and of 32..63 units (class 3: a few thousand words; 64-byte register window, 33 KB of state per CTA)
-__global__ void __launch_bounds__(PBL_THREADS, 4) k_dp_lock64_spm(const __grid_constant__ PipeParams P) {
-    __shared__ PblSmem<16> S;
-    pbl_kernel<true, 16>(P, S);
-}
-__global__ void __launch_bounds__(PBL_THREADS, 4) k_dp_lock64_bl(const __grid_constant__ PipeParams P) {
-    __shared__ PblSmem<16> S;
-    pbl_kernel<false, 16>(P, S);
-}
+// ... and of 32..63 units (class 3: a few thousand words): one warp per word (dpt_dp_warp.cuh).  The lock-step kernel's
+// 64-byte instantiation (pbl_kernel<., 16>) solved them in 0.127 ms - one serial chain per word - this one in ~0.02 ms.
+__global__ void __launch_bounds__(PBW_THREADS) k_dp_warp_spm(const __grid_constant__ PipeParams P) { pbw_kernel<true>(P); }
+__global__ void __launch_bounds__(PBW_THREADS) k_dp_warp_bl(const __grid_constant__ PipeParams P) { pbw_kernel<false>(P); }
 
 // thread-per-word DP with local-memory state: odd words, words longer than a warp, words the cooperative kernel deferred
 __global__ void __launch_bounds__(PB_THREADS, DPT_PB_CTAS) k_dp_distinct(const __grid_constant__ PipeParams P) {
@@ -488,10 +484,9 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
     }
     }
     if (do_dp) {
-        // The few long words (32..63 units: the lock-step kernel's 64-byte instantiation; odd words and words of more
-        // than 63 units: the thread-per-word kernel - each a long serial chain, 0.13 ms however few they are) run BESIDE
-        // the lock-step kernel on a side stream of the library (fork / join with events: from the caller's point of view
-        // everything is ordered on `st`).
+        // The few long words (32..63 units: one warp per word; odd words and words of more than 63 units: the
+        // thread-per-word kernel, a serial chain per word) run BESIDE the lock-step kernel on a side stream of the library
+        // (fork / join with events: from the caller's point of view everything is ordered on `st`).
         SideStream& side = side_stream();
         const bool forked = side.ok();
         cudaStream_t s1 = forked ? side.stream : st;
@@ -500,11 +495,11 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
             cudaStreamWaitEvent(s1, side.fork, 0);
         }
         {
-            ProfScope prof(P.spm ? "k_dp_lock64_spm" : "k_dp_lock64_bl", s1);
+            ProfScope prof(P.spm ? "k_dp_warp_spm" : "k_dp_warp_bl", s1);
             if (P.spm)
-                k_dp_lock64_spm<<<(unsigned)(sm_count * 2), PBL_THREADS, 0, s1>>>(P);
+                k_dp_warp_spm<<<(unsigned)(sm_count * 4), PBW_THREADS, 0, s1>>>(P);
             else
-                k_dp_lock64_bl<<<(unsigned)(sm_count * 2), PBL_THREADS, 0, s1>>>(P);
+                k_dp_warp_bl<<<(unsigned)(sm_count * 4), PBW_THREADS, 0, s1>>>(P);
             ++g_launches;
         }
         {
@@ -528,14 +523,14 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
                 k_dp_lock_bl<<<(unsigned)(sm_count * bl_ctas), PBL_THREADS, 0, st>>>(P);
             ++g_launches;
         }
-        if (P.spm) {  // the words the lock-step kernel deferred (byte-level rules never defer)
+        if (forked) cudaStreamWaitEvent(st, side.join, 0);  // (the side stream's kernels defer words too)
+        if (P.spm) {  // the words the lock-step kernels deferred (byte-level rules never defer)
             ProfScope prof("k_dp_distinct_deferred", st);
             PipeParams P2 = P;
             P2.coop = 2;
             k_dp_distinct<<<(unsigned)(sm_count * 2), PB_THREADS, 0, st>>>(P2);
             ++g_launches;
         }
-        if (forked) cudaStreamWaitEvent(st, side.join, 0);
         {
             ProfScope prof("k_dp_distinct_long", st);
             k_dp_distinct_long<<<(unsigned)(sm_count * 2), PB_THREADS, 0, st>>>(P);
