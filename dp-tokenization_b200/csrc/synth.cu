@@ -101,6 +101,14 @@ __device__ int sy_word(const SynthLex& L, const dpt_synth_params& sp, int64_t do
         }
     } else {
         n += sy_put_lex(L, k, cap, out ? out + n : nullptr);
+        if (sp.suffix_prob) {  // redundancy sweep: make this occurrence a word of its own
+            const uint64_t r3 = sy_mix(r2 ^ 0x5AFFull);
+            if ((uint32_t)(r3 >> 32) < sp.suffix_prob || sp.suffix_prob == 0xFFFFFFFFu) {
+                if (out)
+                    for (int q = 0; q < 4; ++q) out[n + q] = (uint8_t)('a' + (uint32_t)((r3 >> (5 * q)) & 31u) % 26u);
+                n += 4;
+            }
+        }
     }
     if (sy_sentence_end(sp.seed, doc, w, n_words, (uint32_t)sp.sentence_mean)) {
         if (out) out[n] = '.';

@@ -38,7 +38,7 @@ class VocabInfo(C.Structure):
 
 class SynthParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("words_lo", C.c_int32), ("words_hi", C.c_int32), ("sentence_mean", C.c_int32),
-                ("flags", C.c_int32), ("frac_b", C.c_uint32), ("reserved", C.c_uint32)]
+                ("flags", C.c_int32), ("frac_b", C.c_uint32), ("suffix_prob", C.c_uint32)]
 
 
 if not os.path.isfile(LIB_PATH):

@@ -306,7 +306,8 @@ typedef struct dpt_synth_params {
     int32_t sentence_mean;       /* a sentence ends after each word with probability 1 / sentence_mean     */
     int32_t flags;               /* bit 0: lexicon A is ASCII (capitalise sentence starts), bit 1: B is    */
     uint32_t frac_b;             /* P(document uses lexicon B) * 2^32                                      */
-    uint32_t reserved;
+    uint32_t suffix_prob;        /* P(a plain word gets 4 hash-derived letters appended) * 2^32: raises the share of
+                                    DISTINCT words (redundancy sweep of the dedup pipeline; 0 = off)          */
 } dpt_synth_params;
 int dpt_synth_corpus(const uint8_t* d_lex_a_bytes, const int64_t* d_lex_a_offs, const uint32_t* d_lex_a_cdf, int32_t n_a,
                      const uint8_t* d_lex_b_bytes, const int64_t* d_lex_b_offs, const uint32_t* d_lex_b_cdf, int32_t n_b,

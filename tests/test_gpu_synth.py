@@ -37,6 +37,16 @@ def test_device_generator_properties_and_parity(dev):
     other, _ = synth_device.generate(en, n_docs, seed=8, words_per_doc=(150, 900), device=dev, lex_b=ar, frac_b=0.4)
     assert other.numel() != text.numel() or not torch.equal(other, text)  # the seed matters
     raw = text.cpu().numpy().tobytes()
+    # the host port of the generator (bench.py --impl reference runs without a GPU) gives the same documents
+    h_en = synth_device.HostLexicon(synth.make_lexicon(20_000, seed=0))
+    h_ar = synth_device.HostLexicon(synth.make_arabic_lexicon(20_000, seed=0))
+    h_docs = synth_device.generate_host(h_en, 12, seed=7, words_per_doc=(150, 900), lex_b=h_ar, frac_b=0.4, doc_base=3)
+    ho = offs.cpu().numpy()
+    assert h_docs == [raw[ho[d]:ho[d + 1]] for d in range(3, 15)]
+    sfx, so = synth_device.generate(en, 4, seed=9, words_per_doc=(50, 60), device=dev, suffix_prob=0.5)
+    sraw, so = sfx.cpu().numpy().tobytes(), so.cpu().numpy()
+    assert synth_device.generate_host(h_en, 4, seed=9, words_per_doc=(50, 60), suffix_prob=0.5) == \
+        [sraw[so[d]:so[d + 1]] for d in range(4)]
     h_offs = offs.cpu().numpy()
     docs = [raw[h_offs[d]:h_offs[d + 1]].decode("utf-8") for d in range(n_docs)]   # valid UTF-8, document by document
     n_ar = sum(1 for d in docs if any("؀" <= ch <= "ۿ" for ch in d[:200]))
