@@ -449,6 +449,14 @@ int dpt_lattice_word(const dpt_vocab* v, const uint8_t* d_text, int32_t n_bytes,
     return rc ? fail(rc, "dpt_lattice_word: launch failed") : DPT_OK;
 }
 
+int dpt_min_tokens_word(const dpt_vocab* v, const uint8_t* d_text, int32_t n_bytes, const uint8_t* d_unit_starts,
+                        int32_t* d_out, int32_t* d_scratch, void* stream) {
+    if (int rc = check_ready(v, "dpt_min_tokens_word")) return rc;
+    if (n_bytes <= 0 || !d_text || !d_out || !d_scratch) return fail(DPT_EINVAL, "dpt_min_tokens_word: bad argument");
+    const int rc = dpt::min_tokens_word(v, d_text, n_bytes, d_unit_starts, d_out, d_scratch, (cudaStream_t)stream);
+    return rc ? fail(rc, "dpt_min_tokens_word: launch failed") : DPT_OK;
+}
+
 int dpt_pad_batch(const int32_t* d_ids_a, const int64_t* d_doc_tok_offs_a, const int32_t* d_ids_b,
                   const int64_t* d_doc_tok_offs_b, int64_t doc_begin, int64_t n_rows, int64_t row_len, int64_t pad_id,
                   int32_t pad_left, int64_t* d_input_ids, int64_t* d_attention_mask, int64_t* d_row_lens, void* stream) {

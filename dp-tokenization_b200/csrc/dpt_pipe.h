@@ -87,13 +87,17 @@ constexpr unsigned long long PD_MASK = (1ull << 62) - 1;
 
 constexpr uint32_t RES_UNTOK = 1u << 24;      // result meta: word_len (24 bits) | flags
 constexpr uint32_t RES_POOLED = 1u << 25;     // more than RES_INLINE ids: they live in the pool at ids[0] | ids[1] << 32
-constexpr int RES_INLINE = 3;
+constexpr int RES_INLINE = 7;
+constexpr int RES_HEAD = 3;                   // ids in the first 16 bytes of a record
 constexpr uint32_t RES_LONG = 1u << 26;       // solved by the long-word kernel
 
-// Result of one distinct word: 16 bytes, indexed by the word's table slot.  Nine of ten word OCCURRENCES have at most
-// three tokens, so kernel C's one 16-byte gather per word brings everything it needs; the 32-byte records of round 1
-// (7 ids inline) made the table a sparse 67 MB that fought the streaming refs/ids for L2 (hit rate 47 %).
-struct alignas(16) ResRec {
+// Result of one distinct word: ONE 32-byte sector, indexed by the word's table slot.  Kernel C gathers the first 16 bytes
+// (meta + ids[0..2]: nine of ten word OCCURRENCES have at most three tokens) and, for words of 4..7 tokens, the second 16
+// bytes of the SAME sector (an L1 hit behind the first load); only words of more than 7 tokens go through the id pool.
+// (Round 2 tried 16-byte records with 3 ids inline: the sector footprint in L2 is the same - one sector per live record
+// either way, hit rate 47 % -> 50 % - and the pool copy of every word of 4+ tokens, a serial loop at 2.5 of 32 lanes,
+// became 38 % of kernel C's instructions: 0.160 -> 0.183 ms.)
+struct alignas(32) ResRec {
     uint32_t meta;           // word_len (len_dp[n], 24 bits) | RES_* flags
     int32_t ids[RES_INLINE];
 };
@@ -183,7 +187,10 @@ struct ASmemT {
     uint32_t mWS[PA_NW + 2];  // word starts
     uint32_t mCX[PA_NW + 2];  // positions that make their word "odd" (solved from the raw text, not deduplicated)
     uint32_t mSY[PA_NW + 2];  // byte-level rules: synchronisation points of the split scanner
-    uint32_t mAL[kSpm ? 2 : PA_NW + 2];  // byte-level rules: ASCII letters (the split scanner skips over their runs)
+    uint32_t mAL[kSpm ? 2 : PA_NW + 2];  // byte-level rules: every byte of a letter (the split scanner skips over their runs)
+    uint32_t mNW[kSpm ? 2 : PA_NW + 2];  // byte-level rules: positions whose character can follow a synchronising space
+    alignas(16) uint8_t code[kSpm ? 16 : PA_R + 64];  // byte-level rules: dpt_char_code of the character at every position
+    alignas(16) uint8_t lut[kSpm ? 16 : 128];         // ... and of the 128 ASCII characters
     uint32_t cnt[PA_NW + 2];
     uint32_t dsn[PA_NW + 2];  // byte-level rules: document starts in front of each mask word
     uint16_t wlist[WL_CAP];   // region index of the words of the current window (| 0x8000: a document's '<s>' word)
@@ -386,6 +393,13 @@ struct PaLetterSkip {
         return p < end ? p : end;
     }
 };
+// the split scanners' character source over a tile's code array (dpt_split_rules.h: DptTextSrc): index = global offset
+struct PaCodeSrc {
+    const uint8_t* code;  // S.code - g0
+    const uint8_t* text;  // S.text - g0
+    DPT_HD DptChar at(int64_t p, int64_t) const { return dpt_char_of_code(code[p]); }
+    DPT_HD uint32_t byte(int64_t p) const { return text[p]; }
+};
 // Length class of a word by its `units` (body bytes, + 1 for the SPM marker): 0..2 -> the lock-step DP kernel with a
 // 32-byte register window (the CTA sorts its words by exact length anyway; the classes only keep A's queues apart),
 // 3 -> its 64-byte instantiation, 4 -> the thread-per-word kernel.
@@ -468,11 +482,21 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
             const int w = PA_NW + (nt - 5 - tid);
             S.mCS[w] = S.mSP[w] = S.mM3[w] = S.mCF[w] = S.mWS[w] = S.mCX[w] = S.cnt[w] = S.mSY[w] = 0;
         }
-        if (!spm)
-            for (int w = tid; w < PA_NW; w += nt) {
+        if (!spm) {
+            for (int w = tid; w < PA_NW + 2; w += nt) {
                 S.mSY[w] = 0;
                 S.mWS[w] = 0;
+                S.mAL[w] = 0;
             }
+            for (int i = tid; i < 128 + 4; i += nt) {
+                if (i < 128) {  // codes of the ASCII characters (conflict-free look-ups in the mask pass: one LUT word per bank)
+                    const uint8_t b = (uint8_t)i;
+                    S.lut[i] = (uint8_t)dpt_char_code(dpt_char_at(DptUniView{P.V.uni1, P.V.uni2}, &b, 0, 1));
+                } else {
+                    *reinterpret_cast<uint4*>(&S.code[PA_R + 16 * (i - 128)]) = uint4{0u, 0u, 0u, 0u};
+                }
+            }
+        }
         // Document starts of the region, by the first warp alone while the text loads are in flight: a 32-ary search
         // for the first document (4 rounds of loads instead of the 16 dependent ones of a binary search, which was the
         // longest thing in front of the first barrier: ncu v12), then one offset per lane.
@@ -522,9 +546,64 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
         reinterpret_cast<uint16_t*>(S.mSP)[hw] = (uint16_t)sp;
         reinterpret_cast<uint16_t*>(S.mM3)[hw] = (uint16_t)(spm ? m3 : 0u);
         if (!spm) {
-            // bytes of letter characters: ASCII letters (SWAR)
+            // What the split scanners will ask about every position of these 16 bytes, answered once, by all threads at
+            // once: the character's class, length and the three code-point tests (dpt_char_code).  The scanners run one
+            // thread per stretch, so every instruction a character costs THEM is paid at a fraction of a warp's lanes:
+            // decoding UTF-8 and walking the two-stage class table there was most of this kernel (ncu, round 2: 758 M
+            // warp-instructions per 100 MB at 16.7 lanes).
+            const bool bloom = P.rule == 4;
+            uint32_t cw[4] = {0u, 0u, 0u, 0u};
+            uint32_t nw = 0;
+            const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+            // ASCII bytes: one conflict-free LUT look-up each (a non-ASCII byte looks up its low 7 bits and is patched below)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t c = S.lut[(xs[k >> 2] >> (8 * (k & 3))) & 0x7Fu];
+                cw[k >> 2] |= c << (8 * (k & 3));
+                nw |= (uint32_t)((c & 3u) != DPT_CLS_S && !(bloom && (c & DPT_CODE_BX))) << k;
+            }
+            // al: 16 bits + the spill of a letter that runs into the next 16 bytes
             uint32_t al = pp_letters4(x.x) | (pp_letters4(x.y) << 4) | (pp_letters4(x.z) << 8) | (pp_letters4(x.w) << 12);
-            reinterpret_cast<uint16_t*>(S.mAL)[hw] = (uint16_t)al;
+            uint32_t hi = ((((x.x & 0x80808080u) >> 7) * 0x01020408u) >> 24) | (((((x.y & 0x80808080u) >> 7) * 0x01020408u) >> 24) << 4) |
+                          (((((x.z & 0x80808080u) >> 7) * 0x01020408u) >> 24) << 8) | (((((x.w & 0x80808080u) >> 7) * 0x01020408u) >> 24) << 12);
+            if (hi) {  // non-ASCII bytes, one at a time (ONE copy of the decoder in the kernel: unrolled it thrashed the instruction cache)
+                const DptUniView U{P.V.uni1, P.V.uni2};
+                const int r0 = 16 * hw;
+                // document starts at r0 + 1 .. r0 + 18: a character cut by a document boundary is malformed
+                const uint64_t dsw = (((uint64_t)S.mDS[r0 >> 5] | ((uint64_t)S.mDS[(r0 >> 5) + 1] << 32)) >> (r0 & 31)) >> 1;
+                uint32_t c4[4] = {0u, 0u, 0u, 0u};  // codes of the non-ASCII positions, and the bytes they replace
+                uint32_t keep = 0xFFFFu;
+                do {
+                    const int k = pp_ctz(hi);
+                    const uint32_t near = (uint32_t)(dsw >> k) & 7u;  // document starts at r + 1, r + 2, r + 3
+                    const int lim = near ? pp_ctz(near) + 1 : 4;
+                    const DptChar ch = dpt_char_at(U, t, k, k + lim);
+                    const uint32_t c = dpt_char_code(ch);
+                    const uint32_t span = ((1u << ch.len) - 1u) << k;  // the bytes of this character: the scanners only ever
+                    hi &= ~span;                                       // ask about its first
+                    keep &= ~(1u << k);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)  // (static indices: c4 stays in registers)
+                        if ((k >> 2) == q) c4[q] |= c << (8 * (k & 3));
+                    const uint32_t isnw = (uint32_t)((c & 3u) != DPT_CLS_S && !(bloom && (c & DPT_CODE_BX)));
+                    nw = (nw & ~(1u << k)) | (isnw << k);
+                    if (ch.cls == DPT_CLS_L) al |= span;
+                } while (hi);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {  // byte-select: patched positions take c4, the others keep the LUT code
+                    const uint32_t kb = (keep >> (4 * q)) & 15u;
+                    const uint32_t km = ((kb & 1u) * 0xFFu) | ((kb & 2u) * (0xFF00u >> 1)) | ((kb & 4u) * (0xFF0000u >> 2)) | ((kb & 8u) * (0xFF000000u >> 3));
+                    cw[q] = (cw[q] & km) | (c4[q] & ~km);
+                }
+            }
+            *reinterpret_cast<uint4*>(&S.code[16 * hw]) = uint4{cw[0], cw[1], cw[2], cw[3]};
+            reinterpret_cast<uint16_t*>(S.mNW)[hw] = (uint16_t)nw;
+            // letters reach up to 3 bytes into the next thread's bits: everyone ORs into the zeroed mask
+            if (al) {
+                const uint64_t a64 = (uint64_t)al << (16 * (hw & 1));
+                blk.atomic_or(&S.mAL[hw >> 1], (uint32_t)a64);
+                if (a64 >> 32) blk.atomic_or(&S.mAL[(hw >> 1) + 1], (uint32_t)(a64 >> 32));
+            }
         }
     }
     blk.sync();
@@ -568,19 +647,14 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
         // (1) synchronisation points: document starts and every space whose next character is a non-whitespace
         // character of the same document
         for (int w = tid; w < PA_NW; w += nt) {
-            const uint32_t ds = S.mDS[w];
-            uint32_t sy = ds, sp = S.mSP[w];
-            while (sp) {
-                const int r = (w << 5) + pp_ctz(sp);
-                sp &= sp - 1;
-                if (r > PA_R - 6) continue;  // next character may not be loaded completely: no sync, scanned through
-                // only a document start within the next character can matter here
-                const uint64_t near = (((uint64_t)S.mDS[w] | ((uint64_t)S.mDS[w + 1] << 32)) >> (r & 31)) >> 1;
-                const int dend = (near & 0x1Fu) ? r + 1 + pp_ctz((uint32_t)(near & 0x1Fu)) : r + 8;
-                if (dpt_is_sync_space(P.rule, U, S.text, r, dend)) sy |= 1u << (r & 31);
-            }
-            S.mSY[w] = sy;
-            S.mCF[w] = S.mCS[w] | ds;
+            // a space, the next position in the same document, and a character there that is no whitespace (BLOOM: a
+            // character of the class) - dpt_is_sync_space, 32 positions at a time on the masks of the code pass
+            const uint32_t ds = S.mDS[w], dsn = S.mDS[w + 1];
+            const uint32_t nwn = w + 1 < PA_NW ? S.mNW[w + 1] : 0u;
+            uint32_t sy = S.mSP[w] & ((S.mNW[w] >> 1) | (nwn << 31)) & ~((ds >> 1) | (dsn << 31));
+            // within 6 bytes of the region's end the next character may not be loaded completely: no sync, scanned through
+            sy &= pp_range_mask(w, 0, PA_R - 5);
+            S.mSY[w] = sy | ds;
             S.mCX[w] = 0;
         }
         blk.sync();
@@ -644,15 +718,15 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                 // probe loop).
                 const int64_t rend = g0 + PA_R;
                 const int64_t send = dend < rend ? dend : rend;
-                const uint8_t* tsm = S.text - g0;
+                const PaCodeSrc tsm{S.code - g0, S.text - g0};
                 bool undecided = false;
                 while (p < stop) {
                     int64_t pe;
                     if (p >= g0) {
 #if defined(DPT_NO_LETTER_SKIP)  // tuning variant: the scanner walks letter runs character by character
-                        pe = dpt_piece_end(P.rule, U, tsm, p, send);
+                        pe = dpt_piece_end_src(P.rule, tsm, p, send, DptNoSkip{});
 #else
-                        pe = dpt_piece_end(P.rule, U, tsm, p, send, PaLetterSkip{S.mAL, g0});
+                        pe = dpt_piece_end_src(P.rule, tsm, p, send, PaLetterSkip{S.mAL, g0});
 #endif
                         if (send < dend && pe + 8 > rend) {
                             undecided = true;
@@ -1243,6 +1317,13 @@ DPT_PIPE_FN uint4 pc_ld_head(const ResRec* r) {
     return *reinterpret_cast<const uint4*>(r);
 #endif
 }
+DPT_PIPE_FN uint4 pc_ld_tail(const ResRec* r) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(reinterpret_cast<const uint4*>(r) + 1);
+#else
+    return reinterpret_cast<const uint4*>(r)[1];
+#endif
+}
 DPT_PIPE_FN const ResRec* pc_record_ptr(const PipeParams& P, uint32_t ref) {
     if ((ref & REF_KIND) == REF_ODD) {
         const uint32_t j = ref & REF_INDEX;
@@ -1383,6 +1464,14 @@ DPT_PIPE_FN void pc_run_tile(Blk& blk, const PipeParams& P, CSmem& S, const int 
                 if (gt < cap) dst[gt] = (int32_t)head[k].y;
                 if (nk > 1 && gt + 1 < cap) dst[gt + 1] = (int32_t)head[k].z;
                 if (nk > 2 && gt + 2 < cap) dst[gt + 2] = (int32_t)head[k].w;
+                if (nk > (uint32_t)RES_HEAD) {  // ids[3..6]: the second half of the record's sector
+                    const ResRec* r = pc_record_ptr(P, ref[k]);
+                    const uint4 t = r ? pc_ld_tail(r) : uint4{0u, 0u, 0u, 0u};
+                    if (gt + 3 < cap) dst[gt + 3] = (int32_t)t.x;
+                    if (nk > 4 && gt + 4 < cap) dst[gt + 4] = (int32_t)t.y;
+                    if (nk > 5 && gt + 5 < cap) dst[gt + 5] = (int32_t)t.z;
+                    if (nk > 6 && gt + 6 < cap) dst[gt + 6] = (int32_t)t.w;
+                }
             }
             gt += nk;
         }

@@ -388,6 +388,33 @@ __global__ void k_doc_tok_offs(const int64_t* __restrict__ doc_first_word, int64
     doc_tok_offs[d] = d == n_docs ? tok_offs[n_words] : tok_offs[doc_first_word[d]];
 }
 
+// Length-only DP with infinity initialisation (inspect_tokenizer.py:77-86 `min_tokens_for_string`): differs from the
+// lattice's len_dp only where the phantom initialisation of dp_tokenize.py:28 shows (untokenizable input).  One serial
+// thread like k_lattice: a known-answer entry point, not a throughput path.  out[0] = dp[n], -1 = infinity.
+__global__ void k_min_tokens(DptVocabView V, const uint8_t* __restrict__ s, int32_t n, const uint8_t* __restrict__ unit_starts,
+                             int32_t* __restrict__ out, int32_t* __restrict__ dp /* n+1 scratch, by byte position */) {
+    if (threadIdx.x || blockIdx.x) return;
+    const int32_t INF = 0x3FFFFFFF;
+    for (int32_t p = 0; p <= n; ++p) {
+        const bool b = (p == 0 || p == n) ? true
+                       : unit_starts      ? unit_starts[p] != 0
+                       : V.unit_mode == 0 ? true
+                                          : dpt_is_cp_start(s[p]);
+        dp[p] = b ? INF : -1;  // -1: not a unit boundary
+    }
+    dp[0] = 0;
+    for (int32_t j = 0; j < n; ++j) {
+        if (dp[j] < 0 || dp[j] >= INF) continue;
+        uint32_t entry = DPT_DA_ROOT_ENTRY;
+        for (int32_t i = j + 1; i <= n; ++i) {
+            if (!dpt_da_step(V.da, entry, s[i - 1])) break;
+            if ((entry & DPT_DA_TERMINAL) && dp[i] >= 0 && dp[j] + 1 < dp[i]) dp[i] = dp[j] + 1;
+        }
+    }
+    out[0] = dp[n] >= INF ? -1 : dp[n];
+}
+
+
 // ---------------------------------------------------------------------------------------------
 // lattice of one word (enumerate-all API, dp_tokenize.py:27-47): single thread, tiny inputs
 // ---------------------------------------------------------------------------------------------
@@ -816,6 +843,12 @@ int lattice_word(const dpt_vocab* v, const uint8_t* d_text, int32_t n_bytes, con
                  int32_t* d_unit_of, cudaStream_t st) {
     DPT_LAUNCH(k_lattice, 1, 32, st, v->d_view, d_text, n_bytes, d_unit_starts, d_len_dp, d_pred_offs, d_pred, pred_cap,
                d_n_out, d_unit_of);
+    return cudaGetLastError() == cudaSuccess ? DPT_OK : DPT_ECUDA;
+}
+
+int min_tokens_word(const dpt_vocab* v, const uint8_t* d_text, int32_t n_bytes, const uint8_t* d_unit_starts, int32_t* d_out,
+                    int32_t* d_scratch, cudaStream_t st) {
+    DPT_LAUNCH(k_min_tokens, 1, 32, st, v->d_view, d_text, n_bytes, d_unit_starts, d_out, d_scratch);
     return cudaGetLastError() == cudaSuccess ? DPT_OK : DPT_ECUDA;
 }
 

@@ -72,6 +72,9 @@ int lattice_word(const dpt_vocab* v, const uint8_t* d_text, int32_t n_bytes, con
                  int32_t* d_len_dp, int32_t* d_pred_offs, int32_t* d_pred, int32_t pred_cap, int32_t* d_n_out,
                  int32_t* d_unit_of, cudaStream_t st);
 
+int min_tokens_word(const dpt_vocab* v, const uint8_t* d_text, int32_t n_bytes, const uint8_t* d_unit_starts, int32_t* d_out,
+                    int32_t* d_scratch, cudaStream_t st);
+
 // synthetic corpus generator on the device (synth.cu; measurement support, not on the tokenization path)
 int synth_run(const uint8_t* a_bytes, const int64_t* a_offs, const uint32_t* a_cdf, int32_t a_n, const uint8_t* b_bytes,
               const int64_t* b_offs, const uint32_t* b_cdf, int32_t b_n, const dpt_synth_params* sp, int64_t doc_base,

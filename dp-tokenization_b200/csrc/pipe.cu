@@ -63,7 +63,11 @@ struct DevBlk {
         return atomicCAS(p, expect, desired);
     }
 
-    // block-wide exclusive scan of one uint32 per thread; every thread must call.  sm: >= 34 words.
+    // block-wide exclusive scan of one uint32 per thread; every thread must call.  sm: >= 34 words.  ONE barrier per call:
+    // the warp totals go to one of two alternating 16-word buffers and every warp scans them for itself with shuffles (a
+    // warp can only be two calls ahead of another after both passed the barrier of the call in between, so a buffer is
+    // never rewritten while it is still being read).  (Round 1: three barriers per call - 12 per tile of kernel A.)
+    mutable uint32_t scan_phase = 0;
     __device__ __forceinline__ uint32_t exclusive_scan(uint32_t v, uint32_t* sm, uint32_t& total) const {
         const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         uint32_t inc = v;
@@ -72,23 +76,19 @@ struct DevBlk {
             const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane >= (unsigned)d) inc += o;
         }
-        if (lane == 31) sm[warp] = inc;
+        uint32_t* const buf = sm + scan_phase;
+        scan_phase ^= 16u;
+        if (lane == 31) buf[warp] = inc;
         __syncthreads();
-        if (warp == 0) {
-            const uint32_t w = lane < nwarps ? sm[lane] : 0u;
-            uint32_t winc = w;
+        const uint32_t w = lane < nwarps ? buf[lane] : 0u;
+        uint32_t winc = w;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, winc, d);
-                if (lane >= (unsigned)d) winc += o;
-            }
-            sm[lane] = winc - w;
-            if (lane == 31) sm[32] = winc;
+        for (int d = 1; d < 16; d <<= 1) {  // at most 16 warps per block
+            const uint32_t o = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= (unsigned)d) winc += o;
         }
-        __syncthreads();
-        const uint32_t base = sm[warp];
-        total = sm[32];
-        __syncthreads();
+        total = __shfl_sync(0xffffffffu, winc, 15);
+        const uint32_t base = __shfl_sync(0xffffffffu, winc - w, warp);
         return base + inc - v;
     }
 
@@ -157,7 +157,10 @@ struct DevBlk {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {  // older tiles publish earlier, so every one of these becomes non-zero
                     const int idx = base - (lane * 4 + j);
-                    while ((v[j] >> 62) == 0) v[j] = ld_relaxed_gpu(&desc[idx]);
+                    while ((v[j] >> 62) == 0) {  // (a waiting lane gives its issue slots to the warps that are working)
+                        __nanosleep(40);
+                        v[j] = ld_relaxed_gpu(&desc[idx]);
+                    }
                 }
                 unsigned long long c = 0;
                 bool found = false;

@@ -75,6 +75,7 @@ SIGNATURES = {
     "dpt_encode_corpus_general": (C.c_int, [_p, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _p,
                                             _i64, _i32, _p]),
     "dpt_lattice_word": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _i32, _p, _p, _p]),
+    "dpt_min_tokens_word": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p]),
     "dpt_roundtrip_check": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _p, _p]),
     "dpt_narrow_ids_u16": (C.c_int, [_p, _p, _i64, _p, _p, _p]),
     "dpt_pad_batch": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _p, _p, _p, _p]),

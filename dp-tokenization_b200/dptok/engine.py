@@ -112,14 +112,17 @@ class Engine:
     # ---- corpus path: raw documents -> ids ------------------------------------------------------
     def encode_corpus(self, text: torch.Tensor, doc_offs: torch.Tensor, rule: int,
                       ids_cap: Optional[int] = None, word_cap: Optional[int] = None,
-                      force_general: bool = False) -> EncodeResult:
+                      force_general: bool = False, worst_case: bool = False) -> EncodeResult:
         """``text`` uint8 device tensor of concatenated non-empty documents; ``doc_offs`` int64[n_docs+1]
         (``doc_offs[0] == 0``, ``doc_offs[-1] == len(text)``).
 
         The corpus pipeline (``dpt_encode_corpus``): scan + dedup -> one DP per distinct word -> scan + emit,
         enqueued without host synchronisation; this wrapper then reads the 64-byte status vector and retries with
         larger buffers only if a capacity was exceeded.  ``force_general`` runs the non-deduplicating multi-kernel
-        path instead (``dpt_encode_corpus_general``; the cross-check)."""
+        path instead (``dpt_encode_corpus_general``; the cross-check).  ``worst_case``: size the word table and the odd-word
+        and long-word scratch for ANY text of this size at once (a corpus of mostly distinct words overflows the default
+        table of n_bytes / 48 slots: the first pass then reports it and the call runs a second time); ``self.last_worst``
+        says whether the last call needed it."""
         assert text.dtype == torch.uint8 and doc_offs.dtype == torch.int64 and text.is_cuda and doc_offs.is_cuda
         n_bytes = text.numel()
         n_docs = doc_offs.numel() - 1
@@ -130,7 +133,7 @@ class Engine:
             word_cap = n_bytes // 3 + 2 * n_docs + 64
         if force_general:
             return self._encode_corpus_general(text, doc_offs, rule, ids_cap, word_cap)
-        worst = 0
+        worst = 1 if worst_case else 0
         with torch.cuda.device(dev):
             for attempt in range(5):
                 ws = self._workspace(lib.dpt_encode_corpus_workspace(rule, n_bytes, n_docs, word_cap, worst))
@@ -162,12 +165,15 @@ class Engine:
             else:
                 raise _cabi.DptError(_cabi.ECAPACITY, f"capacity retries exhausted: {h}")
         nw = h[_cabi.NOUT_WORDS]
+        self.last_worst = bool(worst)
+        self.last_n_out = h
         return EncodeResult(ids[:h[0]], lens[:nw], flags[:nw], None, counters, h[0], nw, doc_tok, doc_flags)
 
     # ---- corpus path from HOST buffers: chunked, H2D / kernels / D2H overlapped ---------------------------------------
     def encode_corpus_host(self, h_text: torch.Tensor, doc_offs: np.ndarray, rule: int, chunk_bytes: int = 16 << 20,
                            n_streams: int = 3, out_ids: Optional[torch.Tensor] = None,
-                           overlap: bool = False, ids_dtype: torch.dtype = torch.int32) -> "HostResult":
+                           overlap: bool = False, ids_dtype: torch.dtype = torch.int32,
+                           want_ids: bool = True) -> "HostResult":
         """``h_text``: uint8 HOST tensor (pinned for full speed) of concatenated non-empty documents; ``doc_offs``:
         int64[n_docs+1] numpy array.  The corpus is cut at document boundaries into ranges of about ``chunk_bytes``.
         Range k is copied into its place in ONE device text buffer on the copy-in stream, tokenized by
@@ -181,7 +187,10 @@ class Engine:
         is bound by PCIe, whose two directions together move ~57 GB/s on this box (H2D alone 1.81 ms, D2H alone
         1.69 ms, 100.5 + 95.2 MB in 3.43 ms when both run).  ``ids_dtype=torch.uint16`` (vocabularies whose ids all fit
         16 bits: Llama-2 32k, GPT-2 50k) narrows the ids on the device (``dpt_narrow_ids_u16``) so that half as many
-        bytes cross PCIe on the way out; an id that does not fit raises."""
+        bytes cross PCIe on the way out; an id that does not fit raises.  ``want_ids=False``: the ids stay on the device
+        and only the per-document token offsets (8 bytes per document), flags and counters come back - what the statistics
+        loops of the reference consume (``len(dp_tokenize(a))``, main_analyze_s2orc.py:271,
+        main_biomed_translation.py:75-76); see ``corpus_lengths_host``."""
         if ids_dtype not in (torch.int32, torch.uint16):
             raise ValueError("ids_dtype must be torch.int32 or torch.uint16")
         narrow = ids_dtype == torch.uint16
@@ -201,7 +210,9 @@ class Engine:
         ids_cap = max_b // 2 + 2 * max_d + 64
         word_cap = max_b // 3 + 2 * max_d + 64
         word_cap_total = n_bytes // 3 + 2 * n_docs + 64
-        if out_ids is None:
+        if not want_ids:
+            out_ids = torch.empty(0, dtype=ids_dtype)
+        elif out_ids is None:
             out_ids = torch.empty(n_bytes // 2 + 2 * n_docs + 64, dtype=ids_dtype).pin_memory()
         assert out_ids.dtype == ids_dtype
         out_doc_tok = np.zeros(n_docs + 1, dtype=np.int64)
@@ -275,7 +286,8 @@ class Engine:
                     raise _cabi.DptError(_cabi.EINVAL, f"ids_dtype=uint16: {h[12]} token ids of range {k} do not fit 16 bits")
                 with torch.cuda.stream(s_out):              # the host has seen ev_comp: the ids are complete
                     mark("d2h-begin", k, s_out)
-                    out_ids[ids_base:ids_base + n_ids].copy_((sl["ids16"] if narrow else sl["ids"])[:n_ids], non_blocking=True)
+                    if want_ids:
+                        out_ids[ids_base:ids_base + n_ids].copy_((sl["ids16"] if narrow else sl["ids"])[:n_ids], non_blocking=True)
                     sl["ev_out"].record(s_out)
                     mark("d2h-end", k, s_out)
                 out_doc_tok[lo:hi] = sl["h_doc_tok"][:nd].numpy() + ids_base
@@ -351,16 +363,23 @@ class Engine:
                     st.synchronize()
                 res = self.encode_corpus(H["d_text"], H["d_offs"], rule)
                 ids_base = res.n_ids
-                if out_ids.numel() < ids_base:
+                if want_ids and out_ids.numel() < ids_base:
                     out_ids = torch.empty(ids_base, dtype=torch.int32).pin_memory()
                 if narrow and ids_base and int(res.ids.max().item()) > 0xFFFF:
                     raise _cabi.DptError(_cabi.EINVAL, "ids_dtype=uint16: token ids do not fit 16 bits")
-                out_ids[:ids_base].copy_(res.ids)
+                if want_ids:
+                    out_ids[:ids_base].copy_(res.ids)
                 out_doc_tok[:] = res.doc_tok_offs.cpu().numpy()
                 out_doc_flags[:] = res.doc_flags.cpu().numpy()
                 totals[:] = np.asarray(res.counters.cpu().tolist(), dtype=np.int64)
         out_doc_tok[n_docs] = ids_base
-        return HostResult(out_ids[:ids_base], out_doc_tok, out_doc_flags, totals, ids_base, n_chunks)
+        return HostResult(out_ids[:ids_base] if want_ids else out_ids, out_doc_tok, out_doc_flags, totals, ids_base, n_chunks)
+
+    def corpus_lengths_host(self, h_text: torch.Tensor, doc_offs: np.ndarray, rule: int, **kw) -> "HostResult":
+        """Lengths-only result of ``encode_corpus_host``: ``np.diff(result.doc_tok_offs)`` = tokens per document (the
+        reference's ``len(dp_tokenize(document))``), ``result.counters`` = {bytes, words, tokens, untokenizable}; no token
+        id crosses PCIe (8 bytes per document instead of 4 bytes per token on the way out)."""
+        return self.encode_corpus_host(h_text, doc_offs, rule, want_ids=False, **kw)
 
     def _encode_corpus_general(self, text, doc_offs, rule, ids_cap, word_cap) -> EncodeResult:
         """General multi-kernel CUDA path (normalise -> DP count -> scan -> DP emit): any word length."""
@@ -437,6 +456,25 @@ class Engine:
             pr = pred[:n_pred].cpu().tolist()
         preds = [pr[po[u]:po[u + 1]] for u in range(n_units + 1)]
         return ld, preds
+
+    def min_tokens(self, data: bytes, unit_starts: Optional[Sequence[int]] = None) -> float:
+        """dp[n] of the infinity-initialised length-only DP (inspect_tokenizer.py:77-86); float('inf') when unreachable."""
+        n = len(data)
+        if n == 0:
+            return 0
+        dev = self.device
+        with torch.cuda.device(dev):
+            text = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
+            us = None
+            if unit_starts is not None:
+                flags = np.zeros(n, dtype=np.uint8)
+                flags[[p for p in unit_starts if p < n]] = 1
+                us = torch.from_numpy(flags).to(dev)
+            out = torch.empty(1, dtype=torch.int32, device=dev)
+            scratch = torch.empty(n + 2, dtype=torch.int32, device=dev)
+            check(lib.dpt_min_tokens_word(self.vocab.handle, _ptr(text), n, _ptr(us), _ptr(out), _ptr(scratch), self._stream()))
+            v = int(out.item())
+        return float("inf") if v < 0 else v
 
     # ---- training-data feed on device (SURVEY.md 8 row f3) ------------------------------------------------------------
     def pad_batch(self, res: EncodeResult, pad_id: int, doc_begin: int = 0, n_rows: Optional[int] = None,

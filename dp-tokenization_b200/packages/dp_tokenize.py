@@ -24,18 +24,26 @@ _ENGINE_CACHE_MAX = 8
 
 
 def _engine_for(vocabulary) -> Engine:
-    """Compile (or reuse) the vocabulary.  Keyed by content, so mutating a set between calls is safe."""
+    """Compile (or reuse) the vocabulary.  Keyed by content and confirmed by EQUALITY (a hash collision cannot return
+    another vocabulary's engine; mutating a set between calls is safe).  Fast path without the O(|V|) rebuild: the same
+    immutable ``frozenset`` object as before."""
+    ident = _ENGINE_CACHE.get(("id", id(vocabulary))) if isinstance(vocabulary, frozenset) else None
+    if ident is not None and ident[0] is vocabulary:
+        return ident[1]
     try:
-        key = hash(frozenset(vocabulary))
+        fs = frozenset(vocabulary)
     except TypeError:
-        key = hash(frozenset(str(t) for t in vocabulary))
-    ent = _ENGINE_CACHE.get(key)
-    if ent is not None and ent[0] == len(vocabulary):
-        return ent[1]
-    eng = Engine(CompiledVocab.from_strings(vocabulary))
-    if len(_ENGINE_CACHE) >= _ENGINE_CACHE_MAX:
-        _ENGINE_CACHE.pop(next(iter(_ENGINE_CACHE)))
-    _ENGINE_CACHE[key] = (len(vocabulary), eng)
+        fs = frozenset(str(t) for t in vocabulary)
+    ent = _ENGINE_CACHE.get(hash(fs))
+    if ent is not None and ent[0] == fs:
+        eng = ent[1]
+    else:
+        eng = Engine(CompiledVocab.from_strings(vocabulary))
+        while len(_ENGINE_CACHE) >= 2 * _ENGINE_CACHE_MAX:
+            _ENGINE_CACHE.pop(next(iter(_ENGINE_CACHE)))
+        _ENGINE_CACHE[hash(fs)] = (fs, eng)
+    if isinstance(vocabulary, frozenset):
+        _ENGINE_CACHE[("id", id(vocabulary))] = (vocabulary, eng)
     return eng
 
 
@@ -101,3 +109,25 @@ def obtain_longest_token(tokenizations: List[List[str]]) -> List[str]:
         if m > best_len:
             best_len, best = m, toks
     return best
+
+
+def min_tokens_for_string(s, vocabulary):
+    """Fewest vocabulary tokens that spell ``s`` (``str`` or list of units); ``float('inf')`` when there is no
+    segmentation - the reference's ``inspect_tokenizer.min_tokens_for_string`` (inspect_tokenizer.py:77-86, the definition
+    that shadows :62-74; vectors tests/test_tokenization_algorithms.py:14-30).  Unlike ``len_dp[n]`` of
+    ``compute_shortest_tokenizations`` it starts from infinity, not from the phantom ``len_dp[i] = i``.  The DP runs on the
+    GPU (``dpt_min_tokens_word``)."""
+    if len(s) == 0:
+        return 0
+    if isinstance(s, str):
+        data, starts = s.encode("utf-8"), None
+    else:
+        pieces = [u.encode("utf-8") for u in s]
+        if any(len(p) == 0 for p in pieces):
+            raise ValueError("empty units are not supported by the device DP")
+        data = b"".join(pieces)
+        starts, pos = [], 0
+        for p in pieces:
+            starts.append(pos)
+            pos += len(p)
+    return _engine_for(vocabulary).min_tokens(data, starts)

@@ -258,6 +258,14 @@ int dpt_lattice_word(const dpt_vocab* v, const uint8_t* d_text, int32_t n_bytes,
                      int32_t* d_len_dp, int32_t* d_pred_offs, int32_t* d_pred, int32_t pred_cap,
                      int32_t* d_n_out, int32_t* d_scratch, void* stream);
 
+/* ---- length-only DP with INFINITY initialisation (inspect_tokenizer.py:77-86, `min_tokens_for_string`;
+ *      vectors tests/test_tokenization_algorithms.py:14-30): dp[0] = 0, dp[i] = min dp[j] + 1 over vocabulary
+ *      edges.  Differs from d_len_dp of dpt_lattice_word only on untokenizable input (that one carries the
+ *      phantom initialisation of dp_tokenize.py:28).  d_out: int32[1] = dp[n_units], -1 = infinity;
+ *      d_scratch: int32[n_bytes+1].  One serial thread: a known-answer entry point, not a throughput path. */
+int dpt_min_tokens_word(const dpt_vocab* v, const uint8_t* d_text, int32_t n_bytes,
+                        const uint8_t* d_unit_starts, int32_t* d_out, int32_t* d_scratch, void* stream);
+
 /* ---- decode / round-trip check on device (tokenizer_utils.py:82-84,176-179; the asserts at
  *      main_analyze_s2orc.py:85 and main_biomed_translation.py:78): ids -> bytes via the
  *      id->string table (CODEPOINTS vocab: U+2581 -> ' ', "<0xHH>" tokens -> that byte, the one

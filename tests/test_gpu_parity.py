@@ -137,6 +137,33 @@ def test_bytelevel_adapter_golden(dev):
 
 # ------------------------------------------------------------------------------------------------
 # C ABI at scale against the oracle
+def test_min_tokens_for_string_on_gpu(dev):
+    """a6: inspect_tokenizer.py:77-86 through packages.dp_tokenize.min_tokens_for_string (dpt_min_tokens_word): the five
+    vectors of tests/test_tokenization_algorithms.py:14-30, infinity for untokenizable input (where len_dp of the 4-arg
+    API carries the phantom value instead), list-of-units input, and 2,000 random C0 words against the golden values the
+    unmodified reference produced."""
+    from packages.dp_tokenize import compute_shortest_tokenizations, min_tokens_for_string
+    k = load_golden("known_answers.json")
+    assert [min_tokens_for_string(r["s"], set(r["vocab"])) for r in k["min_tokens"]] == [2, 6, 3, 2, 3]
+    for r in k["phantom"]:  # a real segmentation may exist although the 4-arg API returns ([], phantom)
+        from oracle import dp_oracle
+        assert min_tokens_for_string(r["s"], set(r["vocab"])) == dp_oracle.min_tokens(r["s"], set(r["vocab"]))
+    assert min_tokens_for_string("qrsTUV", {"qr", "s", "T", "U", "V", "rsTUV"}) == 5      # phantom len_dp says 2
+    assert compute_shortest_tokenizations("qrsTUV", {"qr", "s", "T", "U", "V", "rsTUV"}, False, "")[1] == 2
+    assert min_tokens_for_string("xyz", {"x", "y"}) == float("inf")
+    assert min_tokens_for_string("", {"x"}) == 0
+    units = ["▁t", "h", "e", "▁", "w"]
+    assert min_tokens_for_string(units, {"▁t", "h", "e", "▁", "w", "▁the", "he", "▁w"}) == 2
+    assert min_tokens_for_string(["ab", "c"], {"a", "bc", "ab", "c"}) == 2
+    assert min_tokens_for_string(["ab", "c"], {"a", "bc"}) == float("inf")   # "a" + "bc" would split inside the unit "ab"
+    assert min_tokens_for_string("abc", {"a", "bc"}) == 2
+    c0 = load_golden("c0_toy.json.gz")
+    vocab = frozenset(c0["vocab"])
+    for r in c0["rows"][:2000]:
+        got = min_tokens_for_string(r["w"], vocab)
+        assert (None if got == float("inf") else got) == r["min_tokens"], r["w"]
+
+
 # ------------------------------------------------------------------------------------------------
 def _llama_engine(name, dev):
     from dptok import assets
@@ -253,6 +280,53 @@ def test_edge_cases_long_oov_untokenizable(dev):
         assert np.array_equal(res.ids.cpu().numpy(), o_ids)
     long_flag = (res.word_flags.cpu().numpy() & 4) != 0
     assert np.array_equal(long_flag, (woffs[1:] - woffs[:-1]) > 64)
+
+
+def test_undersized_word_table_odd_words_and_worst_case_retry(dev):
+    """The word table holds n_bytes / 48 slots.  (1) a corpus whose DISTINCT words outnumber the slots of their
+    neighbourhoods: the occurrences that find 16 probed slots taken become odd words (solved per occurrence from the raw
+    text) - on the GPU, not only in the host emulation; (2) a corpus of distinct words only: the odd-word list overflows
+    too, the pass reports it and the engine runs again with worst-case sizes.  Both bit-exact against the C oracle."""
+    from dptok import _cabi
+    from oracle import adapters
+    from oracle.c_oracle import COracle
+    tok, t2i, eng = _llama_engine("llama2_32k", dev)
+    vocab = set(t2i)
+    orc = COracle(vocab_bytes(t2i, "spm"), 1)
+    rng = random.Random(11)
+    letters = "abcdefghijklmnopqrstuvwxyz"
+
+    def fresh(k):
+        return "".join(rng.choice(letters) for _ in range(rng.randint(3, 11))) + format(k, "x")
+
+    def corpus(n_words, n_distinct, doc_words=180):
+        pool = [fresh(k) for k in range(n_distinct)]
+        seq = pool + [rng.choice(pool) for _ in range(n_words - n_distinct)]
+        rng.shuffle(seq)
+        docs = [" ".join(seq[k:k + doc_words]).encode() for k in range(0, len(seq), doc_words)]
+        offs = np.zeros(len(docs) + 1, dtype=np.int64)
+        np.cumsum([len(d) for d in docs], out=offs[1:])
+        return np.frombuffer(b"".join(docs), dtype=np.uint8).copy(), offs, docs
+
+    for n_words, n_distinct, expect_worst in ((130_000, 46_000, False), (120_000, 120_000, True)):
+        text, offs, docs = corpus(n_words, n_distinct)
+        res = eng.encode_corpus(_to_dev(text, dev), _to_dev(offs, dev), _cabi.RULE_SPM_LLAMA)
+        h = eng.last_n_out
+        assert eng.last_worst == expect_worst, (h, len(text))
+        if not expect_worst:
+            n_slots = 4096
+            while n_slots < len(text) // 48:
+                n_slots *= 2
+            assert n_distinct > n_slots and h[6] > 1000, ("the table was meant to overflow into odd words", n_slots, h)
+        words = []
+        for d in docs:
+            words += [w.encode() for w in adapters.spm_normalise(d.decode(), vocab)]
+        wtext, woffs = pack(words)
+        o_ids, o_lens, o_untok = orc.encode_words(wtext, woffs)
+        assert res.n_words == len(words)
+        assert np.array_equal(res.word_lens.cpu().numpy(), o_lens)
+        assert np.array_equal(res.ids.cpu().numpy(), o_ids)
+        assert res.counters.cpu().tolist() == [len(text), len(words), len(o_ids), int(o_untok.sum())]
 
 
 def test_spm_rule_oov_and_ambiguous_docs(dev):
