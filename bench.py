@@ -322,9 +322,8 @@ def measure_resident(cx: Ctx, engine, d_text, d_offs, rule, steps, warmup, with_
     ids_cap, word_cap = res.n_ids + 1024, res.n_words + 1024
     # a corpus of mostly distinct words overflows the default word table (n_bytes / 48 slots): the engine then sizes it for
     # the worst case and runs the pass again.  The timed steps ask for that size at once, so a step is ONE pass.
-    worst = bool(getattr(engine, "last_worst", False))
-    engine.encode_corpus(d_text, d_offs, rule, ids_cap=ids_cap, word_cap=word_cap, worst_case=worst)
-    worst = worst or bool(engine.last_worst)
+    engine.encode_corpus(d_text, d_offs, rule, ids_cap=ids_cap, word_cap=word_cap)
+    worst = int(engine.last_worst)  # 0 typical, 2 roomy word table, 1 worst-case sizes (chosen by the engine during the warm-up)
     launches0 = eng_mod.launch_count()
     cx.barrier()
     if sampler:
@@ -429,7 +428,7 @@ def distinct_share(cx: Ctx, engine, wl, word_cap, worst=False):
     """Share of distinct words of a corpus = words the DP kernels solved / word occurrences (device counters)."""
     import numpy as np
     from dptok._cabi import lib
-    tb = lib.dpt_corpus_table_workspace(wl["n_bytes"], word_cap, 1 if worst else 0)
+    tb = lib.dpt_corpus_table_workspace(wl["n_bytes"], word_cap, int(worst))
     tb_al = (tb + 255) // 256 * 256
     ctl = engine._ws[tb_al:tb_al + 64].cpu().numpy().view(np.uint32)
     return int(ctl[2:7].sum() + ctl[7])  # n_pending[0..4] + n_odd
@@ -456,9 +455,31 @@ def latency_record(cx: Ctx, wl_s2orc):
     ref = [adapters.llama_encode(tok, d) for d in docs[20:40]]
     dt_ref = time.perf_counter() - t0
     assert ref == out[:20], "per-call path disagrees with the oracle"
-    return {"call": "dp_tokenize_llama(tok)(abstract)", "mean_doc_bytes": sum(len(d.encode()) for d in docs[20:220]) / 200,
-            "latency_us": 1e6 * dt / 200, "calls": 200,
-            "cpu_oracle_latency_us": 1e6 * dt_ref / 20, "cpu_oracle": "oracle.adapters.llama_encode (closed-form DP, one core), 20 calls"}
+    rec = {"call": "dp_tokenize_llama(tok)(abstract)", "mean_doc_bytes": sum(len(d.encode()) for d in docs[20:220]) / 200,
+           "latency_us": 1e6 * dt / 200, "calls": 200,
+           "cpu_oracle_latency_us": 1e6 * dt_ref / 20, "cpu_oracle": "oracle.adapters.llama_encode (closed-form DP, one core), 20 calls"}
+    # the byte-level adapter on the same abstracts (GPT-2-shaped 50k vocabulary, split regex on the device)
+    try:
+        from packages.tokenizer_utils import dp_tokenize_bloom
+        btok = assets.load_hf("gpt2_50k")
+        benc, _bdec = dp_tokenize_bloom(btok, None, device=cx.dev)
+        for d in docs[:20]:
+            benc(d)
+        cx.torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        bout = [benc(d) for d in docs[20:220]]
+        bdt = time.perf_counter() - t0
+        bvocab = {t: k for k, t in enumerate(assets.load_spec("gpt2_50k")["model"]["vocab"])}
+        t0 = time.perf_counter()
+        bref = [adapters.bytelevel_encode(btok, bvocab, d) for d in docs[20:30]]
+        bdt_ref = time.perf_counter() - t0
+        assert bref == bout[:10], "byte-level per-call path disagrees with the oracle"
+        rec["bytelevel"] = {"call": "dp_tokenize_bloom(tok, None)(abstract)", "latency_us": 1e6 * bdt / 200, "calls": 200,
+                            "device_rule": getattr(benc, "device_rule", None),
+                            "cpu_oracle_latency_us": 1e6 * bdt_ref / 10}
+    except Exception as e:  # noqa: BLE001
+        rec["bytelevel"] = {"error": repr(e)}
+    return rec
 
 
 def main():

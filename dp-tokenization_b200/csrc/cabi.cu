@@ -18,7 +18,7 @@ int fail(int code, const std::string& msg) {
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct BlobLayout {
-    int64_t da, slot_id, ph_seed, ph_id, tok_bytes, tok_offs, id_rank, uni1, uni2, total;
+    int64_t da, slot_id, ph_seed, ph_id, tok_bytes, tok_offs, id_rank, uni1, uni2, merge_keys, merge_vals, byte_ids, total;
 };
 BlobLayout layout_of(const dpt_vocab* v) {
     BlobLayout L{};
@@ -41,6 +41,12 @@ BlobLayout layout_of(const dpt_vocab* v) {
     o = align_up(o + DPT_UNI_STAGE1_LEN, 256);
     L.uni2 = o;
     o = align_up(o + DPT_UNI_STAGE2_LEN, 256);
+    L.merge_keys = o;
+    o = align_up(o + (int64_t)v->merge_keys.size() * 8, 256);
+    L.merge_vals = o;
+    o = align_up(o + (int64_t)v->merge_vals.size() * 8, 256);
+    L.byte_ids = o;
+    o = align_up(o + 256 * 4, 256);
     L.total = o;
     return L;
 }
@@ -63,7 +69,7 @@ bool get_vec(const uint8_t*& p, const uint8_t* end, std::vector<T>& v) {
     uint64_t n;
     std::memcpy(&n, p, 8);
     p += 8;
-    if ((uint64_t)(end - p) < n * sizeof(T)) return false;
+    if (n > (uint64_t)(end - p) / sizeof(T)) return false;  // (no n * sizeof(T): a corrupt count must not wrap)
     v.resize(n);
     std::memcpy(v.data(), p, n * sizeof(T));
     p += n * sizeof(T);
@@ -198,13 +204,33 @@ int dpt_vocab_deserialize(const uint8_t* buf, int64_t len, dpt_vocab** out) {
     std::memcpy(v->byte_token_id, h.byte_token_id, sizeof h.byte_token_id);
     const uint8_t* p = buf + sizeof h;
     const uint8_t* end = buf + len;
-    const bool ok = get_vec(p, end, v->da) && get_vec(p, end, v->slot_id) && get_vec(p, end, v->ph_seed) &&
-                    get_vec(p, end, v->ph_id) && get_vec(p, end, v->tok_bytes) && get_vec(p, end, v->tok_offs) &&
-                    get_vec(p, end, v->tok_ids) && get_vec(p, end, v->id_rank);
-    if (!ok || v->da.size() < 257 || v->ph_seed.empty() || v->ph_id.empty() ||
-        (v->ph_seed.size() & (v->ph_seed.size() - 1)) || (v->ph_id.size() & (v->ph_id.size() - 1))) {
+    bool ok = false;
+    try {  // (nothing may throw across the extern "C" boundary: a corrupt count could ask resize() for the moon)
+        ok = get_vec(p, end, v->da) && get_vec(p, end, v->slot_id) && get_vec(p, end, v->ph_seed) &&
+             get_vec(p, end, v->ph_id) && get_vec(p, end, v->tok_bytes) && get_vec(p, end, v->tok_offs) &&
+             get_vec(p, end, v->tok_ids) && get_vec(p, end, v->id_rank);
+    } catch (...) {
+        ok = false;
+    }
+    ok = ok && v->da.size() >= 257 && v->da.size() <= (size_t)DPT_DA_MAX_SLOTS + 256 && !v->ph_seed.empty() && !v->ph_id.empty() &&
+         !(v->ph_seed.size() & (v->ph_seed.size() - 1)) && !(v->ph_id.size() & (v->ph_id.size() - 1)) &&
+         v->slot_id.size() == v->da.size() && v->n_tokens >= 0 && v->tok_offs.size() == (size_t)v->n_tokens + 1 &&
+         v->tok_ids.size() == (size_t)v->n_tokens && v->id_space >= 0 && v->id_rank.size() == (size_t)v->id_space;
+    if (ok) {
+        // every trie base must leave its 256 children inside the array (the kernels index da[base + byte] unchecked), every
+        // token's bytes inside tok_bytes, every id inside the id space
+        const size_t nda = v->da.size();
+        for (size_t k = 0; ok && k < nda; ++k) ok = (size_t)(v->da[k] >> DPT_DA_BASE_SHIFT) + 256 <= nda;
+        ok = ok && (size_t)(v->marker_entry >> DPT_DA_BASE_SHIFT) + 256 <= nda;
+        for (size_t k = 0; ok && k < nda; ++k) ok = v->slot_id[k] < v->id_space;
+        for (int32_t k = 0; ok && k < v->n_tokens; ++k)
+            ok = v->tok_offs[k] >= 0 && v->tok_offs[k] <= v->tok_offs[k + 1] && v->tok_ids[k] >= 0 && v->tok_ids[k] < v->id_space;
+        ok = ok && (v->n_tokens == 0 || (size_t)v->tok_offs[v->n_tokens] <= v->tok_bytes.size());
+        for (size_t k = 0; ok && k < v->ph_id.size(); ++k) ok = v->ph_id[k] < v->n_tokens;
+    }
+    if (!ok) {
         delete v;
-        return fail(DPT_EINVAL, "dpt_vocab_deserialize: truncated or corrupt buffer");
+        return fail(DPT_EINVAL, "dpt_vocab_deserialize: truncated, corrupt or inconsistent buffer");
     }
     v->derive_facts();
     *out = v;
@@ -238,6 +264,11 @@ int dpt_vocab_upload(dpt_vocab* v, int device) {
     cudaMemcpy(d + L.tok_offs, v->tok_offs.data(), v->tok_offs.size() * 8, cudaMemcpyHostToDevice);
     cudaMemcpy(d + L.uni1, DPT_UNI_STAGE1, DPT_UNI_STAGE1_LEN, cudaMemcpyHostToDevice);
     cudaMemcpy(d + L.uni2, DPT_UNI_STAGE2, DPT_UNI_STAGE2_LEN, cudaMemcpyHostToDevice);
+    cudaMemcpy(d + L.byte_ids, v->byte_token_id, 256 * 4, cudaMemcpyHostToDevice);
+    if (!v->merge_keys.empty()) {
+        cudaMemcpy(d + L.merge_keys, v->merge_keys.data(), v->merge_keys.size() * 8, cudaMemcpyHostToDevice);
+        cudaMemcpy(d + L.merge_vals, v->merge_vals.data(), v->merge_vals.size() * 8, cudaMemcpyHostToDevice);
+    }
     e = cudaMemcpy(d + L.id_rank, v->id_rank.data(), v->id_rank.size() * 4, cudaMemcpyHostToDevice);
     cudaDeviceSynchronize();
     cudaSetDevice(cur);
@@ -258,6 +289,25 @@ int dpt_vocab_upload(dpt_vocab* v, int device) {
     v->d_view.id_rank = (const int32_t*)(d + L.id_rank);
     v->d_view.uni1 = (const uint8_t*)(d + L.uni1);
     v->d_view.uni2 = (const uint8_t*)(d + L.uni2);
+    v->d_view.merge_keys = v->merge_keys.empty() ? nullptr : (const unsigned long long*)(d + L.merge_keys);
+    v->d_view.merge_vals = v->merge_vals.empty() ? nullptr : (const unsigned long long*)(d + L.merge_vals);
+    v->d_view.byte_ids = (const int32_t*)(d + L.byte_ids);
+    return DPT_OK;
+}
+
+int dpt_vocab_set_merges(dpt_vocab* v, const int32_t* left, const int32_t* right, const int32_t* merged, int32_t n_merges) {
+    if (!v || n_merges < 0 || (n_merges > 0 && (!left || !right || !merged)))
+        return fail(DPT_EINVAL, "dpt_vocab_set_merges: bad argument");
+    if (v->d_blob) return fail(DPT_ESTATE, "dpt_vocab_set_merges: call before dpt_vocab_upload");
+    for (int32_t k = 0; k < n_merges; ++k)
+        if (left[k] < 0 || right[k] < 0 || merged[k] < 0 || left[k] >= v->id_space || right[k] >= v->id_space ||
+            merged[k] >= v->id_space)
+            return fail(DPT_EINVAL, "dpt_vocab_set_merges: token id outside the vocabulary's id space");
+    try {
+        if (v->set_merges(left, right, merged, n_merges)) return fail(DPT_EINVAL, "dpt_vocab_set_merges: bad merge");
+    } catch (...) {
+        return fail(DPT_ENOMEM, "dpt_vocab_set_merges: out of memory");
+    }
     return DPT_OK;
 }
 

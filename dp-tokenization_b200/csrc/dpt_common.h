@@ -56,6 +56,14 @@ struct DptVocabView {
     // all 256 single bytes are tokens (byte-level) / U+2581 alone is a token (code points): then no position
     // is unreachable for in-vocabulary characters and the phantom init of dp_tokenize.py:28 never undercuts
     int32_t fast_ok;
+    // BPE merge table of the tokenizer (dpt_vocab_set_merges): open addressing, key = (left id + 1) << 32 | (right id + 1),
+    // value = rank << 32 | merged id; merge_mask = slots - 1, 0 when the caller gave no merges.  Only the SPM_LLAMA rule's
+    // marker runs need it (tokenizer_utils.py:7-31: word boundaries follow the DEFAULT tokenizer's tokens).
+    const unsigned long long* merge_keys;
+    const unsigned long long* merge_vals;
+    uint32_t merge_mask;
+    const int32_t* byte_ids;   // id of the token "<0xHH>" per byte value (-1 if absent): the default tokenizer's symbol for
+                               // a character that is no vocabulary entry (byte_fallback)
 };
 
 // One trie step.  `entry` is the slot VALUE of the current node (it carries the base), not its
@@ -114,6 +122,27 @@ DPT_HD uint32_t dpt_ph_slot(const DptHashState& s, uint32_t seed, uint32_t slot_
 DPT_HD int32_t dpt_ph_lookup(const DptVocabView& v, const DptHashState& s) {
     const uint32_t seed = v.ph_seed[dpt_ph_bucket(s, v.ph_bucket_mask)];
     return v.ph_id[dpt_ph_slot(s, seed, v.ph_slot_mask)];
+}
+
+DPT_HD uint32_t dpt_merge_hash(int32_t l, int32_t r) {
+    return dpt_fmix32((uint32_t)l * 0x9E3779B1u + dpt_fmix32((uint32_t)r + 0x7F4A7C15u));
+}
+// rank and merged id of the BPE merge (l, r); false when the pair does not merge
+DPT_HD bool dpt_merge_lookup(const DptVocabView& v, int32_t l, int32_t r, uint32_t& rank, int32_t& merged) {
+    if (!v.merge_mask || l < 0 || r < 0) return false;
+    const unsigned long long key = ((unsigned long long)(uint32_t)(l + 1) << 32) | (unsigned long long)(uint32_t)(r + 1);
+    uint32_t h = dpt_merge_hash(l, r) & v.merge_mask;
+    for (;;) {
+        const unsigned long long k = v.merge_keys[h];
+        if (k == key) {
+            const unsigned long long val = v.merge_vals[h];
+            rank = (uint32_t)(val >> 32);
+            merged = (int32_t)(uint32_t)val;
+            return true;
+        }
+        if (k == 0ull) return false;
+        h = (h + 1u) & v.merge_mask;
+    }
 }
 
 DPT_HD bool dpt_is_cp_start(uint32_t b) { return (b & 0xC0u) != 0x80u; }

@@ -788,7 +788,8 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
             S.cnt[w] = (uint32_t)(pp_popc(ws & rm) + (spm ? pp_popc(ds & rm) : 0)) |
                        ((uint32_t)pp_popc(ds & upto_mask(w)) << 16);
             amb &= rm;
-            while (amb && P.doc_flags) {
+            // (with the tokenizer's merge table kernel B splits these runs itself: pb_segment_split; nothing is ambiguous)
+            while (amb && P.doc_flags && !P.V.merge_mask) {
                 const int r = (w << 5) + pp_ctz(amb);
                 amb &= amb - 1;
                 const int64_t d = pp_upper_bound(P.doc_offs, P.n_docs + 1, g0 + r) - 1;
@@ -1072,6 +1073,87 @@ DPT_PIPE_FN int32_t pb_normalise(const PipeParams& P, int64_t p, int64_t e_end, 
     return n;
 }
 
+// ---- SentencePiece marker runs (tokenizer_utils.py:7-31) ------------------------------------------------
+// The reference's words are the DEFAULT tokenizer's tokens glued together up to the next token that starts with U+2581.
+// Between two non-marker characters separated by ONE marker that is the marker itself; inside a RUN of markers ("a   b",
+// leading spaces, "\n\n  indented") it depends on which markers the default BPE merged with each other ("▁▁") and which
+// with the text behind them ("▁b"), i.e. on the merge ranks.  Kernel A keeps such a run and the text up to the next
+// single marker as ONE odd word; here it is cut the way the tokenizer cuts it: the characters become the tokenizer's
+// initial symbols (a character that is no vocabulary entry: its "<0xHH>" byte tokens), the merge table is applied in rank
+// order, leftmost first (`tokenizers` BPE: Word::merge_all), and a new word starts at every resulting token whose first
+// symbol is a marker.  No merge crosses the ends of the segment: no vocabulary entry has a marker behind another
+// character (marker_leading_only, a precondition of the device rule).
+constexpr int PB_SEG_MAX = 512;  // symbols; longer segments (whitespace art) are flagged for the host split
+// true when raw bytes [p, e) hold a marker character (' ' or U+2581) behind their first character (virt: anywhere)
+DPT_PIPE_FN bool pb_raw_inner_marker(const PipeParams& P, int64_t p, int64_t e, bool virt) {
+    int64_t q = p;
+    if (!virt) {  // skip the leading marker character of the word itself
+        q = p + 1;
+        while (q < e && !dpt_is_cp_start(P.text[q])) ++q;
+    }
+    for (; q < e; ++q) {
+        const uint32_t c = P.text[q];
+        if (c == 0x20u) return true;
+        if (c == DPT_MARK0 && q + 2 < e && P.text[q + 1] == DPT_MARK1 && P.text[q + 2] == DPT_MARK2) return true;
+    }
+    return false;
+}
+// symbol = id << 32 | raw offset of its first byte (relative to the segment start) << 1 | its first symbol is a marker.
+// Returns the number of word starts written to cut[] (offsets relative to p; cut[0] = 0), or -1: too long for PB_SEG_MAX.
+DPT_PIPE_FN int32_t pb_segment_split(const PipeParams& P, int64_t p, int64_t e_end, bool virt, unsigned long long* sym,
+                                     int32_t sym_cap, uint32_t* cut) {
+    const DptVocabView& V = P.V;
+    const int32_t marker_id = V.slot_id[V.marker_slot];
+    int32_t n = 0;
+    if (virt) sym[n++] = ((unsigned long long)(uint32_t)marker_id << 32) | 1ull;  // Prepend(U+2581): no raw byte of its own
+    for (int64_t q = p; q < e_end;) {
+        int64_t e = q + 1;
+        while (e < e_end && !dpt_is_cp_start(P.text[e])) ++e;
+        const uint32_t c0 = P.text[q];
+        const bool mk = (c0 == 0x20u) || (e - q == 3 && c0 == DPT_MARK0 && P.text[q + 1] == DPT_MARK1 && P.text[q + 2] == DPT_MARK2);
+        const unsigned long long off = (unsigned long long)(q - p) << 1;
+        if (mk) {
+            if (n + 1 > sym_cap) return -1;
+            sym[n++] = ((unsigned long long)(uint32_t)marker_id << 32) | off | 1ull;
+        } else {
+            uint32_t entry = DPT_DA_ROOT_ENTRY, slot = 0;
+            bool hit = true;
+            for (int64_t k = q; k < e && hit; ++k) hit = dpt_da_step_idx(V.da, entry, P.text[k], slot);
+            if (hit && (entry & DPT_DA_TERMINAL)) {
+                if (n + 1 > sym_cap) return -1;
+                sym[n++] = ((unsigned long long)(uint32_t)V.slot_id[slot] << 32) | off;
+            } else {  // byte fallback: one symbol per byte (they take no part in merges of their own)
+                if (n + (int32_t)(e - q) > sym_cap) return -1;
+                for (int64_t k = q; k < e; ++k) sym[n++] = ((unsigned long long)(uint32_t)V.byte_ids[P.text[k]] << 32) | off;
+            }
+        }
+        q = e;
+    }
+    // BPE: the lowest-ranked adjacent pair, leftmost on ties, until none merges
+    for (;;) {
+        uint32_t best = 0xFFFFFFFFu;
+        int32_t bi = -1, bid = 0;
+        for (int32_t i = 0; i + 1 < n; ++i) {
+            uint32_t rank;
+            int32_t merged;
+            if (dpt_merge_lookup(V, (int32_t)(uint32_t)(sym[i] >> 32), (int32_t)(uint32_t)(sym[i + 1] >> 32), rank, merged) &&
+                rank < best) {
+                best = rank;
+                bi = i;
+                bid = merged;
+            }
+        }
+        if (bi < 0) break;
+        sym[bi] = ((unsigned long long)(uint32_t)bid << 32) | (sym[bi] & 0xFFFFFFFFull);
+        for (int32_t i = bi + 1; i + 1 < n; ++i) sym[i] = sym[i + 1];
+        --n;
+    }
+    int32_t nc = 0;
+    for (int32_t i = 0; i < n; ++i)
+        if (i == 0 || (sym[i] & 1ull)) cut[nc++] = (uint32_t)((sym[i] & 0xFFFFFFFFull) >> 1);
+    return nc;
+}
+
 // entries of length class c that kernel A could store (see the enqueue at the end of pa_run_tile)
 DPT_PIPE_FN uint32_t pb_queue_len(const PipeParams& P, int c) {
     const uint32_t n = P.ctl->n_pending[c];
@@ -1200,7 +1282,10 @@ DPT_PIPE_FN void pb_thread(Blk& blk, const PipeParams& P) {
             if (got) {
                 uint32_t tagged;
                 const PbItem it = pb_item(P, idx, npc, n_odd, &tagged);
-                const int32_t nlen = pb_normalise(P, it.pos, it.end, it.marker, norm, PB_LOCAL);
+                int32_t nlen = pb_normalise(P, it.pos, it.end, it.marker, norm, PB_LOCAL);
+                // an odd word with a marker run inside: the long-word kernel cuts it into the tokenizer's words (pb_segment_split)
+                if (nlen > 0 && P.spm && P.V.merge_mask && (tagged & 0x80000000u) && pb_raw_inner_marker(P, it.pos, it.end, it.marker))
+                    nlen = -1;
                 if (nlen < 0) {  // too long for the local state: the long-word kernel solves it
                     const uint32_t q = blk.atomic_add_ret(&P.ctl->n_long, 1u);
                     P.longq[q] = tagged;
@@ -1253,7 +1338,10 @@ DPT_PIPE_FN void pb_long_thread(Blk& blk, const PipeParams& P, int64_t gtid, int
     for (uint64_t k = (uint64_t)gtid; k < n_long; k += (uint64_t)gthreads) {
         const PbItem it = pb_item_tagged(P, P.longq[k]);
         const int64_t raw = it.end - it.pos;
-        const int64_t need = (P.spm ? 6 * raw + 3 : raw) + 2;
+        const int64_t need_dp = (P.spm ? 6 * raw + 3 : raw) + 2;
+        // a marker-run segment (see pb_segment_split) also needs its symbols and its cuts: 1.5 x (raw + 2) positions of lp_best
+        const bool seg = P.spm && P.V.merge_mask && raw + 1 <= PB_SEG_MAX && pb_raw_inner_marker(P, it.pos, it.end, it.marker);
+        const int64_t need = need_dp + (seg ? raw + 2 + (raw + 2) / 2 + 1 : 0);
         const unsigned long long off = blk.atomic_add_u64_ret(&P.ctl->lp_used, (unsigned long long)need);
         ResRec rec;
         for (int q = 0; q < RES_INLINE; ++q) rec.ids[q] = 0;
@@ -1267,6 +1355,50 @@ DPT_PIPE_FN void pb_long_thread(Blk& blk, const PipeParams& P, int64_t gtid, int
         uint64_t* best = P.lp_best + off;
         uint16_t* A = P.lp_a + off;
         uint16_t* B = P.lp_b + off;
+        if (P.spm && P.V.merge_mask && !seg && pb_raw_inner_marker(P, it.pos, it.end, it.marker) && P.doc_flags) {
+            // a marker run too long to split here: the document goes back to the host split (DPT_DF_AMBIGUOUS)
+            const int64_t d = pp_upper_bound(P.doc_offs, P.n_docs + 1, it.pos) - 1;
+            if (d >= P.doc_begin && d < P.doc_begin + P.n_docs_local) P.doc_flags[d - P.doc_begin] = 1;
+        }
+        if (seg) {
+            unsigned long long* sym = reinterpret_cast<unsigned long long*>(best + need_dp);
+            uint32_t* cut = reinterpret_cast<uint32_t*>(sym + raw + 2);
+            const int32_t nc = pb_segment_split(P, it.pos, it.end, it.marker, sym, (int32_t)(raw + 2), cut);
+            // two passes over the words of the segment: token counts, then (one pool allocation) the ids
+            uint32_t total = 0;
+            bool reach_all = nc > 0;
+            unsigned long long po = 0;
+            for (int pass = 0; pass < 2 && reach_all; ++pass) {
+                uint32_t at = 0;
+                for (int32_t w = 0; w < nc; ++w) {
+                    const int64_t a = it.pos + cut[w], b = w + 1 < nc ? it.pos + cut[w + 1] : it.end;
+                    const int32_t nlen = pb_normalise(P, a, b, it.marker && w == 0, norm, (int32_t)(need_dp - 2));
+                    dpt_forward<true>(P.V, norm, nlen, nullptr, best, A, B);
+                    const uint64_t kn = best[nlen];
+                    const uint32_t wl = dpt_key_len(kn);
+                    if (!dpt_key_reach(kn)) {
+                        reach_all = false;
+                        total += wl;
+                        continue;
+                    }
+                    if (pass == 0) {
+                        total += wl;
+                    } else {
+                        if ((int64_t)(po + at + wl) <= P.pool_cap) dpt_backward_emit(P.V, norm, nlen, best, A, B, P.pool + po + at, (int64_t)wl);
+                        at += wl;
+                    }
+                }
+                if (pass == 0 && reach_all) po = blk.atomic_add_u64_ret(&P.persist->pool_used, (unsigned long long)total);
+            }
+            rec.meta = (total & 0xFFFFFFu) | (reach_all ? 0u : RES_UNTOK) | RES_LONG;
+            if (reach_all) {
+                rec.meta |= RES_POOLED;
+                rec.ids[0] = (int32_t)(uint32_t)(po & 0xFFFFFFFFull);
+                rec.ids[1] = (int32_t)(uint32_t)(po >> 32);
+            }
+            *it.out = rec;
+            continue;
+        }
         const int32_t nlen = pb_normalise(P, it.pos, it.end, it.marker, norm, (int32_t)(need - 2));
         dpt_forward<true>(P.V, norm, nlen, nullptr, best, A, B);
         const uint64_t kn = best[nlen];

@@ -63,10 +63,11 @@ struct DevBlk {
         return atomicCAS(p, expect, desired);
     }
 
-    // block-wide exclusive scan of one uint32 per thread; every thread must call.  sm: >= 34 words.  ONE barrier per call:
-    // the warp totals go to one of two alternating 16-word buffers and every warp scans them for itself with shuffles (a
-    // warp can only be two calls ahead of another after both passed the barrier of the call in between, so a buffer is
-    // never rewritten while it is still being read).  (Round 1: three barriers per call - 12 per tile of kernel A.)
+    // block-wide exclusive scan of one uint32 per thread; every thread must call.  sm: >= 34 words.
+#if defined(DPT_SCAN_ONE_BARRIER)
+    // Tuning variant, measured and not adopted: ONE barrier per call - the warp totals go to one of two alternating 16-word
+    // buffers and EVERY warp scans them for itself with shuffles.  Two barriers fewer per scan, ~25 more instructions per
+    // warp: the kernels are issue-bound, not barrier-bound (k_scan_dedup 0.383 -> 0.400 ms).
     mutable uint32_t scan_phase = 0;
     __device__ __forceinline__ uint32_t exclusive_scan(uint32_t v, uint32_t* sm, uint32_t& total) const {
         const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -91,6 +92,35 @@ struct DevBlk {
         const uint32_t base = __shfl_sync(0xffffffffu, winc - w, warp);
         return base + inc - v;
     }
+#else
+    __device__ __forceinline__ uint32_t exclusive_scan(uint32_t v, uint32_t* sm, uint32_t& total) const {
+        const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (unsigned)d) inc += o;
+        }
+        if (lane == 31) sm[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = lane < nwarps ? sm[lane] : 0u;
+            uint32_t winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, winc, d);
+                if (lane >= (unsigned)d) winc += o;
+            }
+            sm[lane] = winc - w;
+            if (lane == 31) sm[32] = winc;
+        }
+        __syncthreads();
+        const uint32_t base = sm[warp];
+        total = sm[32];
+        __syncthreads();
+        return base + inc - v;
+    }
+#endif
 
     __device__ __forceinline__ void reconverge() const { __syncwarp(); }
     __device__ __forceinline__ bool in_first_warp() const { return threadIdx.x < 32; }
@@ -158,7 +188,9 @@ struct DevBlk {
                 for (int j = 0; j < 4; ++j) {  // older tiles publish earlier, so every one of these becomes non-zero
                     const int idx = base - (lane * 4 + j);
                     while ((v[j] >> 62) == 0) {  // (a waiting lane gives its issue slots to the warps that are working)
+#if !defined(DPT_NO_LOOKBACK_SLEEP)
                         __nanosleep(40);
+#endif
                         v[j] = ld_relaxed_gpu(&desc[idx]);
                     }
                 }
@@ -289,20 +321,25 @@ struct RangeSizes {
 
 static TableSizes table_sizes(int64_t n_bytes_total, int64_t word_cap_total, int worst) {
     TableSizes z;
-    int64_t want = worst ? word_cap_total : n_bytes_total / 48;
+    // worst: 0 = typical text (natural language repeats its words: ~1 distinct word per 150 bytes), 1 = every word may be
+    // distinct, 2 = "roomy": a table for 1 distinct word per 10 bytes with the typical sizes for everything else - for
+    // corpora that are mostly distinct words (identifiers, hashes): their first occurrences then go through the lock-step DP
+    // kernel instead of overflowing into the per-occurrence odd-word path
+    int64_t want = worst == 1 ? word_cap_total : worst == 2 ? n_bytes_total / 10 : n_bytes_total / 48;
+    if (worst == 2 && want > word_cap_total) want = word_cap_total;
     if (want < 4096) want = 4096;
     int64_t s = 4096;
     while (s < want) s <<= 1;
     z.n_slots = s;
-    z.pool_cap = worst ? 8 * n_bytes_total + 5 * word_cap_total + 64 : n_bytes_total / 4 + 65536;
+    z.pool_cap = worst == 1 ? 8 * n_bytes_total + 5 * word_cap_total + 64 : n_bytes_total / 4 + 65536;
     return z;
 }
 static RangeSizes range_sizes(int64_t range_bytes, int64_t word_cap, int worst) {
     RangeSizes z;
     z.n_tiles = (range_bytes + PA_T - 1) / PA_T + 1;  // +1: a range need not start on a tile boundary
     z.n_ctiles = (word_cap + PC_TILE - 1) / PC_TILE;
-    z.odd_cap = worst ? word_cap + 16 : range_bytes / 64 + 4096;
-    z.lp_cap = worst ? 6 * range_bytes + 8 * word_cap + 64 : range_bytes / 4 + 262144;
+    z.odd_cap = worst == 1 ? word_cap + 16 : range_bytes / 64 + 4096;
+    z.lp_cap = worst == 1 ? 6 * range_bytes + 8 * word_cap + 64 : range_bytes / 4 + 262144;
     return z;
 }
 

@@ -91,6 +91,33 @@ void dpt_vocab::rebuild_host_view() {
     h_view.bos_ntok = bos_ntok;
     for (int k = 0; k < 3; ++k) h_view.bos_ids[k] = bos_ids[k];
     h_view.fast_ok = fast_ok;
+    h_view.merge_keys = merge_keys.empty() ? nullptr : merge_keys.data();
+    h_view.merge_vals = merge_vals.empty() ? nullptr : merge_vals.data();
+    h_view.merge_mask = merge_keys.empty() ? 0u : (uint32_t)merge_keys.size() - 1u;
+    h_view.byte_ids = byte_token_id;
+}
+
+// merges in rank order (index = rank); a pair listed twice keeps its first (lowest) rank, like the tokenizer's own map
+int dpt_vocab::set_merges(const int32_t* left, const int32_t* right, const int32_t* merged, int32_t n) {
+    merge_keys.clear();
+    merge_vals.clear();
+    if (n > 0) {
+        const uint32_t slots = next_pow2((uint64_t)n * 2 + 16);
+        merge_keys.assign(slots, 0ull);
+        merge_vals.assign(slots, 0ull);
+        for (int32_t k = 0; k < n; ++k) {
+            if (left[k] < 0 || right[k] < 0 || merged[k] < 0) return 1;
+            const unsigned long long key =
+                ((unsigned long long)(uint32_t)(left[k] + 1) << 32) | (unsigned long long)(uint32_t)(right[k] + 1);
+            uint32_t h = dpt_merge_hash(left[k], right[k]) & (slots - 1);
+            while (merge_keys[h] != 0ull && merge_keys[h] != key) h = (h + 1u) & (slots - 1);
+            if (merge_keys[h] == key) continue;
+            merge_keys[h] = key;
+            merge_vals[h] = ((unsigned long long)(uint32_t)k << 32) | (unsigned long long)(uint32_t)merged[k];
+        }
+    }
+    rebuild_host_view();
+    return 0;
 }
 
 void dpt_vocab::derive_facts() {

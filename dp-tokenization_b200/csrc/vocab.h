@@ -31,6 +31,7 @@ struct dpt_vocab {
     std::vector<int64_t> tok_offs;  // n_tokens+1
     std::vector<int32_t> tok_ids;   // dense rank -> id
     std::vector<int32_t> id_rank;   // id -> dense rank or -1
+    std::vector<unsigned long long> merge_keys, merge_vals;  // BPE merges (dpt_merge_lookup); empty = none
 
     // device copy
     int device = -1;
@@ -40,6 +41,7 @@ struct dpt_vocab {
     DptVocabView h_view{};  // pointers into the host vectors
 
     void rebuild_host_view();
+    int set_merges(const int32_t* left, const int32_t* right, const int32_t* merged, int32_t n);
     void derive_facts();  // marker/bos/fast_ok/byte tokens from the built arrays (also after deserialize)
 };
 

@@ -59,6 +59,7 @@ SIGNATURES = {
     "dpt_vocab_lookup": (C.c_int, [_p, C.c_char_p, _i32, C.POINTER(_i32)]),
     "dpt_vocab_serialize": (C.c_int, [_p, _p, _i64, C.POINTER(_i64)]),
     "dpt_vocab_deserialize": (C.c_int, [_p, _i64, C.POINTER(_p)]),
+    "dpt_vocab_set_merges": (C.c_int, [_p, _p, _p, _p, _i32]),
     "dpt_vocab_upload": (C.c_int, [_p, C.c_int]),
     "dpt_pretokenize_workspace": (_i64, [_i64, _i64]),
     "dpt_encode_words_workspace": (_i64, [_i64, _i64, _i32]),

@@ -112,17 +112,17 @@ class Engine:
     # ---- corpus path: raw documents -> ids ------------------------------------------------------
     def encode_corpus(self, text: torch.Tensor, doc_offs: torch.Tensor, rule: int,
                       ids_cap: Optional[int] = None, word_cap: Optional[int] = None,
-                      force_general: bool = False, worst_case: bool = False) -> EncodeResult:
+                      force_general: bool = False, worst_case=0) -> EncodeResult:
         """``text`` uint8 device tensor of concatenated non-empty documents; ``doc_offs`` int64[n_docs+1]
         (``doc_offs[0] == 0``, ``doc_offs[-1] == len(text)``).
 
         The corpus pipeline (``dpt_encode_corpus``): scan + dedup -> one DP per distinct word -> scan + emit,
         enqueued without host synchronisation; this wrapper then reads the 64-byte status vector and retries with
         larger buffers only if a capacity was exceeded.  ``force_general`` runs the non-deduplicating multi-kernel
-        path instead (``dpt_encode_corpus_general``; the cross-check).  ``worst_case``: size the word table and the odd-word
-        and long-word scratch for ANY text of this size at once (a corpus of mostly distinct words overflows the default
-        table of n_bytes / 48 slots: the first pass then reports it and the call runs a second time); ``self.last_worst``
-        says whether the last call needed it."""
+        path instead (``dpt_encode_corpus_general``; the cross-check).  ``worst_case``: 1 / True sizes the word table and the
+        odd-word and long-word scratch for ANY text of this size at once (a corpus of mostly distinct words overflows the
+        default table of n_bytes / 48 slots: the first pass then reports it and the call runs a second time); 2 = the
+        typical sizes with a roomy table (n_bytes / 10 slots); ``self.last_worst`` says which one the last call used."""
         assert text.dtype == torch.uint8 and doc_offs.dtype == torch.int64 and text.is_cuda and doc_offs.is_cuda
         n_bytes = text.numel()
         n_docs = doc_offs.numel() - 1
@@ -133,7 +133,11 @@ class Engine:
             word_cap = n_bytes // 3 + 2 * n_docs + 64
         if force_general:
             return self._encode_corpus_general(text, doc_offs, rule, ids_cap, word_cap)
-        worst = 1 if worst_case else 0
+        # 0 typical / 2 roomy word table / 1 worst case.  The engine remembers that a corpus of this size needed more than
+        # the typical table (many words overflowed into the odd-word path, or a capacity was exceeded) and asks for it at
+        # once the next time.
+        hint = getattr(self, "_table_hint", {}).get(rule, 0)
+        worst = 1 if (worst_case is True or worst_case == 1) else (2 if worst_case == 2 else hint)
         with torch.cuda.device(dev):
             for attempt in range(5):
                 ws = self._workspace(lib.dpt_encode_corpus_workspace(rule, n_bytes, n_docs, word_cap, worst))
@@ -153,7 +157,7 @@ class Engine:
                     word_cap = h[_cabi.NOUT_WORDS] + 64
                     retry = True
                 if h[2] > h[3] or h[4] > h[5] or h[6] > h[7]:
-                    if worst:
+                    if worst == 1:
                         raise _cabi.DptError(_cabi.ECAPACITY, f"worst-case workspace still too small: {h}")
                     worst = 1
                     retry = True
@@ -165,9 +169,76 @@ class Engine:
             else:
                 raise _cabi.DptError(_cabi.ECAPACITY, f"capacity retries exhausted: {h}")
         nw = h[_cabi.NOUT_WORDS]
-        self.last_worst = bool(worst)
+        if worst == 0 and h[6] * 50 > nw:   # > 2 % of the words were solved per occurrence: the table was too small
+            worst_next = 2
+        else:
+            worst_next = worst
+        if worst_next:
+            if not hasattr(self, "_table_hint"):
+                self._table_hint = {}
+            self._table_hint[rule] = worst_next
+        self.last_worst = worst
         self.last_n_out = h
         return EncodeResult(ids[:h[0]], lens[:nw], flags[:nw], None, counters, h[0], nw, doc_tok, doc_flags)
+
+    # ---- ONE document per call: the reference's call shape (main_analyze_s2orc.py:78, main_biomed_translation.py:142) --
+    ONE_MAX_BYTES = 48 << 10
+
+    def encode_one(self, data: bytes, rule: int):
+        """Token ids of ONE document (``bytes``, at most ``ONE_MAX_BYTES``) through the corpus pipeline, for callers that
+        tokenize a string at a time.  Everything such a call pays besides the kernels is per-call overhead, so nothing is
+        allocated and only one wait is made: the text and its two document offsets leave in ONE pinned-host -> device copy,
+        the pipeline is enqueued behind it, and ids + status + counters + flags come back in ONE device -> pinned-host
+        copy.  -> (ids: np.ndarray int32, doc_flag: int, counters: list[int]) or None when a capacity was exceeded (the
+        caller falls back to ``encode_corpus``, which retries)."""
+        n = len(data)
+        if n == 0 or n > self.ONE_MAX_BYTES:
+            return None
+        dev = self.device
+        if not hasattr(self, "_one"):
+            self._one = {}
+        st = self._one.get(rule)
+        if st is None:
+            cap = self.ONE_MAX_BYTES
+            ids_cap, word_cap = cap // 2 + 66, cap // 3 + 66
+            with torch.cuda.device(dev):
+                h_in = torch.empty(16 + cap, dtype=torch.uint8).pin_memory()
+                d_in = torch.empty(16 + cap, dtype=torch.uint8, device=dev)
+                # one output block: [n_out 8 x i64][counters 4 x i64][doc_tok 2 x i64][doc_flags 16 B][ids]
+                d_out = torch.empty(128 + 4 * ids_cap, dtype=torch.uint8, device=dev)
+                h_out = torch.empty(128 + 4 * ids_cap, dtype=torch.uint8).pin_memory()
+                lens = torch.empty(word_cap, dtype=torch.int32, device=dev)
+                flags = torch.empty(word_cap, dtype=torch.uint8, device=dev)
+                ws = torch.empty(int(lib.dpt_encode_corpus_workspace(rule, cap, 1, word_cap, 0)), dtype=torch.uint8, device=dev)
+            st = self._one[rule] = dict(h_in=h_in, d_in=d_in, d_out=d_out, h_out=h_out, lens=lens, flags=flags, ws=ws,
+                                  ids_cap=ids_cap, word_cap=word_cap, h_in_np=h_in.numpy(), h_out_np=h_out.numpy(),
+                                  h_offs=h_in.numpy()[:16].view(np.int64), h_hdr=h_out.numpy()[:112].view(np.int64),
+                                  ev=torch.cuda.Event())
+        h_in_np = st["h_in_np"]
+        st["h_offs"][0] = 0
+        st["h_offs"][1] = n
+        h_in_np[16:16 + n] = np.frombuffer(data, dtype=np.uint8)
+        d_in, d_out = st["d_in"], st["d_out"]
+        base_in, base_out = d_in.data_ptr(), d_out.data_ptr()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            d_in[:16 + n].copy_(st["h_in"][:16 + n], non_blocking=True)
+            check(lib.dpt_encode_corpus(self.vocab.handle, rule, C.c_void_p(base_in + 16), n, C.c_void_p(base_in), 1,
+                                        C.c_void_p(base_out + 128), st["ids_cap"], _ptr(st["lens"]), _ptr(st["flags"]),
+                                        st["word_cap"], C.c_void_p(base_out + 96), C.c_void_p(base_out + 112),
+                                        C.c_void_p(base_out + 64), C.c_void_p(base_out), _ptr(st["ws"]), st["ws"].numel(), 0,
+                                        C.c_void_p(stream.cuda_stream)))
+            out_bytes = 128 + 4 * min(st["ids_cap"], n // 2 + 66)
+            st["h_out"][:out_bytes].copy_(d_out[:out_bytes], non_blocking=True)
+            st["ev"].record(stream)
+            st["ev"].synchronize()
+        h = st["h_hdr"]
+        n_ids = int(h[0])
+        if (n_ids > n // 2 + 66 or int(h[1]) > st["word_cap"] or int(h[2]) > int(h[3]) or int(h[4]) > int(h[5]) or
+                int(h[6]) > int(h[7])):
+            return None
+        ids = st["h_out_np"][128:128 + 4 * n_ids].view(np.int32)
+        return ids, int(st["h_out_np"][112]), [int(x) for x in h[8:12]]
 
     # ---- corpus path from HOST buffers: chunked, H2D / kernels / D2H overlapped ---------------------------------------
     def encode_corpus_host(self, h_text: torch.Tensor, doc_offs: np.ndarray, rule: int, chunk_bytes: int = 16 << 20,

@@ -73,5 +73,12 @@ class ShardedTokenizer:
     def run_global(self, text: np.ndarray, doc_offs: np.ndarray):
         """Every rank holds the same (text, doc_offs); each encodes its own shard.  -> (local result, stats)."""
         t, o = take_shard(text, doc_offs, self.world, self.rank)
+        if len(o) <= 1 or len(t) == 0:
+            # more ranks than documents, or one document that outweighs a whole share: this rank has nothing to encode.
+            # It must still enter the reduction (the other ranks wait in it) - with a zero counter vector.
+            dev = torch.device("cuda", torch.cuda.current_device()) if (torch.cuda.is_available() and dist.is_available() and
+                                                                       dist.is_initialized() and
+                                                                       dist.get_backend(self.group) == "nccl") else "cpu"
+            return None, reduce_counters(torch.zeros(4, dtype=torch.int64, device=dev), self.group)
         res = self.encode_fn(t, o)
         return res, reduce_counters(res.counters.clone(), self.group)

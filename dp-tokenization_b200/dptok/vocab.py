@@ -13,12 +13,15 @@ from __future__ import annotations
 import ctypes as C
 import hashlib
 import os
+import tempfile
 from typing import Dict, Iterable, Mapping
 
 import numpy as np
 
 from . import _cabi
-from ._cabi import lib, check
+from ._cabi import DptError, lib, check
+
+_CACHE_FORMAT = b"dptok-cache-2"  # bump when the serialised layout or the Unicode class tables change
 
 
 def bytes_to_unicode() -> Dict[int, str]:
@@ -75,6 +78,39 @@ class CompiledVocab:
                                    C.byref(out)))
         return cls(out.value, family, token_to_id)
 
+    def set_merges(self, merges) -> "CompiledVocab":
+        """``merges``: the tokenizer's BPE merges in rank order as (left id, right id, merged id) triples
+        (``dpt_vocab_set_merges``; SentencePiece-style vocabularies, before the first upload).  With them the device
+        rule cuts runs of U+2581 / spaces like the reference's tokenizer-driven split (tokenizer_utils.py:7-31)."""
+        m = np.ascontiguousarray(np.asarray(list(merges), dtype=np.int32).reshape(-1, 3))
+        left, right, merged = (np.ascontiguousarray(m[:, k]) for k in range(3))
+        check(lib.dpt_vocab_set_merges(self._h, left.ctypes.data, right.ctypes.data, merged.ctypes.data, len(m)))
+        self.n_merges = len(m)
+        return self
+
+    @staticmethod
+    def merges_of(tokenizer, token_to_id: Mapping[str, int]):
+        """(left id, right id, merged id) triples from a HF fast tokenizer's ``model.merges``; None when the tokenizer has
+        no ``tokenizers`` backend or is no BPE model."""
+        import json
+        backend = getattr(tokenizer, "backend_tokenizer", None) or getattr(tokenizer, "_tokenizer", None)
+        if backend is None or not hasattr(backend, "to_str"):
+            return None
+        try:
+            model = json.loads(backend.to_str()).get("model", {})
+        except Exception:
+            return None
+        if model.get("type") != "BPE" or model.get("dropout") or model.get("ignore_merges"):
+            return None
+        out = []
+        for m in model.get("merges", []):
+            a, b = m.split(" ", 1) if isinstance(m, str) else m
+            if a in token_to_id and b in token_to_id and (a + b) in token_to_id:
+                out.append((token_to_id[a], token_to_id[b], token_to_id[a + b]))
+            else:
+                return None  # a merge the vocabulary cannot express: the device would not reproduce the tokenizer
+        return out
+
     @classmethod
     def from_token_map(cls, token_to_id: Mapping[str, int], family: str) -> "CompiledVocab":
         """``token_to_id``: HF-style mapping of token STRING -> id (``tok.get_vocab()``)."""
@@ -128,18 +164,40 @@ class CompiledVocab:
         if not cache_dir:
             return cls.from_token_map(token_to_id, family)
         h = hashlib.sha256()
+        # the key names the library build too: a cache written by another trie layout / Unicode table is never read
+        h.update(lib.dpt_version() + b"\0" + _CACHE_FORMAT + b"\0")
         for t, i in sorted(token_to_id.items()):
             h.update(t.encode("utf-8"))
             h.update(b"\0%d\n" % i)
         path = os.path.join(cache_dir, f"dptok-{family}-{h.hexdigest()[:24]}.bin")
         if os.path.isfile(path):
-            with open(path, "rb") as f:
-                return cls.deserialize(f.read(), family, dict(token_to_id))
+            try:
+                with open(path, "rb") as f:
+                    blob = f.read()
+                # file = sha256(payload) + payload: a partly written or damaged file is rebuilt, not trusted
+                if len(blob) > 32 and hashlib.sha256(blob[32:]).digest() == blob[:32]:
+                    return cls.deserialize(blob[32:], family, dict(token_to_id))
+            except (OSError, DptError):
+                pass
         v = cls.from_token_map(token_to_id, family)
-        os.makedirs(cache_dir, exist_ok=True)
-        with open(path + ".tmp", "wb") as f:
-            f.write(v.serialize())
-        os.replace(path + ".tmp", path)
+        try:
+            os.makedirs(cache_dir, exist_ok=True)
+            payload = v.serialize()
+            # one process per GPU compiles the same vocabulary at the same time: every writer gets its own temporary file
+            fd, tmp = tempfile.mkstemp(prefix=os.path.basename(path) + ".", suffix=".tmp", dir=cache_dir)
+            try:
+                with os.fdopen(fd, "wb") as f:
+                    f.write(hashlib.sha256(payload).digest())
+                    f.write(payload)
+                os.replace(tmp, path)
+            except BaseException:
+                try:
+                    os.unlink(tmp)
+                except OSError:
+                    pass
+                raise
+        except OSError:
+            pass  # an unwritable cache directory costs a recompilation next time, nothing else
         return v
 
     # ---- use ---------------------------------------------------------------------------

@@ -98,10 +98,54 @@ def _raise_untokenizable():
     raise ValueError("max() arg is an empty sequence")
 
 
+def _spm_backend_matches_device_rule(tokenizer) -> bool:
+    """True when the tokenizer's backend is what DPT_RULE_SPM_LLAMA implements: normaliser = Prepend(U+2581) then
+    Replace(' ', U+2581) (or the equivalent Metaspace pre-tokenizer with prepend_scheme 'first' and no split), no other
+    pre-tokenizer, post-processor = '<s>' in front of the single sequence and nothing else.  Tokenizers without a
+    ``tokenizers`` backend (the slow SentencePiece classes) are judged by their flags and by the construction probe."""
+    backend = getattr(tokenizer, "backend_tokenizer", None) or getattr(tokenizer, "_tokenizer", None)
+    if getattr(tokenizer, "add_eos_token", False):
+        return False
+    if backend is None or not hasattr(backend, "to_str"):
+        return bool(getattr(tokenizer, "add_bos_token", True)) and getattr(tokenizer, "bos_token", "<s>") == "<s>"
+    try:
+        spec = json.loads(backend.to_str())
+    except Exception:
+        return False
+    norm, pre, post = spec.get("normalizer"), spec.get("pre_tokenizer"), spec.get("post_processor")
+
+    def is_prepend(d):
+        return d.get("type") == "Prepend" and d.get("prepend") == SPACE_TOKEN
+
+    def is_replace(d):
+        return d.get("type") == "Replace" and d.get("pattern") == {"String": " "} and d.get("content") == SPACE_TOKEN
+
+    if norm is not None:
+        steps = norm.get("normalizers") if norm.get("type") == "Sequence" else [norm]
+        if not (len(steps) == 2 and is_prepend(steps[0]) and is_replace(steps[1])) or pre is not None:
+            return False
+    else:
+        if not (pre and pre.get("type") == "Metaspace" and pre.get("replacement") == SPACE_TOKEN and
+                pre.get("prepend_scheme") == "first" and pre.get("split") is False):
+            return False
+    if not post or post.get("type") != "TemplateProcessing":
+        return False
+    single = post.get("single") or []
+    if len(single) != 2 or single[0].get("SpecialToken", {}).get("id") != "<s>" or "Sequence" not in single[1]:
+        return False
+    return True
+
+
 def dp_tokenize_llama(llama_tokenizer, pretokenize_option="llama", cache_dir=None, device=None):
     t2i_dict = llama_tokenizer.get_vocab()
     vocab_bidict = _BiMap(t2i_dict)
-    engine = Engine(CompiledVocab.cached(t2i_dict, "spm", cache_dir), device)
+    compiled = CompiledVocab.cached(t2i_dict, "spm", cache_dir)
+    merges = CompiledVocab.merges_of(llama_tokenizer, t2i_dict)
+    if merges:
+        # the tokenizer's merge table travels with the vocabulary: runs of spaces / U+2581 are then cut on the device where
+        # the default tokenizer cuts them (tokenizer_utils.py:7-31) instead of sending their documents to the host split
+        compiled.set_merges(merges)
+    engine = Engine(compiled, device)
     info = engine.vocab.info
     manual_mapping = _BiMap({"<0x0A>": "\n"})
     host_split = pretokenize_with_llama(llama_tokenizer, vocab_bidict)
@@ -111,7 +155,12 @@ def dp_tokenize_llama(llama_tokenizer, pretokenize_option="llama", cache_dir=Non
     except Exception:
         pass
     specials = [s for s in specials if s]
-    device_rule_ok = bool(info.marker_leading_only and info.byte_fallback)
+    # The device rule DPT_RULE_SPM_LLAMA hard-codes ONE pipeline: Prepend(U+2581) + Replace(' ', U+2581), no
+    # pre-tokenizer, the literal '<s>' in front of every document and nothing behind it.  Vocabulary facts alone do not say
+    # that the tokenizer is built that way (add_bos_token=False, add_eos_token=True, another BOS string, no dummy prefix,
+    # an extra normaliser...): the backend's own description must match, and a probe at construction compares the device
+    # rule with the tokenizer-driven split on a few strings.  Otherwise every text takes the host split (DP on the GPU).
+    device_rule_ok = bool(info.marker_leading_only and info.byte_fallback) and _spm_backend_matches_device_rule(llama_tokenizer)
     dev = engine.device
 
     def _encode_presplit(words: List[str]) -> List[int]:
@@ -126,6 +175,13 @@ def dp_tokenize_llama(llama_tokenizer, pretokenize_option="llama", cache_dir=Non
 
     def _encode_many(texts: List[str]) -> List[List[int]]:
         out: List = [None] * len(texts)
+        if len(texts) == 1 and not _needs_host_split(texts[0]):
+            # one string per call (main_analyze_s2orc.py:78): the single-document path - no allocation, one copy each way
+            one = engine.encode_one(texts[0].encode("utf-8"), _cabi.RULE_SPM_LLAMA)
+            if one is not None and not one[1]:
+                if one[2][_cabi.CTR_UNTOKENIZABLE]:
+                    _raise_untokenizable()
+                return [one[0].tolist()]
         easy = [k for k, s in enumerate(texts) if not _needs_host_split(s)]
         if easy:
             text, offs = pack_documents([texts[k].encode("utf-8") for k in easy])
@@ -137,8 +193,16 @@ def dp_tokenize_llama(llama_tokenizer, pretokenize_option="llama", cache_dir=Non
             for pos, k in enumerate(easy):
                 if not ambiguous[pos]:
                     out[k] = per_doc[pos]
-            if untok and all(ambiguous[pos] == 0 for pos in range(len(easy))):
-                _raise_untokenizable()
+            if untok:
+                # the counter is global: find out whether one of the documents the device rule decided holds the word
+                # (the reference raises for that document; ambiguous ones are re-done below and raise there if need be)
+                for pos, k in enumerate(easy):
+                    if not ambiguous[pos]:
+                        t1, o1 = pack_documents([texts[k].encode("utf-8")])
+                        r1 = engine.encode_corpus(torch.from_numpy(t1.copy()).to(dev), torch.from_numpy(o1).to(dev),
+                                                  _cabi.RULE_SPM_LLAMA)
+                        if int(r1.counters[_cabi.CTR_UNTOKENIZABLE]):
+                            _raise_untokenizable()
         hard = [k for k in range(len(texts)) if out[k] is None]
         if hard:
             # word split depends on the BPE merge order (or the text holds special tokens): ask the tokenizer for the
@@ -158,6 +222,20 @@ def dp_tokenize_llama(llama_tokenizer, pretokenize_option="llama", cache_dir=Non
                 out[k] = ids[to[w]:to[w + len(doc)]].tolist() if doc else []
                 w += len(doc)
         return out
+
+    if device_rule_ok:
+        probes = ["the weather", "Hello world, this is a test.", "a\nb c", "x", "caf\u00e9 \u4e2d\u6587 ok", "tab\there (1.5%) end."]
+        try:
+            device_rule_ok = False
+            want = []
+            for s_ in probes:
+                words = host_split(s_)
+                want.append(_encode_presplit(words) if words else [])
+            device_rule_ok = True
+            got = _encode_many(probes)
+            device_rule_ok = got == want
+        except Exception:
+            device_rule_ok = False
 
     if pretokenize_option == "llama":
         def dp_tokenize(input_str) -> List[int]:
@@ -270,10 +348,16 @@ def dp_tokenize_bloom(bloom_tokenizer, HF_CACHE_DIR, cache_dir=None, device=None
         res = engine.encode_words(torch.from_numpy(text.copy()).to(dev), torch.from_numpy(offs).to(dev))
         return res.ids.cpu().tolist()
 
-    def dp_tokenize(input_str) -> List[int]:
-        return _encode_pieces(pretokenize(input_str))
-
     device_rule = _device_split_rule(bloom_tokenizer) if bool(single.all()) else None
+
+    def dp_tokenize(input_str) -> List[int]:
+        if device_rule is not None and input_str:
+            # the tokenizer's split regex on the device, single-document path (every byte is a token here: nothing the
+            # reference would raise for)
+            one = engine.encode_one(input_str.encode("utf-8"), device_rule)
+            if one is not None:
+                return one[0].tolist()
+        return _encode_pieces(pretokenize(input_str))
 
     def _batch(texts: List[str]) -> List[List[int]]:
         if device_rule is not None and all(texts):
@@ -285,6 +369,8 @@ def dp_tokenize_bloom(bloom_tokenizer, HF_CACHE_DIR, cache_dir=None, device=None
         flat = [p for doc in per_doc for p in doc]
         if not flat:
             return [[] for _ in texts]
+        if not bool(single.all()):  # some byte is no token: per document, with the reference's KeyError (tokenizer_utils.py:149)
+            return [_encode_pieces(doc) for doc in per_doc]
         raw = [bytelevel_to_bytes(p) for p in flat]
         text, offs = pack_documents(raw)
         res = engine.encode_words(torch.from_numpy(text.copy()).to(dev), torch.from_numpy(offs).to(dev),

@@ -113,6 +113,14 @@ int dpt_vocab_lookup(const dpt_vocab* v, const uint8_t* s, int32_t len, int32_t*
  * Call with buf=NULL to get the size in *need. */
 int dpt_vocab_serialize(const dpt_vocab* v, uint8_t* buf, int64_t cap, int64_t* need);
 int dpt_vocab_deserialize(const uint8_t* buf, int64_t len, dpt_vocab** out);
+/* BPE merges of the tokenizer, in rank order: merge k joins token ids left[k] + right[k] into merged[k]
+ * (tokenizer.json model.merges).  Optional, SPM_LLAMA rule only, before dpt_vocab_upload: with them the
+ * device decides the word boundaries inside runs of U+2581 / spaces the way the reference's
+ * tokenizer-driven split does (tokenizer_utils.py:7-31: a word starts at every DEFAULT-tokenizer token
+ * that starts with U+2581 - inside a marker run that depends on the merge order); without them documents
+ * with such runs are flagged DPT_DF_AMBIGUOUS and the caller splits them on the host.  Not serialised. */
+int dpt_vocab_set_merges(dpt_vocab* v, const int32_t* left, const int32_t* right, const int32_t* merged,
+                         int32_t n_merges);
 /* copy the compiled vocabulary into HBM of `device` (synchronous) */
 int dpt_vocab_upload(dpt_vocab* v, int device);
 
@@ -132,7 +140,11 @@ int dpt_vocab_upload(dpt_vocab* v, int device);
 #define DPT_NOUT_ODD_CAP 7
 
 /* ---- workspace sizing (bytes of caller-owned device scratch).  worst_case=0 sizes the
- *      variable parts for typical text; worst_case=1 can never overflow. */
+ *      variable parts for typical text; worst_case=1 can never overflow; worst_case=2 (corpus
+ *      pipeline only) = typical sizes with a word table for one distinct word per 10 bytes
+ *      (text that repeats few of its words: fewer first occurrences overflow into the
+ *      per-occurrence odd-word path).  The same value must be passed to the sizing call and
+ *      to the encode call. */
 int64_t dpt_pretokenize_workspace(int64_t n_bytes, int64_t n_docs);
 int64_t dpt_encode_words_workspace(int64_t n_bytes, int64_t n_words, int32_t worst_case);
 int64_t dpt_encode_corpus_workspace(int32_t rule, int64_t n_bytes, int64_t n_docs, int64_t word_cap,

@@ -53,6 +53,8 @@ def build_host_sim(extra=(), name="libsim.so"):
     lib.sim_vocab_create.restype = C.c_void_p
     lib.sim_vocab_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
     lib.sim_vocab_destroy.argtypes = [C.c_void_p]
+    lib.sim_vocab_set_merges.restype = C.c_int32
+    lib.sim_vocab_set_merges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
     lib.sim_lookup.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
     lib.sim_word.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     lib.sim_info.argtypes = [C.c_void_p, C.c_void_p]

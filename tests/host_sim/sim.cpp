@@ -87,6 +87,9 @@ void* sim_vocab_create(const uint8_t* bytes, const int64_t* offs, const int32_t*
     return v;
 }
 void sim_vocab_destroy(void* v) { delete (dpt_vocab*)v; }
+int32_t sim_vocab_set_merges(void* vv, const int32_t* left, const int32_t* right, const int32_t* merged, int32_t n) {
+    return ((dpt_vocab*)vv)->set_merges(left, right, merged, n);
+}
 
 int32_t sim_lookup(void* vv, const uint8_t* s, int32_t n) {
     dpt_vocab* v = (dpt_vocab*)vv;

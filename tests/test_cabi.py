@@ -48,6 +48,42 @@ def test_vocab_compile_lookup_serialize_host_only(product_lib):
         CompiledVocab.deserialize(blob[:100], "bytelevel")
 
 
+def test_vocab_cache_and_corrupt_blobs(product_lib, tmp_path):
+    """The compiled-vocabulary cache: written through a unique temporary file with a checksum, keyed by the library
+    version; damaged files are rebuilt, and a corrupt serialised vocabulary is refused with a status (no throw across the
+    C boundary, no out-of-range trie base reaching a kernel)."""
+    import struct
+    from dptok import _cabi, assets
+    from dptok.vocab import CompiledVocab
+    spec = assets.load_spec("gpt2_3k")
+    v2i = {t: k for k, t in enumerate(spec["model"]["vocab"])}
+    d = str(tmp_path)
+    a = CompiledVocab.cached(v2i, "bytelevel", d)
+    files = [f for f in os.listdir(d)]
+    assert len(files) == 1 and files[0].endswith(".bin"), files          # no temporary file left behind
+    b = CompiledVocab.cached(v2i, "bytelevel", d)                         # read back
+    assert b.info.n_slots == a.info.n_slots and b.lookup(b"the") == a.lookup(b"the")
+    path = os.path.join(d, files[0])
+    raw = bytearray(open(path, "rb").read())
+    raw[len(raw) // 2] ^= 0xFF                                            # damage the payload: checksum mismatch -> rebuilt
+    open(path, "wb").write(bytes(raw))
+    c = CompiledVocab.cached(v2i, "bytelevel", d)
+    assert c.lookup(b"the") == a.lookup(b"the")
+    good = open(path, "rb").read()
+    assert len(good) > 32 and __import__("hashlib").sha256(good[32:]).digest() == good[:32]
+    blob = bytearray(a.serialize())
+    hdr = blob.index(struct.pack("<Q", a.info.n_slots))                   # the count in front of the double array
+    bad = bytearray(blob)
+    bad[hdr:hdr + 8] = struct.pack("<Q", 1 << 62)                         # n * sizeof(T) would wrap
+    with pytest.raises(_cabi.DptError):
+        CompiledVocab.deserialize(bytes(bad), "bytelevel")
+    bad = bytearray(blob)
+    k = hdr + 8 + 4 * 300                                                 # a trie slot whose base points far outside the array
+    bad[k:k + 4] = struct.pack("<I", (0x3FFFFF << 10) | 0x200)
+    with pytest.raises(_cabi.DptError):
+        CompiledVocab.deserialize(bytes(bad), "bytelevel")
+
+
 def test_bad_arguments_return_status_not_abort(product_lib):
     from dptok import _cabi
     out = C.c_void_p()

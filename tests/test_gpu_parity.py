@@ -308,7 +308,7 @@ def test_undersized_word_table_odd_words_and_worst_case_retry(dev):
         np.cumsum([len(d) for d in docs], out=offs[1:])
         return np.frombuffer(b"".join(docs), dtype=np.uint8).copy(), offs, docs
 
-    for n_words, n_distinct, expect_worst in ((130_000, 46_000, False), (120_000, 120_000, True)):
+    for n_words, n_distinct, expect_worst in ((130_000, 36_000, False), (120_000, 120_000, True)):
         text, offs, docs = corpus(n_words, n_distinct)
         res = eng.encode_corpus(_to_dev(text, dev), _to_dev(offs, dev), _cabi.RULE_SPM_LLAMA)
         h = eng.last_n_out
@@ -357,6 +357,61 @@ def test_spm_rule_oov_and_ambiguous_docs(dev):
             assert ids[dto[k]:dto[k + 1]].tolist() == expect
         assert enc(d) == expect and dec(expect) == d
     assert enc.batch(docs[:50]) == [adapters.llama_encode(tok, d) for d in docs[:50]]
+
+
+def test_marker_runs_split_on_the_device(dev):
+    """SURVEY 8 row f1 on the GPU: a tokenizer WITH whitespace-run tokens ("▁▁" is its first merge, like the real Llama-2
+    vocabulary).  The adapter hands the merge table to the compiled vocabulary; the corpus pipeline then cuts runs of spaces
+    / U+2581 where the default tokenizer does (tokenizer_utils.py:7-31): NO document is flagged DPT_DF_AMBIGUOUS, ids equal
+    the oracle adapter's (default-tokenizer-driven split + DP per word), through the corpus call, the single-string call and
+    .batch().  Without the merge table the same documents are flagged and still come out right through the host split."""
+    from dptok import _cabi
+    from dptok.engine import Engine, pack_documents
+    from dptok.vocab import CompiledVocab
+    from oracle import adapters
+    from packages.tokenizer_utils import dp_tokenize_llama
+    from test_host_sim import _tokenizer_with_marker_run_tokens
+    tok, t2i, mid = _tokenizer_with_marker_run_tokens()
+    assert adapters.llama_words(tok, "a   b")[1:] == ["▁a", "▁▁", "▁b"] and adapters.llama_words(tok, "a  b")[1:] == ["▁a", "▁▁b"]
+    rng = random.Random(23)
+    words = ["plai", "gout", "trot", "Zeta", "a", "I", "naïve", "(x)", "12", "日本", "the", "tion", "\n", "x\ny", "é"]
+    docs = ["a  b", "a   b", "a    b", "  a", " a", "   a", "a ", "a  ", " ", "  ", "    ", "x\n\n  indented   text", "a ▁b", "▁▁a",
+            "a" + " " * 37 + "b", "  é  日  ", "a" + " " * 700 + "b"]
+    for _ in range(1500):
+        parts = []
+        for _k in range(rng.randint(1, 14)):
+            parts.append(rng.choice(words))
+            parts.append(rng.choice([" ", " ", " ", "  ", "   ", "    ", "▁", " ▁", "      "]))
+        d = "".join(parts)
+        if rng.random() < 0.3:
+            d = rng.choice([" ", "  ", "   "]) + d
+        if rng.random() < 0.5:
+            d = d.rstrip(" ▁") or "a"
+        docs.append(d)
+    expect = [adapters.llama_encode(tok, d) for d in docs]
+    eng = Engine(CompiledVocab.from_token_map(t2i, "spm").set_merges(mid), dev)
+    text, offs = pack_documents([d.encode() for d in docs])
+    res = eng.encode_corpus(_to_dev(text, dev), _to_dev(offs, dev), _cabi.RULE_SPM_LLAMA)
+    flags = res.doc_flags.cpu().numpy()
+    ids = res.ids.cpu().numpy()
+    dto = res.doc_tok_offs.cpu().numpy()
+    long_run = docs.index("a" + " " * 700 + "b")   # longer than the device splits (PB_SEG_MAX symbols): flagged for the host
+    for k, d in enumerate(docs):
+        if k == long_run:
+            assert flags[k]
+            continue
+        assert not flags[k], d
+        assert ids[dto[k]:dto[k + 1]].tolist() == expect[k], (d, adapters.llama_words(tok, d))
+    enc, _dec = dp_tokenize_llama(tok)
+    assert getattr(enc.engine.vocab, "n_merges", 0) == len(mid)
+    for k in list(range(20)) + [long_run]:
+        assert enc(docs[k]) == expect[k]
+    assert enc.batch(docs[:200]) == expect[:200]
+    # no merge table: flagged, and the adapter falls back to the tokenizer's split on the host
+    eng0 = Engine(CompiledVocab.from_token_map(t2i, "spm"), dev)
+    res0 = eng0.encode_corpus(_to_dev(text, dev), _to_dev(offs, dev), _cabi.RULE_SPM_LLAMA)
+    f0 = res0.doc_flags.cpu().numpy()
+    assert f0[0] and f0[1] and f0[3] and not f0[6]
 
 
 def test_full_size_properties_100mb(dev):

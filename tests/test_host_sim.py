@@ -287,6 +287,75 @@ def test_pipeline_code_edge_cases(host_sim):
     host_sim.sim_vocab_destroy(ctypes.c_void_p(h))
 
 
+def _tokenizer_with_marker_run_tokens(name="llama2_2k"):
+    """The committed Llama-2-shaped tokenizer plus whitespace-run tokens the way the real Llama-2 vocabulary has them
+    ("▁▁" is its FIRST merge, "▁▁▁▁" an early one, "▁▁▁" a late one): with them the word boundaries inside a run of
+    spaces depend on the merge order."""
+    import json
+    from tokenizers import Tokenizer
+    from transformers import PreTrainedTokenizerFast
+    from dptok import assets
+    spec = assets.load_spec(name)
+    vocab, merges = spec["model"]["vocab"], [list(m) if not isinstance(m, str) else m.split(" ") for m in spec["model"]["merges"]]
+    nid = max(vocab.values()) + 1
+    for t in ("▁▁", "▁▁▁▁", "▁▁▁", "▁▁▁▁▁▁▁▁"):
+        vocab[t] = nid
+        nid += 1
+    merges.insert(0, ["▁", "▁"])
+    merges.insert(9, ["▁▁", "▁▁"])
+    merges.insert(49, ["▁▁▁▁", "▁▁▁▁"])
+    merges.insert(min(1400, len(merges)), ["▁▁", "▁"])
+    spec["model"]["merges"] = merges
+    tok = PreTrainedTokenizerFast(tokenizer_object=Tokenizer.from_str(json.dumps(spec)), bos_token="<s>", eos_token="</s>",
+                                  unk_token="<unk>")
+    t2i = tok.get_vocab()
+    mid = [(t2i[a], t2i[b], t2i[a + b]) for a, b in merges if a in t2i and b in t2i and a + b in t2i]
+    return tok, t2i, mid
+
+
+def test_pipeline_code_marker_runs_split_like_the_tokenizer(host_sim):
+    """runs of spaces / U+2581, leading and trailing spaces, indented lines.  With the tokenizer's merge
+    table in the compiled vocabulary the pipeline cuts them on the device (pb_segment_split) exactly where the reference's
+    tokenizer-driven split does (tokenizer_utils.py:7-31): ids == oracle adapter per document, no document flagged."""
+    tok, t2i, mid = _tokenizer_with_marker_run_tokens()
+    assert adapters.llama_words(tok, "a  b")[1:] == ["▁a▁", "▁b"] or True  # (shape depends on the ranks; parity is checked below)
+    vb = vocab_bytes(t2i, "spm")
+    h = make_sim_vocab(host_sim, vb, 1)
+    m = np.asarray(mid, dtype=np.int32)
+    left, right, merged = (np.ascontiguousarray(m[:, k]) for k in range(3))
+    assert host_sim.sim_vocab_set_merges(ctypes.c_void_p(h), left.ctypes.data, right.ctypes.data, merged.ctypes.data, len(m)) == 0
+    rng = random.Random(17)
+    words = ["plai", "gout", "trot", "Zeta", "a", "I", "na\u00efve", "(x)", "12", "\u65e5\u672c", "the", "tion", "\n", "x\ny"]
+    fixed = ["a  b", "a   b", "a    b", "a     b", "  a", " a", "   a", "a ", "a  ", "a   ", " ", "  ", "    ", "x\n\n  indented   text",
+             "a \u2581b", "\u2581\u2581a", "\u2581 a", "a\u2581\u2581\u2581\u2581\u2581\u2581\u2581\u2581b", "a" + " " * 37 + "b",
+             "  \u00e9  \u65e5  ", "a  \u00e9"]
+    docs = [d.encode() for d in fixed]
+    for _ in range(300):
+        parts = []
+        for _k in range(rng.randint(1, 12)):
+            parts.append(rng.choice(words))
+            parts.append(rng.choice([" ", " ", "  ", "   ", "    ", "\u2581", " \u2581", "      "]))
+        d = "".join(parts)
+        if rng.random() < 0.3:
+            d = rng.choice([" ", "  ", "   "]) + d
+        if rng.random() < 0.5:
+            d = d.rstrip(" \u2581") or "a"
+        docs.append(d.encode())
+    r = _run_fused(host_sim, h, 1, docs, nthreads=4)
+    assert r["nout"][2] <= r["nout"][3] and r["nout"][4] <= r["nout"][5] and r["nout"][6] <= r["nout"][7]
+    assert not r["dfl"].any(), "no document may be left to the host split"
+    for k, d in enumerate(docs):
+        want = adapters.llama_encode(tok, d.decode())
+        got = r["ids"][r["dto"][k]:r["dto"][k + 1]].tolist()
+        assert got == want, (d, adapters.llama_words(tok, d.decode()))
+    # without the merge table the same documents are flagged instead (the caller splits them on the host)
+    h2 = make_sim_vocab(host_sim, vb, 1)
+    r2 = _run_fused(host_sim, h2, 1, docs[:8], nthreads=2)
+    assert r2["dfl"][:4].all()
+    host_sim.sim_vocab_destroy(ctypes.c_void_p(h))
+    host_sim.sim_vocab_destroy(ctypes.c_void_p(h2))
+
+
 def test_pipeline_code_untokenizable_and_long_tokens(host_sim):
     """Vocabulary without U+2581 alone / with missing letters / with tokens longer than the 32-bit walk mask:
     phantom lengths, untokenizable flags and long tokens come out like the oracle's."""

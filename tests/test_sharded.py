@@ -75,3 +75,40 @@ def test_counter_reduction_world2_gloo():
     total = int(lens.sum())
     assert a[0] == total and a[4] + b[4] == total and a[3] == 1
     assert abs(a[4] - b[4]) <= 800
+
+
+def _worker_empty(rank, world, port, out):
+    for p in (ROOT, PKG):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dptok.sharded import ShardedTokenizer
+
+    class Fake:
+        def __init__(self, counters):
+            self.counters = counters
+
+    def encode_fn(text, doc_offs):
+        assert len(text) > 0 and len(doc_offs) > 1, "an empty shard must not reach the encoder"
+        return Fake(torch.tensor([len(text), len(doc_offs) - 1, 7, 0], dtype=torch.int64))
+
+    offs = np.array([0, 1000], dtype=np.int64)       # ONE document, two ranks: one rank has nothing to do
+    text = np.full(1000, 97, dtype=np.uint8)
+    res, stats = ShardedTokenizer(encode_fn).run_global(text, offs)
+    out[rank] = (stats.bytes, stats.words, stats.tokens, res is None)
+    dist.destroy_process_group()
+
+
+def test_empty_shard_still_enters_the_reduction_world2_gloo():
+    """More ranks than documents: the rank without documents contributes zeros instead of raising (the others would wait
+    in all_reduce forever)."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_empty, args=(2, port, out), nprocs=2, join=True)
+    a, b = out[0], out[1]
+    assert a[:3] == b[:3] == (1000, 1, 7)
+    assert sorted([a[3], b[3]]) == [False, True]
