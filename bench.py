@@ -227,7 +227,10 @@ class Ctx:
             saved = os.dup(1)
             os.dup2(2, 1)
             try:
-                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+                import datetime
+                # (a rank that fails must cost the others minutes, not the default ten per collective)
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank),
+                                        timeout=datetime.timedelta(seconds=240))
                 dist.all_reduce(torch.zeros(1, device=self.dev))
                 torch.cuda.synchronize()
             finally:
@@ -239,8 +242,10 @@ class Ctx:
         self.lex = {}
         self.peak, self.peak_src = measured_peaks()
 
-    def barrier(self):
-        if self.world > 1:
+    def barrier(self, collective=True):
+        # collective=False: a measurement only THIS rank makes (rank 0's single-GPU pass at N > 1) must not enter a
+        # collective the other ranks never call
+        if self.world > 1 and collective:
             self.dist.barrier()
         self.torch.cuda.synchronize()
 
@@ -311,7 +316,7 @@ def build_workload(cx: Ctx, name: str, size_mb: float, seed_rank: int = 0, suffi
     return wl
 
 
-def measure_resident(cx: Ctx, engine, d_text, d_offs, rule, steps, warmup, with_profile=True, sampler=None):
+def measure_resident(cx: Ctx, engine, d_text, d_offs, rule, steps, warmup, with_profile=True, sampler=None, collective=True):
     """K timed steps with the text resident in HBM: CUDA events per step, L2 flushed between steps.  Then (optionally) the
     same K steps once more with a CUDA event pair around every kernel launch (per-kernel times for the roofline)."""
     from dptok import engine as eng_mod
@@ -325,7 +330,7 @@ def measure_resident(cx: Ctx, engine, d_text, d_offs, rule, steps, warmup, with_
     engine.encode_corpus(d_text, d_offs, rule, ids_cap=ids_cap, word_cap=word_cap)
     worst = int(engine.last_worst)  # 0 typical, 2 roomy word table, 1 worst-case sizes (chosen by the engine during the warm-up)
     launches0 = eng_mod.launch_count()
-    cx.barrier()
+    cx.barrier(collective)
     if sampler:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -335,7 +340,7 @@ def measure_resident(cx: Ctx, engine, d_text, d_offs, rule, steps, warmup, with_
         ev[k][0].record()
         res = engine.encode_corpus(d_text, d_offs, rule, ids_cap=ids_cap, word_cap=word_cap, worst_case=worst)
         ev[k][1].record()
-    cx.barrier()
+    cx.barrier(collective)
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if sampler else None
     launches = eng_mod.launch_count() - launches0
@@ -653,7 +658,8 @@ def main_multi(cx: Ctx, args):
     # rank 0 alone: the whole corpus on one GPU - the reference point of the strong scaling and of the counters
     strong = None
     if rank == 0:
-        m1 = measure_resident(cx, engine, wl["d_text"], wl["d_offs"], wl["rule"], max(3, min(steps, 5)), 3, with_profile=False)
+        m1 = measure_resident(cx, engine, wl["d_text"], wl["d_offs"], wl["rule"], max(3, min(steps, 5)), 3, with_profile=False,
+                              collective=False)
         n1_ms = m1["total_ms"] / len(m1["step_ms"])
         strong = {"n1_ms_per_step": n1_ms, "nN_ms_per_step": total_ms / steps, "speedup": n1_ms / (total_ms / steps),
                   "counters_single_gpu": m1["counters"], "counters_reduced": g, "counters_match": m1["counters"] == g,

@@ -285,8 +285,8 @@ static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * 
 // One side stream + fork/join events per host thread and device (created on first use, kept for the life of the thread).
 struct SideStream {
     int device = -1;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr;
     bool ok() const { return stream != nullptr; }
 };
 static SideStream& side_stream() {
@@ -300,9 +300,15 @@ static SideStream& side_stream() {
         s.device = dev;
         if (!(off && off[0] == '1')) {
             if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) s.stream = nullptr;
-            if (s.stream && (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
-                             cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess)) {
+            if (s.stream && cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking) != cudaSuccess) {
                 cudaStreamDestroy(s.stream);
+                s.stream = nullptr;
+            }
+            if (s.stream && (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+                             cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess ||
+                             cudaEventCreateWithFlags(&s.join2, cudaEventDisableTiming) != cudaSuccess)) {
+                cudaStreamDestroy(s.stream);
+                cudaStreamDestroy(s.stream2);
                 s.stream = nullptr;
             }
         }
@@ -527,12 +533,16 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
         // The few long words (32..63 units: one warp per word; odd words and words of more than 63 units: the
         // thread-per-word kernel, a serial chain per word) run BESIDE the lock-step kernel on a side stream of the library
         // (fork / join with events: from the caller's point of view everything is ordered on `st`).
+        // (TWO side streams: on one, the thread-per-word kernel waited behind the warp kernel - each stretched to ~0.2 ms by
+        // sharing the SMs with the lock-step kernel - and their sum, not the lock-step kernel, was the critical path.)
         SideStream& side = side_stream();
         const bool forked = side.ok();
         cudaStream_t s1 = forked ? side.stream : st;
+        cudaStream_t s2 = forked ? side.stream2 : st;
         if (forked) {
             cudaEventRecord(side.fork, st);
             cudaStreamWaitEvent(s1, side.fork, 0);
+            cudaStreamWaitEvent(s2, side.fork, 0);
         }
         {
             ProfScope prof(P.spm ? "k_dp_warp_spm" : "k_dp_warp_bl", s1);
@@ -542,14 +552,15 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
                 k_dp_warp_bl<<<(unsigned)(sm_count * 4), PBW_THREADS, 0, s1>>>(P);
             ++g_launches;
         }
+        if (forked) cudaEventRecord(side.join, s1);
         {
-            ProfScope prof("k_dp_distinct", s1);
+            ProfScope prof("k_dp_distinct", s2);
             PipeParams P1 = P;
             P1.coop = 1;
-            k_dp_distinct<<<(unsigned)(sm_count * 2), PB_THREADS, 0, s1>>>(P1);
+            k_dp_distinct<<<(unsigned)(sm_count * 2), PB_THREADS, 0, s2>>>(P1);
             ++g_launches;
         }
-        if (forked) cudaEventRecord(side.join, s1);
+        if (forked) cudaEventRecord(side.join2, s2);
         {
             ProfScope prof(P.spm ? "k_dp_lock_spm" : "k_dp_lock_bl", st);
             static int bl_ctas = 0;  // CTAs per SM of the lock-step kernel's grid (development knob: DPT_BL_GRID)
@@ -563,7 +574,10 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
                 k_dp_lock_bl<<<(unsigned)(sm_count * bl_ctas), PBL_THREADS, 0, st>>>(P);
             ++g_launches;
         }
-        if (forked) cudaStreamWaitEvent(st, side.join, 0);  // (the side stream's kernels defer words too)
+        if (forked) {  // (the side streams' kernels defer words too)
+            cudaStreamWaitEvent(st, side.join, 0);
+            cudaStreamWaitEvent(st, side.join2, 0);
+        }
         if (P.spm) {  // the words the lock-step kernels deferred (byte-level rules never defer)
             ProfScope prof("k_dp_distinct_deferred", st);
             PipeParams P2 = P;

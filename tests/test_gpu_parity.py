@@ -414,6 +414,29 @@ def test_marker_runs_split_on_the_device(dev):
     assert f0[0] and f0[1] and f0[3] and not f0[6]
 
 
+def test_unaligned_corpus_buffer(dev):
+    """A corpus that does not start on a 16-byte boundary (a shard cut out of a larger device buffer, as the multi-GPU
+    driver does): same result as the aligned copy, for the SentencePiece and a byte-level rule."""
+    from dptok import _cabi, assets, synth
+    from dptok.engine import Engine
+    from dptok.vocab import CompiledVocab
+    tok, t2i, eng = _llama_engine("llama2_32k", dev)
+    text, doc_offs = synth.gen_documents(1_500_000, seed=5, newline_headers=True)
+    spec = assets.load_spec("gpt2_3k")
+    beng = Engine(CompiledVocab.from_token_map({t: k for k, t in enumerate(spec["model"]["vocab"])}, "bytelevel"), dev)
+    for engine, rule in ((eng, _cabi.RULE_SPM_LLAMA), (beng, _cabi.RULE_GPT2)):
+        ref = engine.encode_corpus(_to_dev(text, dev), _to_dev(doc_offs, dev), rule)
+        for mis in (1, 3, 4, 9):
+            buf = torch.zeros(len(text) + 64, dtype=torch.uint8, device=dev)
+            buf[mis:mis + len(text)] = _to_dev(text, dev)
+            view = buf[mis:mis + len(text)]
+            assert view.data_ptr() % 16 == mis
+            got = engine.encode_corpus(view, _to_dev(doc_offs, dev), rule)
+            assert got.n_ids == ref.n_ids and got.n_words == ref.n_words
+            assert torch.equal(got.ids, ref.ids) and torch.equal(got.word_lens, ref.word_lens)
+            assert torch.equal(got.doc_tok_offs, ref.doc_tok_offs)
+
+
 def test_full_size_properties_100mb(dev):
     """BASELINE.json configs[1] at full size (100 MB, Llama-2-shaped 32k vocab): size-independent properties -
     device decode round-trips every document, counters are consistent, the DP never uses more tokens than the
