@@ -18,7 +18,7 @@ int fail(int code, const std::string& msg) {
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct BlobLayout {
-    int64_t da, slot_id, ph_seed, ph_id, tok_bytes, tok_offs, id_rank, uni1, uni2, merge_keys, merge_vals, byte_ids, total;
+    int64_t da, slot_id, ph_seed, ph_id, tok_bytes, tok_offs, id_rank, uni1, uni2, merge_keys, merge_vals, byte_ids, code2, total;
 };
 BlobLayout layout_of(const dpt_vocab* v) {
     BlobLayout L{};
@@ -47,6 +47,8 @@ BlobLayout layout_of(const dpt_vocab* v) {
     o = align_up(o + (int64_t)v->merge_vals.size() * 8, 256);
     L.byte_ids = o;
     o = align_up(o + 256 * 4, 256);
+    L.code2 = o;
+    o = align_up(o + 2048, 256);
     L.total = o;
     return L;
 }
@@ -265,6 +267,7 @@ int dpt_vocab_upload(dpt_vocab* v, int device) {
     cudaMemcpy(d + L.uni1, DPT_UNI_STAGE1, DPT_UNI_STAGE1_LEN, cudaMemcpyHostToDevice);
     cudaMemcpy(d + L.uni2, DPT_UNI_STAGE2, DPT_UNI_STAGE2_LEN, cudaMemcpyHostToDevice);
     cudaMemcpy(d + L.byte_ids, v->byte_token_id, 256 * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(d + L.code2, v->code2, 2048, cudaMemcpyHostToDevice);
     if (!v->merge_keys.empty()) {
         cudaMemcpy(d + L.merge_keys, v->merge_keys.data(), v->merge_keys.size() * 8, cudaMemcpyHostToDevice);
         cudaMemcpy(d + L.merge_vals, v->merge_vals.data(), v->merge_vals.size() * 8, cudaMemcpyHostToDevice);
@@ -292,6 +295,7 @@ int dpt_vocab_upload(dpt_vocab* v, int device) {
     v->d_view.merge_keys = v->merge_keys.empty() ? nullptr : (const unsigned long long*)(d + L.merge_keys);
     v->d_view.merge_vals = v->merge_vals.empty() ? nullptr : (const unsigned long long*)(d + L.merge_vals);
     v->d_view.byte_ids = (const int32_t*)(d + L.byte_ids);
+    v->d_view.code2 = (const uint8_t*)(d + L.code2);
     return DPT_OK;
 }
 

@@ -64,6 +64,8 @@ struct DptVocabView {
     uint32_t merge_mask;
     const int32_t* byte_ids;   // id of the token "<0xHH>" per byte value (-1 if absent): the default tokenizer's symbol for
                                // a character that is no vocabulary entry (byte_fallback)
+    const uint8_t* code2;      // dpt_char_code of every 2-byte UTF-8 character, indexed by its 11-bit code point (2048 B):
+                               // Latin-1 .. Arabic in ONE look-up in kernel A's code pass (dpt_split_rules.h)
 };
 
 // One trie step.  `entry` is the slot VALUE of the current node (it carries the base), not its

@@ -51,8 +51,28 @@ constexpr int PA_HALO = 32;                   // look-behind (multiple of 32 kee
 constexpr int PA_LA = 96;                     // look-ahead: a word that ends within it is handled in-tile
 constexpr int PA_R = PA_HALO + PA_T + PA_LA;  // region bytes = 4096 = 256 x 16: one 16-byte load and one 16-bit mask
                                               // slice per thread (4096-byte tiles made 8 threads go round twice: 0.390 -> 0.380 ms)
+static_assert(PA_HALO == 32 && PA_LA == 96, "PaGeom spells the halo and the look-ahead out");
 constexpr int PA_NW = PA_R / 32;
 constexpr int PA_THREADS = DPT_PA_THREADS;
+// Tile geometry per boundary rule.  The byte-level kernels keep the 3968-byte tile (their shared memory - code array,
+// sync-point and document lists - grows with the region: 37 KB at 4 KB).  The SentencePiece kernel takes 8064-byte tiles
+// (8192-byte region) with windows of 1152 words at 5 CTAs/SM and 48 registers: the per-tile work (document search,
+// look-back, scans, barriers) is amortised over twice the bytes and nothing spills - 0.378 -> 0.352 ms on the B200; 6016
+// and 11136-byte tiles, 4 or 6 CTAs/SM and 512 threads were all slower (profiles/r2_variants_tile_size.txt).  PA_T / PA_R /
+// PA_NW / PA_WIN below are the byte-level geometry and, for the host's sizing, the upper bound of the tile count.
+#ifndef DPT_PA_T_SPM
+#define DPT_PA_T_SPM 8064
+#endif
+#ifndef DPT_PA_WIN_SPM
+#define DPT_PA_WIN_SPM 1152
+#endif
+template <bool kSpm>
+struct PaGeom {
+    static constexpr int T = kSpm ? DPT_PA_T_SPM : DPT_PA_T;
+    static constexpr int R = 32 + T + 96;  // PA_HALO + T + PA_LA
+    static constexpr int NW = R / 32;
+    static constexpr int WIN = kSpm ? DPT_PA_WIN_SPM : DPT_PA_WIN;
+};
 constexpr int PA_MAXLEN = 63;                 // longest word body (bytes) that goes through the dedup table
 constexpr int PA_PROBES = 16;                // (8: ~5e-4 of the distinct words found their neighbourhood full and became odd words)
 constexpr int PB_THREADS = 128;
@@ -175,6 +195,7 @@ struct PipeParams {
 
 template <bool kSpm>
 struct ASmemT {
+    static constexpr int PA_R = PaGeom<kSpm>::R, PA_NW = PaGeom<kSpm>::NW, PA_WIN = PaGeom<kSpm>::WIN;  // (this rule's geometry)
     // list capacity: SPM needs one window of entries; byte-level rules also list their synchronisation points
     // (up to one per byte of the region)
     static constexpr int WL_CAP = kSpm ? PA_WIN : PA_R + 32;
@@ -438,6 +459,9 @@ DPT_PIPE_FN int64_t pp_spm_word_end_global(const PipeParams& P, int64_t g_ws, in
 // =========================================================================================================
 template <class Blk, bool kSpm>
 DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, const int tile) {
+    // this rule's tile geometry (the names shadow the namespace-level byte-level constants on purpose)
+    constexpr int PA_T = PaGeom<kSpm>::T, PA_R = PaGeom<kSpm>::R, PA_NW = PaGeom<kSpm>::NW, PA_WIN = PaGeom<kSpm>::WIN;
+    static_assert(PA_R % 32 == 0 && PA_R < 32768 && PA_WIN <= 65535, "region indices are 15 bits, counts 16");
     const int tid = blk.tid(), nt = blk.nthreads();
     const int64_t t0 = ((int64_t)P.tile_first + tile) * PA_T;
     const int64_t g0 = t0 - PA_HALO;  // global offset of region index 0
@@ -587,8 +611,20 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                     const int k = pp_ctz(hi);
                     const uint32_t near = (uint32_t)(dsw >> k) & 7u;  // document starts at r + 1, r + 2, r + 3
                     const int lim = near ? pp_ctz(near) + 1 : 4;
-                    const DptChar ch = dpt_char_at(U, t, k, k + lim);
-                    const uint32_t c = dpt_char_code(ch);
+                    DptChar ch;
+                    uint32_t c;
+                    const uint32_t b0 = t[k], b1 = t[k + 1];
+                    if ((b0 & 0xE0u) == 0xC0u && lim >= 2 && (b1 & 0xC0u) == 0x80u) {
+                        // a 2-byte character (Latin-1 .. Arabic): its code straight from the table by code point - the same
+                        // value dpt_char_code(dpt_char_at(...)) gives, without the decode and the two-stage class look-up
+                        c = P.V.code2[((b0 & 0x1Fu) << 6) | (b1 & 0x3Fu)];
+                        ch.len = 2;
+                        ch.cls = c & 3u;
+                        ch.cp = 0;
+                    } else {
+                        ch = dpt_char_at(U, t, k, k + lim);
+                        c = dpt_char_code(ch);
+                    }
                     const uint32_t span = ((1u << ch.len) - 1u) << k;  // the bytes of this character: the scanners only ever
                     hi &= ~span;                                       // ask about its first
                     keep &= ~(1u << k);
@@ -619,6 +655,9 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
     blk.sync();
 
     // ---- boundary rule -> word starts ---------------------------------------------------------------------
+    const int chunk = (PA_NW + nt - 1) / nt;  // mask words per thread: [w0, w1)
+    const int w0 = tid * chunk, w1 = (w0 + chunk) < PA_NW ? (w0 + chunk) : PA_NW;
+    uint32_t my_cnt = 0;  // entries that start in this thread's mask words | document starts up to them << 16
     if (!spm) {
         // Byte-level rules (dpt_split_rules.h).  (0) for every mask word the next document start at or after it
         // (documents are long: without this every "where does this document end" question scans the whole mask).
@@ -668,16 +707,16 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
             S.mCX[w] = 0;
         }
         blk.sync();
-        // (2) the stretch that covers the first byte of the tile starts at the last sync point at or before it
-        if (tid == 0) {
-            int sf = -1;
-            for (int w = own_lo >> 5; w >= 0 && sf < 0; --w) {
-                const uint32_t m = S.mSY[w] & pp_range_mask(w, 0, own_lo + 1);
-                if (m) sf = (w << 5) + 31 - pp_clz(m);
-            }
-            S.s_first = sf;
-            S.first_sync_global = -1;
-            if (sf < 0) {  // no sync point in the look-behind: walk back through the text (rare: a piece-free run > 32 B)
+        // (2) the stretch that covers the first byte of the tile starts at the last sync point at or before it: every
+        // thread finds it for itself in the one or two mask words of the look-behind (a thread-0 section and a barrier
+        // here kept 255 threads waiting)
+        int sf = -1;
+        for (int w = own_lo >> 5; w >= 0 && sf < 0; --w) {
+            const uint32_t m = S.mSY[w] & pp_range_mask(w, 0, own_lo + 1);
+            if (m) sf = (w << 5) + 31 - pp_clz(m);
+        }
+        if (sf < 0) {  // (block-uniform) no sync point in the look-behind: walk back through the text (rare: a piece-free run > 32 B)
+            if (tid == 0) {
                 const int64_t d = pp_upper_bound(P.doc_offs, P.n_docs + 1, t0) - 1;
                 const int64_t dstart = P.doc_offs[d < 0 ? 0 : d];
                 const int nd = next_ds(own_lo);
@@ -686,18 +725,15 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                 while (q > dstart && !dpt_is_sync_space(P.rule, U, P.text, q, dend)) --q;
                 S.first_sync_global = q < dstart ? dstart : q;
             }
+            blk.sync();
         }
-        blk.sync();
         // (3) one thread per stretch between consecutive sync points: sequential regex scanner, marks piece starts
         {
-            const int sf = S.s_first;
             const int chunk = (PA_NW + nt - 1) / nt;
             // stretch list = sync bits in (max(sf,-1) .. PA_R); the first stretch starts at sf (or in global memory)
-            for (int w = tid; w < PA_NW; w += nt) S.cnt[w] = (uint32_t)pp_popc(S.mSY[w] & pp_range_mask(w, sf < 0 ? 0 : sf, PA_R));
-            blk.sync();
             const int w0 = tid * chunk, w1 = (w0 + chunk) < PA_NW ? (w0 + chunk) : PA_NW;
             uint32_t mine = 0;
-            for (int w = w0; w < w1; ++w) mine += S.cnt[w];
+            for (int w = w0; w < w1; ++w) mine += (uint32_t)pp_popc(S.mSY[w] & pp_range_mask(w, sf < 0 ? 0 : sf, PA_R));
             uint32_t total;
             uint32_t off = blk.exclusive_scan(mine, S.scan, total);
             for (int w = w0; w < w1; ++w) {
@@ -758,15 +794,15 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
             }
         }
         blk.sync();
-        for (int w = tid; w < PA_NW; w += nt) {
+        for (int w = w0; w < w1; ++w) {  // (this thread's own mask words: their counts stay in a register)
             const uint32_t ds = S.mDS[w];
             const uint32_t ws = S.mWS[w] | ds;
             S.mWS[w] = ws;
-            S.cnt[w] = (uint32_t)pp_popc(ws & own_mask(w)) | ((uint32_t)pp_popc(ds & upto_mask(w)) << 16);
+            my_cnt += (uint32_t)pp_popc(ws & own_mask(w)) | ((uint32_t)pp_popc(ds & upto_mask(w)) << 16);
         }
     } else
     {
-        for (int w = tid; w < PA_NW; w += nt) {
+        for (int w = w0; w < w1; ++w) {
             const uint32_t ds = S.mDS[w], dsn = S.mDS[w + 1], dsp = w ? S.mDS[w - 1] : 0u;
             const uint32_t cs = S.mCS[w], csn = (w + 1 < PA_NW) ? S.mCS[w + 1] : ~0u, csp = w ? S.mCS[w - 1] : 0u;
             // raw U+2581 at p: E2 96 81 inside one document, followed by a character start
@@ -795,8 +831,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
             if (cx) S.any_cx = 1u;
             const uint32_t rm = own_mask(w);
             // words (and '<s>' words) that start in this tile | document starts up to here << 16
-            S.cnt[w] = (uint32_t)(pp_popc(ws & rm) + (spm ? pp_popc(ds & rm) : 0)) |
-                       ((uint32_t)pp_popc(ds & upto_mask(w)) << 16);
+            my_cnt += (uint32_t)(pp_popc(ws & rm) + (spm ? pp_popc(ds & rm) : 0)) | ((uint32_t)pp_popc(ds & upto_mask(w)) << 16);
             amb &= rm;
             // (with the tokenizer's merge table kernel B splits these runs itself: pb_segment_split; nothing is ambiguous)
             while (amb && P.doc_flags && !P.V.merge_mask) {
@@ -807,18 +842,15 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
             }
         }
     }
-    blk.sync();
+    // (no barrier here: every thread wrote the word-start masks of its own mask words and kept their counts; the scan's
+    // barriers order the masks for the probe phase, which reads its neighbours')
 
     // ---- entries (words and '<s>' words) that start in this tile, in corpus order ---------------------------------
-    const int chunk = (PA_NW + nt - 1) / nt;
-    const int w0 = tid * chunk, w1 = (w0 + chunk) < PA_NW ? (w0 + chunk) : PA_NW;
     uint32_t my_off, my_dord;
     int ne;
     {
-        uint32_t mine = 0;
-        for (int w = w0; w < w1; ++w) mine += S.cnt[w];
         uint32_t total;
-        const uint32_t ex = blk.exclusive_scan(mine, S.scan, total);
+        const uint32_t ex = blk.exclusive_scan(my_cnt, S.scan, total);
         my_off = ex & 0xFFFFu;
         my_dord = ex >> 16;  // document starts in the region before this thread's chunk
         ne = (int)(total & 0xFFFFu);

@@ -15,7 +15,7 @@
 
 // resident CTAs per SM the kernels are compiled for (register budgets; tuned on the B200, profiles/README.md)
 #ifndef DPT_PA_CTAS
-#define DPT_PA_CTAS 8
+#define DPT_PA_CTAS 5  // SentencePiece kernel A: 8064-byte tiles, 48 registers, 30 KB of shared memory
 #endif
 #ifndef DPT_PABL_CTAS
 #define DPT_PABL_CTAS 4  // byte-level kernel A: 55 registers; 5 and 6 CTAs measured slower over the two byte-level workloads
@@ -218,7 +218,7 @@ struct DevBlk {
     }
 };
 
-// SPM_LLAMA rule: 20 KB of shared memory and <= 32 registers -> 8 CTAs (64 warps) per SM
+// SPM_LLAMA rule: 8 KB regions, 30 KB of shared memory, <= 48 registers -> 5 CTAs (40 warps) per SM (PaGeom, dpt_pipe.h)
 __global__ void __launch_bounds__(PA_THREADS, DPT_PA_CTAS) k_scan_dedup(const __grid_constant__ PipeParams P) {
     __shared__ ASmemT<true> S;
     DevBlk blk;
@@ -226,9 +226,11 @@ __global__ void __launch_bounds__(PA_THREADS, DPT_PA_CTAS) k_scan_dedup(const __
 }
 // byte-level rules (GPT-2, Llama-3): the split scanner needs more registers and the sync-point list more memory
 __global__ void __launch_bounds__(PA_THREADS, DPT_PABL_CTAS) k_scan_dedup_bl(const __grid_constant__ PipeParams P) {
+#if !defined(DPT_VARIANT_SPM_ONLY)  // (tuning builds of the SentencePiece kernel with tile sizes whose byte-level shared memory exceeds 48 KB)
     __shared__ ASmemT<false> S;
     DevBlk blk;
     pa_kernel<DevBlk, false>(blk, P, S);
+#endif
 }
 
 // the lock-step DP (dpt_dp_lock.cuh): words of at most 31 units (length classes 0..2) ...
@@ -241,7 +243,8 @@ __global__ void __launch_bounds__(PBL_THREADS, DPT_PBL_CTAS) k_dp_lock_bl(const 
     pbl_kernel<false, 8>(P, S);
 }
 // ... and of 32..63 units (class 3: a few thousand words): one warp per word (dpt_dp_warp.cuh).  The lock-step kernel's
-// 64-byte instantiation (pbl_kernel<., 16>) solved them in 0.127 ms - one serial chain per word - this one in ~0.02 ms.
+// 64-row instantiation (pbl_kernel<., 16>) solved them in 0.127 ms - one serial chain per word - this one in ~0.02 ms; with
+// ~45 k such words (German compounds of the sentence-pair corpus) the two are level (0.27 / 0.31 ms), so there is one path.
 __global__ void __launch_bounds__(PBW_THREADS) k_dp_warp_spm(const __grid_constant__ PipeParams P) { pbw_kernel<true>(P); }
 __global__ void __launch_bounds__(PBW_THREADS) k_dp_warp_bl(const __grid_constant__ PipeParams P) { pbw_kernel<false>(P); }
 
@@ -498,8 +501,9 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
             clear.n16[1] = (unsigned long long)((zero_bytes + 15) / 16);  // (up to 8 bytes of the padding in front of refs)
         }
     }
-    P.tile_first = (int32_t)(byte_begin / PA_T);
-    P.n_tiles = (int32_t)((byte_end + PA_T - 1) / PA_T - byte_begin / PA_T);
+    const int64_t pa_t = rule == DPT_RULE_SPM_LLAMA ? PaGeom<true>::T : PaGeom<false>::T;  // (<= the sizing's PA_T tiles either way)
+    P.tile_first = (int32_t)(byte_begin / pa_t);
+    P.n_tiles = (int32_t)((byte_end + pa_t - 1) / pa_t - byte_begin / pa_t);
     P.n_ctiles = (int32_t)z.n_ctiles;
     P.spm = rule == DPT_RULE_SPM_LLAMA ? 1 : 0;
     P.rule = rule;

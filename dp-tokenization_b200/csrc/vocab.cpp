@@ -2,6 +2,7 @@
 // Replaces the Python `set`/`dict` of tokenizer_utils.py:57,105-113 whose `in` probe is the inner
 // operation of dp_tokenize.py:39.  Host-only C++; the result is uploaded to HBM as one blob.
 #include "vocab.h"
+#include "dpt_split_rules.h"
 
 #include "dpt_dp_core.h"
 #include "dpt_unicode_tables.h"
@@ -95,6 +96,17 @@ void dpt_vocab::rebuild_host_view() {
     h_view.merge_vals = merge_vals.empty() ? nullptr : merge_vals.data();
     h_view.merge_mask = merge_keys.empty() ? 0u : (uint32_t)merge_keys.size() - 1u;
     h_view.byte_ids = byte_token_id;
+    {   // (the same for every vocabulary: a function of the Unicode class tables only)
+        const DptUniView U{DPT_UNI_STAGE1, DPT_UNI_STAGE2};
+        for (uint32_t cp = 0; cp < 2048; ++cp) {
+            DptChar c;
+            c.cp = cp;
+            c.len = 2;
+            c.cls = dpt_cp_class(U, cp);
+            code2[cp] = (uint8_t)dpt_char_code(c);
+        }
+    }
+    h_view.code2 = code2;
 }
 
 // merges in rank order (index = rank); a pair listed twice keeps its first (lowest) rank, like the tokenizer's own map

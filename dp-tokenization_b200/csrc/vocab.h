@@ -32,6 +32,7 @@ struct dpt_vocab {
     std::vector<int32_t> tok_ids;   // dense rank -> id
     std::vector<int32_t> id_rank;   // id -> dense rank or -1
     std::vector<unsigned long long> merge_keys, merge_vals;  // BPE merges (dpt_merge_lookup); empty = none
+    uint8_t code2[2048];                                     // DptVocabView::code2
 
     // device copy
     int device = -1;

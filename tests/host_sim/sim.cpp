@@ -217,7 +217,8 @@ int32_t sim_encode_corpus_pipe(void* vv, int32_t rule, const uint8_t* text, int6
         P.doc_flags = doc_flags ? r_dflags.data() : nullptr;
         P.counters = (unsigned long long*)r_ctr;
         P.n_out = r_nout;
-        const int64_t n_tiles = (b1 + PA_T - 1) / PA_T - b0 / PA_T, n_ctiles = (r_word_cap + PC_TILE - 1) / PC_TILE;
+        const int64_t pa_t = rule == 1 ? PaGeom<true>::T : PaGeom<false>::T;  // this rule's tile (dpt_pipe.h: PaGeom)
+        const int64_t n_tiles = (b1 + pa_t - 1) / pa_t - b0 / pa_t, n_ctiles = (r_word_cap + PC_TILE - 1) / PC_TILE;
         PipeCtl ctl{};
         std::vector<unsigned long long> dw(n_tiles + 1, 0), dt(n_ctiles + 1, 0);
         std::vector<ResRec> odd_res(odd_cap);
@@ -248,7 +249,7 @@ int32_t sim_encode_corpus_pipe(void* vv, int32_t rule, const uint8_t* text, int6
         P.pool_cap = pool_cap;
         P.lp_cap = lp_cap;
         P.slot_mask = (uint32_t)(n_slots - 1);
-        P.tile_first = (int32_t)(b0 / PA_T);
+        P.tile_first = (int32_t)(b0 / pa_t);
         P.n_tiles = (int32_t)n_tiles;
         P.n_ctiles = (int32_t)n_ctiles;
         P.spm = rule == 1 ? 1 : 0;  // DPT_RULE_SPM_LLAMA
