@@ -391,7 +391,10 @@ def roofline_of(cx: Ctx, m, n_bytes, steps, total_ms=None):
     tr = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.isfile(tr):
         try:
-            out["traffic"] = json.load(open(tr)).get(name)
+            t = json.load(open(tr))
+            # the capture was taken on a 100 MB corpus: only a launch over (about) as many bytes can be compared with it
+            if abs(n_bytes - t.get("_capture_corpus_bytes", 100_000_000)) <= 0.05 * t.get("_capture_corpus_bytes", 100_000_000):
+                out["traffic"] = t.get(name)
         except Exception:
             pass
     return out
