@@ -383,7 +383,10 @@ def roofline_of(cx: Ctx, m, n_bytes, steps, total_ms=None):
     out = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": cx.peak, "unit": "GB/s",
            "frac": achieved / cx.peak, "traffic": None, "peak_source": cx.peak_src,
            "kernel_algorithmic_bytes_per_launch": k_ab / launches_per_step,
-           "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": ms / sum(r[2] for r in prof),
+           "kernel_ms_per_launch": per_launch_ms,
+           # share of the STEP (kernels on the library's side streams overlap the lock-step DP kernel: the per-kernel times
+           # do not add up to the step)
+           "kernel_share_of_step": ms / total_ms if total_ms > 0 else None,
            "algorithmic_bytes_per_step": ab,
            "whole_path_achieved_gbs": whole, "whole_path_frac": whole / cx.peak,
            "kernels_ms_per_step": {r[0]: r[2] / steps for r in prof},
@@ -439,6 +442,8 @@ def distinct_share(cx: Ctx, engine, wl, word_cap, worst=False):
     tb = lib.dpt_corpus_table_workspace(wl["n_bytes"], word_cap, int(worst))
     tb_al = (tb + 255) // 256 * 256
     ctl = engine._ws[tb_al:tb_al + 64].cpu().numpy().view(np.uint32)
+    distinct_share.last = {"queued_by_length_class": [int(x) for x in ctl[2:7]], "odd_words": int(ctl[7]), "long_words": int(ctl[8]),
+                           "deferred_words": int(ctl[9])}
     return int(ctl[2:7].sum() + ctl[7])  # n_pending[0..4] + n_odd
 
 
@@ -601,6 +606,7 @@ def main():
                 nd = distinct_share(cx, oeng, owl, om["word_cap"], om["worst"])
                 redundancy["rows"].append({"suffix_prob": p, "distinct_words": nd, "words": rec["words"],
                                            "distinct_share": nd / max(rec["words"], 1), "worst_case_table": om["worst"],
+                                           "dp_work_lists": getattr(distinct_share, "last", None),
                                            "ms_per_step": rec["ms_per_step"],
                                            "value": rec["value"], "kernels_ms_per_step": rec["roofline"]["kernels_ms_per_step"]})
                 del owl, om

@@ -334,8 +334,10 @@ static TableSizes table_sizes(int64_t n_bytes_total, int64_t word_cap_total, int
     // distinct, 2 = "roomy": a table for 1 distinct word per 10 bytes with the typical sizes for everything else - for
     // corpora that are mostly distinct words (identifiers, hashes): their first occurrences then go through the lock-step DP
     // kernel instead of overflowing into the per-occurrence odd-word path
-    int64_t want = worst == 1 ? word_cap_total : worst == 2 ? n_bytes_total / 10 : n_bytes_total / 48;
-    if (worst == 2 && want > word_cap_total) want = word_cap_total;
+    // (never more than two slots per word the caller makes room for: every word distinct is a load of 1/2, where 16 probes
+    // practically always find a place - at one slot per word 6 % of the words of an all-distinct corpus became odd words)
+    int64_t want = worst == 1 ? 2 * word_cap_total : worst == 2 ? n_bytes_total / 10 : n_bytes_total / 48;
+    if (worst == 2 && want > 2 * word_cap_total) want = 2 * word_cap_total;
     if (want < 4096) want = 4096;
     int64_t s = 4096;
     while (s < want) s <<= 1;
