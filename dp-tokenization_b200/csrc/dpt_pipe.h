@@ -74,7 +74,10 @@ struct PaGeom {
     static constexpr int WIN = kSpm ? DPT_PA_WIN_SPM : DPT_PA_WIN;
 };
 constexpr int PA_MAXLEN = 63;                 // longest word body (bytes) that goes through the dedup table
-constexpr int PA_PROBES = 16;                // (8: ~5e-4 of the distinct words found their neighbourhood full and became odd words)
+constexpr int PA_PROBES = 32;                // probes before a word gives up on the table and becomes an odd word (a run-time loop:
+                                              // nearly every word needs one or two).  16 lost 0.9 % of the words of an all-distinct
+                                              // corpus at a load of 0.45 - linear probing clusters - and their per-occurrence DP
+                                              // (k_dp_distinct, 2.1 ms) was that pass's critical path; 8 lost 5e-4 at a load of 0.3
 constexpr int PB_THREADS = 128;
 constexpr int PB_CLASSES = 5;                 // length classes of the DP work queues (8 measured no better: lane
                                               // imbalance comes from walk depths, not from word length)

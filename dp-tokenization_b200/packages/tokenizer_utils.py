@@ -243,7 +243,7 @@ def dp_tokenize_llama(llama_tokenizer, pretokenize_option="llama", cache_dir=Non
         dp_tokenize.batch = _encode_many
     elif pretokenize_option == "raw":
         raw_split = pretokenize_raw(manual_mapping)
-        vocab = set(t2i_dict)
+        vocab = frozenset(t2i_dict)  # (immutable: dp_tokenize._engine_for recognises the object and compiles it once)
 
         def dp_tokenize(input_str) -> List[int]:
             ids: List[int] = []

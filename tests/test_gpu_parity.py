@@ -308,11 +308,17 @@ def test_undersized_word_table_odd_words_and_worst_case_retry(dev):
         np.cumsum([len(d) for d in docs], out=offs[1:])
         return np.frombuffer(b"".join(docs), dtype=np.uint8).copy(), offs, docs
 
-    for n_words, n_distinct, expect_worst in ((130_000, 36_000, False), (120_000, 120_000, True)):
+    for n_words, n_distinct, expect_worst in ((130_000, 36_000, 0), (120_000, 120_000, 1)):
         text, offs, docs = corpus(n_words, n_distinct)
+        _tok, _t2i, eng = _llama_engine("llama2_32k", dev)   # a fresh engine: no table-size hint from the corpus before
         res = eng.encode_corpus(_to_dev(text, dev), _to_dev(offs, dev), _cabi.RULE_SPM_LLAMA)
         h = eng.last_n_out
         assert eng.last_worst == expect_worst, (h, len(text))
+        if not expect_worst:
+            # > 2 % of the words were odd: the engine asks for the roomy table next time, and with it nothing overflows
+            again = eng.encode_corpus(_to_dev(text, dev), _to_dev(offs, dev), _cabi.RULE_SPM_LLAMA)
+            assert eng.last_worst == 2 and eng.last_n_out[6] < 50, eng.last_n_out
+            assert torch.equal(again.ids, res.ids) and torch.equal(again.word_lens, res.word_lens)
         if not expect_worst:
             n_slots = 4096
             while n_slots < len(text) // 48:
