@@ -1,8 +1,11 @@
 // CUDA kernels (sm_100a) + host launch orchestration for the reference-shaped pipeline:
 //   boundary/normalise  ->  per-word DP (count)  ->  scan  ->  per-word DP (emit)  ->  counters.
 // This is the general path: it accepts ANY word (any length, any unit boundaries, out-of-vocab
-// characters expanded to "<0xHH>" text) and is the exact-by-construction backstop behind the fused
-// tile kernel in fused.cu, which handles the common short-word case at speed.
+// characters expanded to "<0xHH>" text).  It runs one DP per word OCCURRENCE (twice: count, then emit) and is what
+// dpt_encode_words (pre-split words from a host pre-tokenizer) and dpt_encode_corpus_general (the cross-check of the
+// deduplicating corpus pipeline in pipe.cu) are made of; the throughput path is the pipeline.  k_lattice, k_min_tokens
+// (one serial thread) and k_roundtrip (one thread per document) are known-answer / checking entry points, not throughput
+// paths.
 #include <cuda_runtime.h>
 
 #include <cstdio>
