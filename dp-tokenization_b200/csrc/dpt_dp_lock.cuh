@@ -326,7 +326,16 @@ __device__ __forceinline__ void pbl_kernel(const PipeParams& P, PblSmem<NW>& S) 
     const uint32_t nq1 = NW == 8 ? pb_queue_len(P, 1) : 0u, nq0 = NW == 8 ? pb_queue_len(P, 0) : 0u;
     const int cls_first = NW == 8 ? 2 : 3;
     const uint32_t total = nq2 + nq1 + nq0;
-    const uint32_t n_chunks = (total + CHUNK - 1) / CHUNK;
+    // Words per chunk: CHUNK when there is work for every CTA; with fewer words (a 16 MB range of a chunked call adds
+    // ~30 k distinct words, a single document a few hundred) smaller chunks - down to one batch of 32 - so that the words
+    // spread over all CTAs and the kernel takes the time of ONE batch instead of the 8 a full chunk holds (0.17 ms per
+    // launch however few the words were: the chunked host path paid it once per range, profiles/r2_e2e_timeline_n1.txt).
+    uint32_t cw = (uint32_t)CHUNK;
+    if (total < gridDim.x * (uint32_t)CHUNK) {
+        cw = ((total + gridDim.x - 1) / gridDim.x + 31u) & ~31u;
+        cw = cw < 32u ? 32u : cw > (uint32_t)CHUNK ? (uint32_t)CHUNK : cw;
+    }
+    const uint32_t n_chunks = (total + cw - 1) / cw;
     unsigned int* const ticket = NW == 8 ? &P.ctl->lock_ticket : &P.ctl->lock_ticket2;
     for (;;) {
         if (tid == 0) S.chunk = atomicAdd(ticket, 1u);
@@ -334,8 +343,8 @@ __device__ __forceinline__ void pbl_kernel(const PipeParams& P, PblSmem<NW>& S) 
         __syncthreads();
         const uint32_t chunk = S.chunk;
         if (chunk >= n_chunks) break;
-        const uint32_t c0 = chunk * CHUNK;
-        const int count = (int)(total - c0 < (uint32_t)CHUNK ? total - c0 : (uint32_t)CHUNK);
+        const uint32_t c0 = chunk * cw;
+        const int count = (int)(total - c0 < cw ? total - c0 : cw);
         // this thread's words of the chunk
         uint32_t slot[PER];
         unsigned long long tag[PER];
