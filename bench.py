@@ -652,7 +652,7 @@ def main_multi(cx: Ctx, args):
     h_offs = wl["d_offs"].cpu().numpy()
     b = shard_bounds(h_offs, world)
     lo, hi = int(b[rank]), int(b[rank + 1])
-    s_text = wl["d_text"][int(h_offs[lo]):int(h_offs[hi])]
+    s_text = wl["d_text"][int(h_offs[lo]):int(h_offs[hi])].clone()  # this rank's shard in a buffer of its own (16-byte aligned)
     s_offs = (wl["d_offs"][lo:hi + 1] - wl["d_offs"][lo]).contiguous()
     sampler = ClockSampler(cx.local_rank)
     m = measure_resident(cx, engine, s_text, s_offs, wl["rule"], steps, args.warmup, sampler=sampler)
