@@ -38,24 +38,25 @@ struct alignas(16) uint4 {
 namespace dpt {
 
 #ifndef DPT_PA_T
-#define DPT_PA_T 3968
+#define DPT_PA_T 6016  // byte-level rules (PaGeom below has the SentencePiece tile): 6144-byte regions, 57 KB of dynamic shared memory
 #endif
 #ifndef DPT_PA_THREADS
 #define DPT_PA_THREADS 256
 #endif
 #ifndef DPT_PA_WIN
-#define DPT_PA_WIN 768
+#define DPT_PA_WIN 1152
 #endif
 constexpr int PA_T = DPT_PA_T;                // raw bytes per tile of kernel A
 constexpr int PA_HALO = 32;                   // look-behind (multiple of 32 keeps mask words aligned)
 constexpr int PA_LA = 96;                     // look-ahead: a word that ends within it is handled in-tile
-constexpr int PA_R = PA_HALO + PA_T + PA_LA;  // region bytes = 4096 = 256 x 16: one 16-byte load and one 16-bit mask
-                                              // slice per thread (4096-byte tiles made 8 threads go round twice: 0.390 -> 0.380 ms)
+constexpr int PA_R = PA_HALO + PA_T + PA_LA;  // region bytes, a multiple of 32 (mask words) and of 16 (one 16-byte load per thread and round)
 static_assert(PA_HALO == 32 && PA_LA == 96, "PaGeom spells the halo and the look-ahead out");
 constexpr int PA_NW = PA_R / 32;
 constexpr int PA_THREADS = DPT_PA_THREADS;
-// Tile geometry per boundary rule.  The byte-level kernels keep the 3968-byte tile (their shared memory - code array,
-// sync-point and document lists - grows with the region: 37 KB at 4 KB).  The SentencePiece kernel takes 8064-byte tiles
+// Tile geometry per boundary rule.  The byte-level kernels take 6016-byte tiles (6144-byte regions, windows of 1152 words,
+// 3 CTAs/SM at 64 registers: their shared memory - code array, sync-point and document lists - grows with the region, 57 KB
+// here; 1.056 -> 0.974 ms per 100 MB of the Llama-3 mix, 1.003 -> 0.890 on en/de pairs; 8064-byte tiles: 0.999 / 0.948;
+// round 1's 3968-byte tiles at 4 CTAs/SM were the best the 48 KB static limit allowed).  The SentencePiece kernel takes 8064-byte tiles
 // (8192-byte region) with windows of 1152 words at 5 CTAs/SM and 48 registers: the per-tile work (document search,
 // look-back, scans, barriers) is amortised over twice the bytes and nothing spills - 0.378 -> 0.352 ms on the B200; 6016
 // and 11136-byte tiles, 4 or 6 CTAs/SM and 512 threads were all slower (profiles/r2_variants_tile_size.txt).  PA_T / PA_R /

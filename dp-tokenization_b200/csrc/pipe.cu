@@ -18,7 +18,7 @@
 #define DPT_PA_CTAS 5  // SentencePiece kernel A: 8064-byte tiles, 48 registers, 30 KB of shared memory
 #endif
 #ifndef DPT_PABL_CTAS
-#define DPT_PABL_CTAS 4  // byte-level kernel A: 55 registers; 5 and 6 CTAs measured slower over the two byte-level workloads
+#define DPT_PABL_CTAS 3  // byte-level kernel A: 6016-byte tiles, 57 KB of shared memory, <= 64 registers
 #endif
 #ifndef DPT_PB_CTAS
 #define DPT_PB_CTAS 12
@@ -225,12 +225,12 @@ __global__ void __launch_bounds__(PA_THREADS, DPT_PA_CTAS) k_scan_dedup(const __
     pa_kernel<DevBlk, true>(blk, P, S);
 }
 // byte-level rules (GPT-2, Llama-3): the split scanner needs more registers and the sync-point list more memory
+// (its shared memory - 37 KB at 3968-byte tiles - is DYNAMIC, so that tile sizes beyond the 48 KB static limit can be used)
 __global__ void __launch_bounds__(PA_THREADS, DPT_PABL_CTAS) k_scan_dedup_bl(const __grid_constant__ PipeParams P) {
-#if !defined(DPT_VARIANT_SPM_ONLY)  // (tuning builds of the SentencePiece kernel with tile sizes whose byte-level shared memory exceeds 48 KB)
-    __shared__ ASmemT<false> S;
+    extern __shared__ __align__(16) unsigned char pa_bl_smem[];
+    ASmemT<false>& S = *reinterpret_cast<ASmemT<false>*>(pa_bl_smem);
     DevBlk blk;
     pa_kernel<DevBlk, false>(blk, P, S);
-#endif
 }
 
 // the lock-step DP (dpt_dp_lock.cuh): words of at most 31 units (length classes 0..2) ...
@@ -528,10 +528,20 @@ int encode_corpus_range(const dpt_vocab* v, int32_t rule, const uint8_t* d_text,
     if (do_scan) {
     {
         ProfScope prof(P.spm ? "k_scan_dedup" : "k_scan_dedup_bl", st);
-        if (P.spm)
+        if (P.spm) {
             k_scan_dedup<<<(unsigned)P.n_tiles, PA_THREADS, 0, st>>>(P);
-        else
-            k_scan_dedup_bl<<<(unsigned)P.n_tiles, PA_THREADS, 0, st>>>(P);
+        } else {
+            static bool bl_attr = false;  // (per process; the attribute is per function and device - set again after a device change is harmless)
+            static int bl_dev = -1;
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (!bl_attr || bl_dev != dev) {
+                cudaFuncSetAttribute(k_scan_dedup_bl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ASmemT<false>));
+                bl_attr = true;
+                bl_dev = dev;
+            }
+            k_scan_dedup_bl<<<(unsigned)P.n_tiles, PA_THREADS, sizeof(ASmemT<false>), st>>>(P);
+        }
         ++g_launches;
     }
     }
