@@ -91,13 +91,19 @@ constexpr int PB_LOCAL = 72;                  // normalised bytes solved with pe
 #define DPT_PB_REFILL 1
 #endif
 constexpr int PB_REFILL = DPT_PB_REFILL;
-constexpr int PC_THREADS = 256;
+#ifndef DPT_PC_THREADS
+#define DPT_PC_THREADS 256
+#endif
+#ifndef DPT_PC_STAGE
+#define DPT_PC_STAGE 6144
+#endif
+constexpr int PC_THREADS = DPT_PC_THREADS;
 constexpr int PC_PER = 8;                     // words per thread in kernel C
 constexpr int PA_WIN = DPT_PA_WIN;                  // words of a tile handled per pass.  A tile holds ~500-540 words: with 512 most
                                               // byte-level tiles needed a second, nearly empty pass and resolved their look-back
                                               // BEFORE probing (768: k_scan_dedup_bl 1.44 -> 1.38 / 1.46 -> 1.31 ms, SPM unchanged)
 constexpr int PC_TILE = PC_THREADS * PC_PER;
-constexpr int PC_STAGE = 6144;                // ids of one kernel-C tile staged in shared memory (more -> direct writes)
+constexpr int PC_STAGE = DPT_PC_STAGE;                // ids of one kernel-C tile staged in shared memory (more -> direct writes)
 
 // one 32-bit ref per word: top two bits 11 = the '<s>' word in front of an SPM_LLAMA document | document index,
 // 10 = index into the odd-word list (not deduplicated), otherwise the word's table slot
