@@ -214,7 +214,6 @@ struct ASmemT {
     uint32_t mCS[PA_NW + 2];  // code-point start bytes
     uint32_t mSP[PA_NW + 2];  // ' '
     uint32_t mM3[PA_NW + 2];  // E2 96 81 candidates
-    uint32_t mCF[PA_NW + 2];  // character starts = CS | DS
     uint32_t mWS[PA_NW + 2];  // word starts
     uint32_t mCX[PA_NW + 2];  // positions that make their word "odd" (solved from the raw text, not deduplicated)
     uint32_t mSY[PA_NW + 2];  // byte-level rules: synchronisation points of the split scanner
@@ -222,7 +221,6 @@ struct ASmemT {
     uint32_t mNW[kSpm ? 2 : PA_NW + 2];  // byte-level rules: positions whose character can follow a synchronising space
     alignas(16) uint8_t code[kSpm ? 16 : PA_R + 64];  // byte-level rules: dpt_char_code of the character at every position
     alignas(16) uint8_t lut[kSpm ? 16 : 128];         // ... and of the 128 ASCII characters
-    uint32_t cnt[PA_NW + 2];
     uint32_t dsn[PA_NW + 2];  // byte-level rules: document starts in front of each mask word
     uint16_t wlist[WL_CAP];   // region index of the words of the current window (| 0x8000: a document's '<s>' word)
     uint16_t dslist[kSpm ? 2 : PA_R + 32];  // byte-level rules: region indices of the document starts, in order
@@ -232,7 +230,7 @@ struct ASmemT {
     int32_t tile, d_first, n_entries;
     uint32_t any_cx;          // some mCX bit is set in this tile (rare: the per-word range test is skipped otherwise)
     uint32_t n_pend, n_pend_c[PB_CLASSES], cur_c[PB_CLASSES], base_c[PB_CLASSES];
-    int32_t n_sync, s_first, n_ds;
+    int32_t n_sync, n_ds;
     long long region_doc_end, first_sync_global;
     unsigned long long base_w;
 };
@@ -524,7 +522,7 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
         if (tid >= nt - 4) *reinterpret_cast<uint4*>(&S.text[PA_R + 16 * (nt - 1 - tid)]) = uint4{0u, 0u, 0u, 0u};
         if (tid >= nt - 6 && tid < nt - 4) {  // the two mask words behind the region
             const int w = PA_NW + (nt - 5 - tid);
-            S.mCS[w] = S.mSP[w] = S.mM3[w] = S.mCF[w] = S.mWS[w] = S.mCX[w] = S.cnt[w] = S.mSY[w] = 0;
+            S.mCS[w] = S.mSP[w] = S.mM3[w] = S.mWS[w] = S.mCX[w] = S.mSY[w] = 0;
         }
         if (!spm) {
             for (int w = tid; w < PA_NW + 2; w += nt) {
@@ -835,7 +833,6 @@ DPT_PIPE_FN void pa_run_tile(Blk& blk, const PipeParams& P, ASmemT<kSpm>& S, con
                 ws = ds;  // byte-level rules add their own word starts; documents always split
                 cx = 0;
             }
-            S.mCF[w] = cs | ds;
             S.mWS[w] = ws;
             S.mCX[w] = cx;
             if (cx) S.any_cx = 1u;
