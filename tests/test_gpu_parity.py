@@ -443,6 +443,43 @@ def test_unaligned_corpus_buffer(dev):
             assert torch.equal(got.doc_tok_offs, ref.doc_tok_offs)
 
 
+def test_sharded_driver_with_the_real_engine(dev):
+    """SURVEY 8 row e with the real kernels: `ShardedTokenizer.run_global` cuts ONE corpus into contiguous document ranges
+    of equal bytes (`shard_bounds`), every "rank" tokenizes its shard with `Engine.encode_corpus`; the shards' ids,
+    concatenated in rank order, must equal the single-pass ids, and the counters must add up to the single-pass counters
+    (what the NCCL sum gives at N > 1; here the ranks run one after the other in one process).  Both rules."""
+    from dptok import _cabi, assets, synth
+    from dptok.engine import Engine
+    from dptok.sharded import ShardedTokenizer, shard_bounds
+    from dptok.vocab import CompiledVocab
+    tok, t2i, eng = _llama_engine("llama2_32k", dev)
+    spec = assets.load_spec("gpt2_3k")
+    beng = Engine(CompiledVocab.from_token_map({t: k for k, t in enumerate(spec["model"]["vocab"])}, "bytelevel"), dev)
+    text, doc_offs = synth.gen_documents(3_000_000, seed=8, newline_headers=True)
+    for engine, rule in ((eng, _cabi.RULE_SPM_LLAMA), (beng, _cabi.RULE_GPT2)):
+        whole = engine.encode_corpus(_to_dev(text, dev), _to_dev(doc_offs, dev), rule)
+        want_ids = whole.ids.cpu().numpy()
+        want_ctr = whole.counters.cpu().numpy()
+        want_dto = whole.doc_tok_offs.cpu().numpy()
+
+        def encode_fn(t, o):
+            return engine.encode_corpus(_to_dev(np.ascontiguousarray(t), dev), _to_dev(np.ascontiguousarray(o), dev), rule)
+
+        for world in (2, 3, 7):
+            b = shard_bounds(doc_offs, world)
+            ids, ctr, dto = [], np.zeros(4, dtype=np.int64), [np.zeros(1, dtype=np.int64)]
+            for rank in range(world):
+                res, stats = ShardedTokenizer(encode_fn, world=world, rank=rank).run_global(text, doc_offs)
+                assert res is not None and (stats.bytes, stats.words, stats.tokens) == tuple(res.counters.cpu().tolist()[:3])
+                ids.append(res.ids.cpu().numpy())
+                ctr += res.counters.cpu().numpy()
+                dto.append(res.doc_tok_offs.cpu().numpy()[1:] + dto[-1][-1])
+                assert int(res.counters[0]) == int(doc_offs[b[rank + 1]] - doc_offs[b[rank]])
+            assert np.array_equal(np.concatenate(ids), want_ids)
+            assert np.array_equal(ctr, want_ctr)
+            assert np.array_equal(np.concatenate(dto), want_dto)
+
+
 def test_full_size_properties_100mb(dev):
     """BASELINE.json configs[1] at full size (100 MB, Llama-2-shaped 32k vocab): size-independent properties -
     device decode round-trips every document, counters are consistent, the DP never uses more tokens than the
