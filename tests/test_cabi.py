@@ -149,3 +149,57 @@ def test_adapter_recognises_device_split_rules(product_lib):
     spec = json.loads(base.to_str())
     spec["normalizer"] = {"type": "NFC"}                                             # a normaliser in front
     assert _device_split_rule(Wrapped(Tokenizer.from_str(json.dumps(spec)))) is None
+
+
+def test_spm_device_rule_gate_and_merge_table(product_lib):
+    """The SentencePiece device rule is only used for the pipeline it hard-codes (Prepend(U+2581) + Replace(' ', U+2581), no
+    pre-tokenizer, '<s>' in front, nothing behind): `_spm_backend_matches_device_rule` reads the backend's JSON.  The merge
+    table handed to the compiled vocabulary comes from `model.merges` in rank order, in both serialisations (pairs and the
+    legacy "a b" strings); a vocabulary that cannot express a merge gives none."""
+    import json
+    from tokenizers import Tokenizer
+    from dptok import _cabi, assets
+    from dptok.vocab import CompiledVocab
+    from packages.tokenizer_utils import _spm_backend_matches_device_rule
+    tok = assets.load_hf("llama2_2k")
+    assert _spm_backend_matches_device_rule(tok)
+
+    class Wrapped:
+        def __init__(self, backend, **kw):
+            self._tokenizer = backend
+            self.__dict__.update(kw)
+
+    base = json.loads(assets.load_tokenizer("llama2_2k").to_str())
+
+    def variant(edit, **kw):
+        spec = json.loads(json.dumps(base))
+        edit(spec)
+        return Wrapped(Tokenizer.from_str(json.dumps(spec)), **kw)
+
+    assert _spm_backend_matches_device_rule(variant(lambda s: None))
+    assert not _spm_backend_matches_device_rule(variant(lambda s: None, add_eos_token=True))
+    assert not _spm_backend_matches_device_rule(variant(lambda s: s.update(post_processor=None)))              # no '<s>'
+    assert not _spm_backend_matches_device_rule(variant(lambda s: s["normalizer"]["normalizers"].pop(0)))      # no dummy prefix
+    assert not _spm_backend_matches_device_rule(variant(lambda s: s["normalizer"]["normalizers"].append({"type": "NFKC"})))
+    assert not _spm_backend_matches_device_rule(variant(lambda s: s.update(pre_tokenizer={"type": "Whitespace"})))
+
+    def eos_behind(s):
+        s["post_processor"]["single"].append({"SpecialToken": {"id": "<s>", "type_id": 0}})
+    assert not _spm_backend_matches_device_rule(variant(eos_behind))
+
+    t2i = tok.get_vocab()
+    merges = CompiledVocab.merges_of(tok, t2i)
+    assert merges and len(merges) == len(base["model"]["merges"])
+    a, b = base["model"]["merges"][0] if not isinstance(base["model"]["merges"][0], str) else base["model"]["merges"][0].split(" ")
+    assert merges[0] == (t2i[a], t2i[b], t2i[a + b])
+
+    def legacy(s):
+        s["model"]["merges"] = [m if isinstance(m, str) else " ".join(m) for m in s["model"]["merges"]]
+    assert CompiledVocab.merges_of(variant(legacy), t2i) == merges
+    smaller = {t: i for t, i in t2i.items() if t != a + b}
+    assert CompiledVocab.merges_of(tok, smaller) is None
+    # the table goes into the handle before the upload; ids outside the vocabulary are refused with a status
+    cv = CompiledVocab.from_token_map(t2i, "spm").set_merges(merges)
+    assert cv.n_merges == len(merges)
+    with pytest.raises(_cabi.DptError):
+        CompiledVocab.from_token_map(t2i, "spm").set_merges([(0, 1, 10 ** 6)])
