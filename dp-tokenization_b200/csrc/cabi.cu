@@ -328,7 +328,7 @@ int64_t dpt_pretokenize_workspace(int64_t n_bytes, int64_t n_docs) { return dpt:
 
 int64_t dpt_encode_words_workspace(int64_t n_bytes, int64_t n_words, int32_t worst_case) {
     const int64_t pool = worst_case ? 12 * (n_bytes + n_words) : 12 * (n_bytes / 8 + 65536);
-    return dpt::encode_words_workspace_fixed(n_words) + pool + 4096;
+    return dpt::encode_words_workspace_fixed(n_words, n_bytes) + pool + 4096;
 }
 
 int dpt_pretokenize(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, int64_t n_bytes, const int64_t* d_doc_offs,
@@ -357,7 +357,7 @@ int dpt_encode_words(const dpt_vocab* v, const uint8_t* d_text, const int64_t* d
                      int64_t workspace_bytes, void* stream) {
     if (int rc = check_ready(v, "dpt_encode_words")) return rc;
     std::string err;
-    const int rc = dpt::encode_words(v, d_text, d_word_offs, n_words, n_text_bytes, d_ids, ids_cap, d_word_lens,
+    const int rc = dpt::encode_words(v, d_text, d_word_offs, n_words, n_text_bytes, n_text_bytes, d_ids, ids_cap, d_word_lens,
                                      d_word_flags, d_word_tok_offs, d_counters, d_n_out, d_workspace, workspace_bytes,
                                      (cudaStream_t)stream, err);
     return rc ? fail(rc, err) : DPT_OK;
@@ -432,7 +432,7 @@ int dpt_encode_corpus_general(const dpt_vocab* v, int32_t rule, const uint8_t* d
         cudaStreamSynchronize(st);
         return fail(DPT_ECAPACITY, "dpt_encode_corpus: word or normalised-text capacity exceeded (see d_n_out)");
     }
-    rc = dpt::encode_words(v, norm, word_offs, n_words, n_bytes, d_ids, ids_cap, d_word_lens, d_word_flags, tok_offs,
+    rc = dpt::encode_words(v, norm, word_offs, n_words, n_bytes, n_norm, d_ids, ids_cap, d_word_lens, d_word_flags, tok_offs,
                            d_counters, d_n_out, enc_ws, enc_ws_bytes, st, err);
     if (rc) return fail(rc, err);
     int64_t h_tail[2] = {n_norm, norm_cap};

@@ -1,7 +1,8 @@
 // CUDA kernels (sm_100a) + host launch orchestration for the reference-shaped pipeline:
-//   boundary/normalise  ->  per-word DP (count)  ->  scan  ->  per-word DP (emit)  ->  counters.
+//   boundary/normalise  ->  per-word DP (ids into a stash)  ->  scan  ->  placement of the ids  ->  counters.
 // This is the general path: it accepts ANY word (any length, any unit boundaries, out-of-vocab
-// characters expanded to "<0xHH>" text).  It runs one DP per word OCCURRENCE (twice: count, then emit) and is what
+// characters expanded to "<0xHH>" text).  It runs one DP per word OCCURRENCE (the ids wait in a stash at the word's byte
+// offset until the scan over the token counts has placed them) and is what
 // dpt_encode_words (pre-split words from a host pre-tokenizer) and dpt_encode_corpus_general (the cross-check of the
 // deduplicating corpus pipeline in pipe.cu) are made of; the throughput path is the pipeline.  k_lattice, k_min_tokens
 // (one serial thread) and k_roundtrip (one thread per document) are known-answer / checking entry points, not throughput
@@ -219,10 +220,15 @@ struct LongCtl {
     unsigned long long pool_used;    // scratch positions handed out
 };
 
+// One DP per word: forward pass with back-pointers, token count and flags out, and the selected ids into
+// stash[a .. a + len) (a = the word's byte offset: a word of n bytes has at most n tokens, so the stash of one int32 per
+// text byte never overlaps).  k_dp_emit only moves them once the scan has placed the word.  Words lying beyond the
+// stash (a caller whose n_text_bytes understates the text) are solved again in k_dp_emit instead.
 __global__ void __launch_bounds__(DP_THREADS)
 k_dp_count(DptVocabView V, const uint8_t* __restrict__ text, const int64_t* __restrict__ word_offs, int64_t n_words,
            int32_t* __restrict__ lens, uint8_t* __restrict__ flags, const uint8_t* __restrict__ flags_in,
-           int32_t* __restrict__ long_list, int64_t* __restrict__ long_scratch, LongCtl* ctl) {
+           int32_t* __restrict__ long_list, int64_t* __restrict__ long_scratch, LongCtl* ctl,
+           int32_t* __restrict__ stash, int64_t stash_cap) {
     const int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (w >= n_words) return;
     const int64_t a = word_offs[w], b = word_offs[w + 1];
@@ -243,10 +249,12 @@ k_dp_count(DptVocabView V, const uint8_t* __restrict__ text, const int64_t* __re
         return;
     }
     uint64_t best[DP_LOCAL_CAP + 1];
-    dpt_forward<false>(V, text + a, (int32_t)n, nullptr, best, nullptr, nullptr);
+    uint16_t A[DP_LOCAL_CAP + 1], B[DP_LOCAL_CAP + 1];
+    dpt_forward<true>(V, text + a, (int32_t)n, nullptr, best, A, B);
     const uint64_t kn = best[n];
     lens[w] = (int32_t)dpt_key_len(kn);
     flags[w] = f | (dpt_key_reach(kn) ? 0 : DPT_WF_UNTOKENIZABLE);
+    if (a >= 0 && a + n <= stash_cap) dpt_backward_emit(V, text + a, (int32_t)n, best, A, B, stash + a, n);
 }
 
 // long words: one thread each, state in the global pool (12 bytes per position).
@@ -356,17 +364,22 @@ k_tok_offsets(const int32_t* __restrict__ lens, const uint8_t* __restrict__ flag
 
 __global__ void __launch_bounds__(DP_THREADS)
 k_dp_emit(DptVocabView V, const uint8_t* __restrict__ text, const int64_t* __restrict__ word_offs, int64_t n_words,
-          const uint8_t* __restrict__ flags, const int64_t* __restrict__ tok_offs, int32_t* __restrict__ ids,
-          int64_t ids_cap) {
+          const int32_t* __restrict__ lens, const uint8_t* __restrict__ flags, const int64_t* __restrict__ tok_offs,
+          const int32_t* __restrict__ stash, int64_t stash_cap, int32_t* __restrict__ ids, int64_t ids_cap) {
     const int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (w >= n_words) return;
     if (flags[w] & (DPT_WF_UNTOKENIZABLE | DPT_WF_LONG)) return;
     const int64_t a = word_offs[w];
     const int32_t n = (int32_t)(word_offs[w + 1] - a);
+    const int64_t o = tok_offs[w];
+    if (a >= 0 && a + n <= stash_cap) {  // the ids k_dp_count left at the word's byte offset
+        const int32_t len = lens[w];
+        for (int32_t k = 0; k < len && o + k < ids_cap; ++k) ids[o + k] = stash[a + k];
+        return;
+    }
     uint64_t best[DP_LOCAL_CAP + 1];
     uint16_t A[DP_LOCAL_CAP + 1], B[DP_LOCAL_CAP + 1];
     dpt_forward<true>(V, text + a, n, nullptr, best, A, B);
-    const int64_t o = tok_offs[w];
     dpt_backward_emit(V, text + a, n, best, A, B, ids + o, ids_cap - o);
 }
 
@@ -691,7 +704,7 @@ struct Carver {
     int64_t remaining() const { return cap - align_up(used, 256); }
 };
 
-int64_t encode_words_workspace_fixed(int64_t n_words) {
+int64_t encode_words_workspace_fixed(int64_t n_words, int64_t n_text_bytes) {
     const int64_t tiles = (n_words + SCAN_TILE - 1) / SCAN_TILE + 1;
     int64_t b = 0;
     b += align_up(tiles * 8, 256);             // tile sums
@@ -699,11 +712,12 @@ int64_t encode_words_workspace_fixed(int64_t n_words) {
     b += align_up((n_words + 1) * 8, 256);     // tok_offs (when the caller gives none)
     b += align_up(n_words * 4, 256);           // long_list
     b += align_up(n_words * 8, 256);           // long_scratch
+    b += align_up((n_text_bytes > 0 ? n_text_bytes : 0) * 4, 256);  // id stash: one int32 per text byte
     return b + 1024;
 }
 
 int encode_words(const dpt_vocab* v, const uint8_t* d_text, const int64_t* d_word_offs, int64_t n_words,
-                 int64_t n_bytes_for_counter, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens,
+                 int64_t n_bytes_for_counter, int64_t text_extent, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens,
                  uint8_t* d_word_flags, int64_t* d_word_tok_offs, int64_t* d_counters, int64_t* d_n_out,
                  void* d_ws, int64_t ws_bytes, cudaStream_t st, std::string& err) {
     if (n_words < 0 || !d_counters || !d_n_out) {
@@ -718,7 +732,8 @@ int encode_words(const dpt_vocab* v, const uint8_t* d_text, const int64_t* d_wor
         err = "encode_words: more than 2^31-1 words in one call; split the batch";
         return DPT_EINVAL;
     }
-    const int64_t fixed = encode_words_workspace_fixed(n_words);
+    if (text_extent < 0) text_extent = 0;
+    const int64_t fixed = encode_words_workspace_fixed(n_words, text_extent);
     if (!d_ws || ws_bytes < fixed) {
         err = "encode_words: workspace too small (see dpt_encode_words_workspace)";
         return DPT_ECAPACITY;
@@ -731,6 +746,7 @@ int encode_words(const dpt_vocab* v, const uint8_t* d_text, const int64_t* d_wor
     int64_t* tok_offs = d_word_tok_offs ? d_word_tok_offs : cv.take<int64_t>(n_words + 1);
     int32_t* long_list = cv.take<int32_t>(n_words);
     int64_t* long_scratch = cv.take<int64_t>(n_words);
+    int32_t* stash = cv.take<int32_t>(text_extent);
     // remaining workspace is the long-word pool: 12 bytes per position
     const int64_t pool_cap = cv.remaining() > 0 ? (cv.remaining() - 1024) / 12 : 0;
     uint64_t* pool_best = cv.take<uint64_t>(pool_cap > 0 ? pool_cap : 0);
@@ -744,7 +760,7 @@ int encode_words(const dpt_vocab* v, const uint8_t* d_text, const int64_t* d_wor
     if (n_words > 0) {
         const DptVocabView& V = v->d_view;
         DPT_LAUNCH(k_dp_count, blocks_for(n_words, DP_THREADS), DP_THREADS, st, V, d_text, d_word_offs, n_words,
-                   d_word_lens, d_word_flags, (const uint8_t*)nullptr, long_list, long_scratch, ctl);
+                   d_word_lens, d_word_flags, (const uint8_t*)nullptr, long_list, long_scratch, ctl, stash, text_extent);
         DPT_LAUNCH(k_dp_long, 148 * 2, DP_THREADS, st, V, d_text, d_word_offs, long_list, long_scratch, ctl, pool_best,
                    pool_a, pool_b, pool_cap, d_word_lens, d_word_flags, 0, (const int64_t*)nullptr, (int32_t*)nullptr,
                    (int64_t)0);
@@ -754,7 +770,7 @@ int encode_words(const dpt_vocab* v, const uint8_t* d_text, const int64_t* d_wor
         DPT_LAUNCH(k_tok_offsets, (unsigned)tiles, SCAN_THREADS, st, d_word_lens, d_word_flags, n_words, tile_sums, totals,
                    tok_offs);
         DPT_LAUNCH(k_dp_emit, blocks_for(n_words, DP_THREADS), DP_THREADS, st, V, d_text, d_word_offs, n_words,
-                   d_word_flags, tok_offs, d_ids, ids_cap);
+                   d_word_lens, d_word_flags, tok_offs, stash, text_extent, d_ids, ids_cap);
         DPT_LAUNCH(k_dp_long, 148 * 2, DP_THREADS, st, V, d_text, d_word_offs, long_list, long_scratch, ctl, pool_best,
                    pool_a, pool_b, pool_cap, d_word_lens, d_word_flags, 1, tok_offs, d_ids, ids_cap);
     }

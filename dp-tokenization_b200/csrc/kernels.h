@@ -42,12 +42,13 @@ int encode_corpus_pipe(const dpt_vocab* v, int32_t rule, const uint8_t* d_text, 
                        int64_t word_cap, int64_t* d_doc_tok_offs, uint8_t* d_doc_flags, int64_t* d_counters,
                        int64_t* d_n_out, void* d_ws, int64_t ws_bytes, int32_t worst, cudaStream_t st, std::string& err);
 
-int64_t encode_words_workspace_fixed(int64_t n_words);
+int64_t encode_words_workspace_fixed(int64_t n_words, int64_t n_text_bytes);
 int64_t pretokenize_workspace(int64_t n_bytes, int64_t n_docs);
 
-// d_n_out: int64[8] status vector (DPT_NOUT_* in include/dptok.h)
+// d_n_out: int64[8] status vector (DPT_NOUT_* in include/dptok.h).  text_extent: bytes of d_text the words lie in (sizes
+// the id stash; words beyond it are solved a second time instead of being read from the stash).
 int encode_words(const dpt_vocab* v, const uint8_t* d_text, const int64_t* d_word_offs, int64_t n_words,
-                 int64_t n_bytes_for_counter, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens,
+                 int64_t n_bytes_for_counter, int64_t text_extent, int32_t* d_ids, int64_t ids_cap, int32_t* d_word_lens,
                  uint8_t* d_word_flags, int64_t* d_word_tok_offs, int64_t* d_counters, int64_t* d_n_out, void* d_ws,
                  int64_t ws_bytes, cudaStream_t st, std::string& err);
 

@@ -182,6 +182,11 @@ int dpt_pretokenize(const dpt_vocab* v, int32_t rule,
  *      d_counters      = device int64[4] {bytes, words, tokens, untokenizable}, OVERWRITTEN
  *                        (bytes = n_text_bytes as given)
  *      d_n_out         = device int64[8] status vector (above)
+ *      n_text_bytes    = size of d_text (>= d_word_offs[n_words]); the same value goes to
+ *                        dpt_encode_words_workspace.  It sizes the id stash (one int32 per text byte)
+ *                        that lets every word be solved ONCE: DP -> ids at the word's byte offset ->
+ *                        scan over the token counts -> placement.  Words lying beyond n_text_bytes
+ *                        are still encoded correctly, at the price of a second DP.
  *      Asynchronous: returns after enqueueing on `stream`. */
 int dpt_encode_words(const dpt_vocab* v,
                      const uint8_t* d_text, const int64_t* d_word_offs, int64_t n_words,

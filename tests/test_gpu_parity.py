@@ -282,6 +282,49 @@ def test_edge_cases_long_oov_untokenizable(dev):
     assert np.array_equal(long_flag, (woffs[1:] - woffs[:-1]) > 64)
 
 
+def test_encode_words_id_stash_and_its_fallback(dev):
+    """dpt_encode_words solves every word ONCE: the ids wait in a stash of one int32 per text byte (sized by
+    n_text_bytes) until the scan has placed them.  A caller whose n_text_bytes understates the text still gets the
+    same ids (words beyond the stash are solved again at placement time).  C ABI called directly with the full extent,
+    half of it (a word straddles the end of the stash) and 0; all three bit-exact against the C oracle."""
+    from dptok import _cabi
+    from dptok.engine import Engine, _ptr
+    from dptok.vocab import CompiledVocab
+    from oracle.c_oracle import COracle
+    rng = random.Random(5)
+    alpha = "abcdeé▁"
+    toks = set(alpha[:6])
+    for _ in range(300):
+        toks.add("".join(rng.choice(alpha) for _ in range(rng.randint(2, 7))))
+    t2i = {t: k for k, t in enumerate(sorted(toks))}
+    eng = Engine(CompiledVocab.from_token_map(t2i, "spm"), dev)
+    words = ["".join(rng.choice(alpha) for _ in range(rng.choice([1, 2, 3, 5, 8, 13, 21, 40, 64, 65, 90]))).encode()
+             for _ in range(20000)]
+    wtext, woffs = pack(words)
+    o_ids, o_lens, o_untok = COracle(vocab_bytes(t2i, "spm"), 1).encode_words(wtext, woffs)
+    d_text, d_offs = _to_dev(wtext, dev), _to_dev(woffs, dev)
+    n_words, n_bytes = len(words), len(wtext)
+    lib = _cabi.lib
+    for extent in (n_bytes, n_bytes // 2 + 3, 0):
+        ids = torch.full((n_bytes + 64,), -7, dtype=torch.int32, device=dev)
+        lens = torch.empty(n_words, dtype=torch.int32, device=dev)
+        flags = torch.empty(n_words, dtype=torch.uint8, device=dev)
+        counters = torch.empty(4, dtype=torch.int64, device=dev)
+        n_out = torch.empty(8, dtype=torch.int64, device=dev)
+        ws = torch.empty(lib.dpt_encode_words_workspace(extent, n_words, 1) + 12 * n_bytes, dtype=torch.uint8, device=dev)
+        _cabi.check(lib.dpt_encode_words(eng.vocab.handle, _ptr(d_text), _ptr(d_offs), n_words, extent, _ptr(ids),
+                                         ids.numel(), _ptr(lens), _ptr(flags), None, _ptr(counters), _ptr(n_out),
+                                         _ptr(ws), ws.numel(), None))
+        torch.cuda.synchronize()
+        h = n_out.cpu().tolist()
+        assert h[_cabi.NOUT_IDS] == len(o_ids) and h[_cabi.NOUT_POOL_REQ] <= h[_cabi.NOUT_POOL_CAP]
+        assert np.array_equal(ids[:len(o_ids)].cpu().numpy(), o_ids), extent
+        assert (ids[len(o_ids):] == -7).all()
+        assert np.array_equal(lens.cpu().numpy(), o_lens)
+        assert np.array_equal(flags.cpu().numpy() & 1, o_untok)
+        assert counters.cpu().tolist() == [extent, n_words, len(o_ids), int(o_untok.sum())]
+
+
 def test_undersized_word_table_odd_words_and_worst_case_retry(dev):
     """The word table holds n_bytes / 48 slots.  (1) a corpus whose DISTINCT words outnumber the slots of their
     neighbourhoods: the occurrences that find 16 probed slots taken become odd words (solved per occurrence from the raw
