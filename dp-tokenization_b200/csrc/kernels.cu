@@ -5,8 +5,7 @@
 // offset until the scan over the token counts has placed them) and is what
 // dpt_encode_words (pre-split words from a host pre-tokenizer) and dpt_encode_corpus_general (the cross-check of the
 // deduplicating corpus pipeline in pipe.cu) are made of; the throughput path is the pipeline.  k_lattice, k_min_tokens
-// (one serial thread) and k_roundtrip (one thread per document) are known-answer / checking entry points, not throughput
-// paths.
+// (one serial thread) are known-answer entry points, not throughput paths; k_roundtrip checks one document per warp.
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -21,6 +20,7 @@
 #include <vector>
 
 #include "../../include/dptok.h"
+#include "dpt_decode.h"
 #include "dpt_dp_core.h"
 #include "dpt_rules.h"
 #include "kernels.h"
@@ -498,59 +498,39 @@ __global__ void k_lattice(DptVocabView V, const uint8_t* __restrict__ s, int32_t
 
 // ---------------------------------------------------------------------------------------------
 // decode + round-trip check on device (tokenizer_utils.py:82-84,176-179; asserts at
-// main_analyze_s2orc.py:85, main_biomed_translation.py:78).  One thread per document: ids -> token
-// bytes -> (SPM: U+2581 -> ' ', "<0xHH>" -> byte, drop the one leading space the Prepend normaliser
-// introduced) -> compare with the raw document.
+// main_analyze_s2orc.py:85, main_biomed_translation.py:78).  One WARP per document, 32 tokens per round: every lane
+// takes the decoded length of its token (dpt_decode.h: U+2581 -> ' ', "<0xHH>" -> the byte, the one leading space of the
+// Prepend normaliser dropped), a warp scan places the tokens in the raw document, every lane compares its bytes.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int hex_val(uint32_t c) {
-    if (c >= '0' && c <= '9') return (int)c - '0';
-    if (c >= 'A' && c <= 'F') return (int)c - 'A' + 10;
-    return -1;
-}
+constexpr int RT_THREADS = 128;
 
-__global__ void k_roundtrip(DptVocabView V, const int32_t* __restrict__ ids, const int64_t* __restrict__ doc_tok_offs,
-                            const uint8_t* __restrict__ text, const int64_t* __restrict__ doc_offs, int64_t n_docs,
-                            int32_t skip_bos, uint8_t* __restrict__ ok) {
-    const int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (d >= n_docs) return;
+__global__ void __launch_bounds__(RT_THREADS)
+k_roundtrip(DptVocabView V, const int32_t* __restrict__ ids, const int64_t* __restrict__ doc_tok_offs,
+            const uint8_t* __restrict__ text, const int64_t* __restrict__ doc_offs, int64_t n_docs, int32_t skip_bos,
+            uint8_t* __restrict__ ok) {
+    const unsigned lane = threadIdx.x & 31;
+    const int64_t d = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (d >= n_docs) return;  // the whole warp
+    const bool spm = V.unit_mode == 1;
+    const int64_t t0 = doc_tok_offs[d] + (skip_bos ? 1 : 0), t1 = doc_tok_offs[d + 1];
     int64_t p = doc_offs[d];
     const int64_t pe = doc_offs[d + 1];
     bool good = true;
-    bool first_char = true;
-    const bool spm = V.unit_mode == 1;
-    for (int64_t t = doc_tok_offs[d] + (skip_bos ? 1 : 0); t < doc_tok_offs[d + 1] && good; ++t) {
-        const int32_t id = ids[t];
-        const int32_t r = (id >= 0 && id < V.id_space) ? V.id_rank[id] : -1;
-        if (r < 0) {
-            good = false;
-            break;
+    for (int64_t base = t0; base < t1 && good; base += 32) {
+        const int64_t t = base + lane;
+        int64_t a = 0, b = 0;
+        bool fine = true;
+        int32_t dl = 0;
+        if (t < t1) {
+            fine = dpt_tok_span(V, ids[t], a, b);
+            if (fine) dl = dpt_tok_decoded_len(V, a, b, spm, t == t0);
         }
-        const int64_t a = V.tok_offs[r], b = V.tok_offs[r + 1];
-        if (spm && b - a == 6 && V.tok_bytes[a] == '<' && V.tok_bytes[a + 1] == '0' && V.tok_bytes[a + 2] == 'x' &&
-            V.tok_bytes[a + 5] == '>' && hex_val(V.tok_bytes[a + 3]) >= 0 && hex_val(V.tok_bytes[a + 4]) >= 0) {
-            const uint32_t byte = (uint32_t)(hex_val(V.tok_bytes[a + 3]) * 16 + hex_val(V.tok_bytes[a + 4]));
-            good = p < pe && text[p] == byte;
-            ++p;
-            first_char = false;
-            continue;
-        }
-        for (int64_t q = a; q < b && good;) {
-            uint32_t c = V.tok_bytes[q];
-            int adv = 1;
-            if (spm && c == DPT_MARK0 && q + 2 < b && V.tok_bytes[q + 1] == DPT_MARK1 && V.tok_bytes[q + 2] == DPT_MARK2) {
-                c = 0x20u;
-                adv = 3;
-            }
-            q += adv;
-            if (spm && first_char) {
-                first_char = false;
-                if (c == 0x20u) continue;  // the Prepend(U+2581) marker
-            }
-            good = p < pe && text[p] == c;
-            ++p;
-        }
+        const int32_t inc = warp_inclusive_scan(dl);
+        if (fine && t < t1) fine = dpt_tok_matches(V, a, b, spm, t == t0, text, p + inc - dl, pe);
+        good = __all_sync(0xffffffffu, fine);
+        p += __shfl_sync(0xffffffffu, inc, 31);
     }
-    ok[d] = (good && p == pe) ? 1 : 0;
+    if (lane == 0) ok[d] = (good && p == pe) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -838,7 +818,7 @@ int doc_tok_offsets(const int64_t* d_doc_first_word, int64_t n_docs, const int64
 
 int roundtrip_check(const dpt_vocab* v, const int32_t* d_ids, const int64_t* d_doc_tok_offs, const uint8_t* d_text,
                     const int64_t* d_doc_offs, int64_t n_docs, int32_t skip_bos, uint8_t* d_ok, cudaStream_t st) {
-    DPT_LAUNCH(k_roundtrip, blocks_for(n_docs, 128), 128, st, v->d_view, d_ids, d_doc_tok_offs, d_text, d_doc_offs, n_docs,
+    DPT_LAUNCH(k_roundtrip, blocks_for(n_docs * 32, RT_THREADS), RT_THREADS, st, v->d_view, d_ids, d_doc_tok_offs, d_text, d_doc_offs, n_docs,
                skip_bos, d_ok);
     return cudaGetLastError() == cudaSuccess ? DPT_OK : DPT_ECUDA;
 }

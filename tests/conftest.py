@@ -66,6 +66,9 @@ def build_host_sim(extra=(), name="libsim.so"):
                                            C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64,
                                            C.c_int64, C.c_int64, C.c_int32]
+    lib.sim_roundtrip.restype = None
+    lib.sim_roundtrip.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                  C.c_int32]
     return lib
 
 

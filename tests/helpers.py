@@ -68,3 +68,21 @@ def sim_word(sim, h, data, bnd=None):
         us = a.ctypes.data
     r = sim.sim_word(h, data, len(data), us, out.ctypes.data, len(out), ctypes.byref(wl))
     return r, wl.value, out[:max(r, 0)].tolist()
+
+
+def py_roundtrip_ok(id2tok, ids, doc, spm, skip_bos):
+    """ids of one document -> bytes the way tokenizer.decode does (tokenizer_utils.py:82-84, :176-179; id2tok: id -> token
+    bytes of the compiled vocabulary) == the document?  The test-side statement of dpt_roundtrip_check."""
+    out = b""
+    for k, i in enumerate(ids[1:] if skip_bos else ids):
+        t = id2tok.get(int(i))
+        if t is None:
+            return False
+        if spm and len(t) == 6 and t[:3] == b"<0x" and t[5:] == b">" and all(c in b"0123456789ABCDEF" for c in t[3:5]):
+            out += bytes([int(t[3:5], 16)])
+            continue
+        piece = t.replace("\u2581".encode(), b" ") if spm else t
+        if spm and k == 0 and piece[:1] == b" ":
+            piece = piece[1:]
+        out += piece
+    return out == doc

@@ -3,6 +3,7 @@
 // before any GPU time is spent.  Never linked into the product library; nothing under
 // dp-tokenization_b200/ loads it.
 #include <barrier>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -10,6 +11,7 @@
 #include <type_traits>
 #include <vector>
 
+#include "dpt_decode.h"
 #include "dpt_dp_core.h"
 #include "dpt_rules.h"
 #include "dpt_pipe.h"
@@ -317,5 +319,80 @@ int32_t sim_encode_corpus_pipe(void* vv, int32_t rule, const uint8_t* text, int6
     }
     doc_tok_offs[n_docs] = ids_base;
     return 0;
+}
+// Round-trip check of k_roundtrip (kernels.cu).  mode 1: the kernel's loop with its 32 lanes run one after the other
+// (length of each lane's token -> inclusive scan -> compare at the scanned place -> vote), on the functions of
+// dpt_decode.h the kernel calls.  mode 0: an independent serial restatement - decode the ids of the document into a
+// buffer the way tokenizer.decode does (tokenizer_utils.py:82-84, :176-179), then compare the buffer with the text.
+void sim_roundtrip(void* vv, const int32_t* ids, const int64_t* doc_tok_offs, const uint8_t* text, const int64_t* doc_offs,
+                   int64_t n_docs, int32_t skip_bos, uint8_t* ok, int32_t mode) {
+    const DptVocabView& V = ((dpt_vocab*)vv)->h_view;
+    const bool spm = V.unit_mode == 1;
+    for (int64_t d = 0; d < n_docs; ++d) {
+        const int64_t t0 = doc_tok_offs[d] + (skip_bos ? 1 : 0), t1 = doc_tok_offs[d + 1];
+        const int64_t pe = doc_offs[d + 1];
+        if (mode == 0) {
+            std::string out;
+            bool valid = true;
+            for (int64_t t = t0; t < t1 && valid; ++t) {
+                int64_t a, b;
+                if (!dpt_tok_span(V, ids[t], a, b)) {
+                    valid = false;
+                    break;
+                }
+                std::string tokstr((const char*)V.tok_bytes + a, (size_t)(b - a));
+                unsigned byte = 0;
+                char tail = 0;
+                if (spm && tokstr.size() == 6 && sscanf(tokstr.c_str(), "<0x%2X%c", &byte, &tail) == 2 && tail == '>' &&
+                    !(tokstr[3] >= 'a' && tokstr[3] <= 'f') && !(tokstr[4] >= 'a' && tokstr[4] <= 'f')) {
+                    out.push_back((char)byte);
+                    continue;
+                }
+                std::string piece;
+                for (size_t q = 0; q < tokstr.size();) {
+                    if (spm && tokstr.compare(q, 3, "\xE2\x96\x81") == 0) {
+                        piece.push_back(' ');
+                        q += 3;
+                    } else {
+                        piece.push_back(tokstr[q++]);
+                    }
+                }
+                if (spm && t == t0 && !piece.empty() && piece[0] == ' ') piece.erase(0, 1);
+                out += piece;
+            }
+            const int64_t p0 = doc_offs[d];
+            ok[d] = valid && (int64_t)out.size() == pe - p0 && memcmp(out.data(), text + p0, out.size()) == 0;
+            continue;
+        }
+        int64_t p = doc_offs[d];
+        bool good = true;
+        for (int64_t base = t0; base < t1 && good; base += 32) {
+            int64_t a[32], b[32];
+            bool fine[32];
+            int32_t dl[32], inc[32];
+            for (int lane = 0; lane < 32; ++lane) {
+                const int64_t t = base + lane;
+                a[lane] = b[lane] = 0;
+                fine[lane] = true;
+                dl[lane] = 0;
+                if (t < t1) {
+                    fine[lane] = dpt_tok_span(V, ids[t], a[lane], b[lane]);
+                    if (fine[lane]) dl[lane] = dpt_tok_decoded_len(V, a[lane], b[lane], spm, t == t0);
+                }
+            }
+            int32_t run = 0;
+            for (int lane = 0; lane < 32; ++lane) inc[lane] = run += dl[lane];
+            bool all = true;
+            for (int lane = 0; lane < 32; ++lane) {
+                const int64_t t = base + lane;
+                if (fine[lane] && t < t1)
+                    fine[lane] = dpt_tok_matches(V, a[lane], b[lane], spm, t == t0, text, p + inc[lane] - dl[lane], pe);
+                all = all && fine[lane];
+            }
+            good = all;
+            p += inc[31];
+        }
+        ok[d] = (good && p == pe) ? 1 : 0;
+    }
 }
 }

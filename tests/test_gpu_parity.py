@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from conftest import load_golden
-from helpers import bytelevel_table, pack, sha1_json, vocab_bytes
+from helpers import bytelevel_table, pack, py_roundtrip_ok, sha1_json, vocab_bytes
 
 pytestmark = pytest.mark.gpu
 
@@ -215,6 +215,42 @@ def test_corpus_path_vs_oracle_llama32k(dev):
     res_bad = type(res)(bad, res.word_lens, res.word_flags, None, res.counters, res.n_ids, res.n_words, res.doc_tok_offs,
                         res.doc_flags)
     assert not bool(eng.roundtrip_ok(res_bad, _to_dev(text, dev), _to_dev(doc_offs, dev), skip_bos=True)[0])
+
+
+def test_roundtrip_check_on_damaged_ids(dev):
+    """dpt_roundtrip_check (one warp per document, 32 tokens per round): every document gets one id replaced at a random
+    position (any round, any lane) or stays intact; the per-document verdicts equal a Python decode of the same ids.
+    SentencePiece (skip_bos, byte tokens, the dropped leading space) and byte-level vocabularies."""
+    from dptok import _cabi, assets, synth
+    from dptok.engine import Engine
+    from dptok.vocab import CompiledVocab
+    rng = random.Random(3)
+    tok, t2i, eng = _llama_engine("llama2_32k", dev)
+    text, doc_offs = synth.gen_documents(1_500_000, seed=6, newline_headers=True)
+    v2i = {t: k for k, t in enumerate(assets.load_spec("gpt2_50k")["model"]["vocab"])}
+    eng_b = Engine(CompiledVocab.from_token_map(v2i, "bytelevel"), dev)
+    text_b, offs_b = synth.gen_sentence_pairs(600_000, seed=6)
+    for engine, vb, txt, offs, rule, spm in ((eng, vocab_bytes(t2i, "spm"), text, doc_offs, _cabi.RULE_SPM_LLAMA, True),
+                                             (eng_b, vocab_bytes(v2i, "bytelevel"), text_b, offs_b, _cabi.RULE_GPT2, False)):
+        d_text, d_offs = _to_dev(txt, dev), _to_dev(offs, dev)
+        res = engine.encode_corpus(d_text, d_offs, rule)
+        assert bool(engine.roundtrip_ok(res, d_text, d_offs, skip_bos=spm).all())
+        ids = res.ids.cpu().numpy().copy()
+        dto = res.doc_tok_offs.cpu().numpy()
+        raw = txt.tobytes()
+        id2tok = {i: t for t, i in vb.items()}
+        all_ids = sorted(id2tok)
+        n_docs = len(offs) - 1
+        for d in range(n_docs):
+            if rng.random() < 0.7 and dto[d + 1] - dto[d] > 1:
+                ids[rng.randrange(dto[d] + (1 if spm else 0), dto[d + 1])] = rng.choice(all_ids + [-1, 2 ** 31 - 1])
+        expect = np.array([py_roundtrip_ok(id2tok, ids[dto[d]:dto[d + 1]], raw[offs[d]:offs[d + 1]], spm, spm)
+                           for d in range(n_docs)])
+        assert expect.any() and not expect.all()
+        bad = type(res)(_to_dev(ids, dev), res.word_lens, res.word_flags, None, res.counters, res.n_ids, res.n_words,
+                        res.doc_tok_offs, res.doc_flags)
+        got = engine.roundtrip_ok(bad, d_text, d_offs, skip_bos=spm).cpu().numpy() != 0
+        assert np.array_equal(got, expect)
 
 
 def test_presplit_bytelevel_vs_oracle_gpt2_50k(dev):

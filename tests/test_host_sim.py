@@ -8,7 +8,7 @@ import random
 import numpy as np
 
 from conftest import load_golden
-from helpers import make_sim_vocab, pack, sim_word, vocab_bytes
+from helpers import make_sim_vocab, pack, py_roundtrip_ok, sim_word, vocab_bytes
 from oracle import adapters, dp_oracle
 
 
@@ -458,6 +458,91 @@ def test_pipeline_code_bytelevel_rules(host_sim):
         big = [("x" * 20000 + " y").encode(), ("7" * 9000 + "a").encode(), (" " * 6000 + "z\n" * 3000).encode(),
                ("." * 5000 + " " + "," * 4200 + " q").encode(), ("\u3002" * 1500 + " \u3000" * 700 + "w").encode()]
         _check_bytelevel(host_sim, h, tok, vb, rule, big, nthreads=4)
+        host_sim.sim_vocab_destroy(ctypes.c_void_p(h))
+
+
+# ------------------------------------------------------------------------------------------------
+# Round-trip check (k_roundtrip: one warp per document, csrc/dpt_decode.h): the kernel's loop with its lanes emulated,
+# an independent serial decode in C++, and a Python decode of the same ids must agree - on true tokenizations and on
+# damaged ones.
+# ------------------------------------------------------------------------------------------------
+def _roundtrip(host_sim, h, ids, dto, docs, skip_bos, mode):
+    raw = b"".join(docs)
+    text = np.frombuffer(raw + b"\0" * 8, np.uint8).copy()
+    offs = np.zeros(len(docs) + 1, np.int64)
+    offs[1:] = np.cumsum([len(d) for d in docs])
+    ids = np.ascontiguousarray(ids, np.int32)
+    dto = np.ascontiguousarray(dto, np.int64)
+    ok = np.full(len(docs), 9, np.uint8)
+    host_sim.sim_roundtrip(h, ids.ctypes.data, dto.ctypes.data, text.ctypes.data, offs.ctypes.data, len(docs),
+                           1 if skip_bos else 0, ok.ctypes.data, mode)
+    return ok
+
+
+def test_roundtrip_check_code(host_sim):
+    from dptok import assets, synth
+    rng = random.Random(9)
+    cases = []
+    # SentencePiece: S2ORC-shaped text + documents that start with a byte token, a space, hold newlines / OOV characters
+    tok = assets.load_hf("llama2_2k")
+    vb = vocab_bytes(tok.get_vocab(), "spm")
+    text, doc_offs = synth.gen_documents(120_000, seed=4, lexicon=synth.make_lexicon(3000, seed=4), newline_headers=True)
+    raw = text.tobytes()
+    docs = [raw[doc_offs[k]:doc_offs[k + 1]] for k in range(len(doc_offs) - 1)]
+    docs += [s.encode() for s in ("\nstarts with a newline", "日本 starts with an OOV character", "x", "Z\tq\n",
+                                  "caf\u00e9 na\u00efve \u2014 ok", "a " * 300 + "end", "tail space ")]
+    cases.append((vb, 1, 1, docs, True))
+    # byte-level: sentence pairs and Arabic, GPT-2 split rule
+    v2i = {t: k for k, t in enumerate(assets.load_spec("gpt2_3k")["model"]["vocab"])}
+    text, doc_offs = synth.gen_sentence_pairs(60_000, seed=2)
+    raw = text.tobytes()
+    docs = [raw[doc_offs[k]:doc_offs[k + 1]] for k in range(len(doc_offs) - 1)]
+    text, doc_offs = synth.gen_documents(30_000, seed=2, flavour="ar", lexicon=synth.make_arabic_lexicon(2000, seed=2))
+    raw = text.tobytes()
+    docs += [raw[doc_offs[k]:doc_offs[k + 1]] for k in range(len(doc_offs) - 1)]
+    cases.append((vocab_bytes(v2i, "bytelevel"), 0, 2, docs, False))
+    for vb, mode, rule, docs, skip_bos in cases:
+        spm = mode == 1
+        h = make_sim_vocab(host_sim, vb, mode)
+        id2tok = {i: t for t, i in vb.items()}
+        r = _run_fused(host_sim, h, rule, docs, nthreads=4)
+        ids, dto = r["ids"], r["dto"]
+        assert not r["dfl"].any() and r["ctr"][3] == 0
+        assert max(dto[k + 1] - dto[k] for k in range(len(docs))) > 40      # documents of more than one 32-token round
+        for m in (0, 1):
+            assert _roundtrip(host_sim, h, ids, dto, docs, skip_bos, m).all()
+        # damaged ids: one change per document (another token, a dropped / doubled / appended token, an id that is none)
+        all_ids = sorted(id2tok)
+        new_ids, new_dto, expect = [], [0], []
+        for k, d in enumerate(docs):
+            row = ids[dto[k]:dto[k + 1]].tolist()
+            lo = 1 if skip_bos else 0
+            kind = rng.choice(["swap", "drop", "double", "append", "invalid", "same", "bos"])
+            pos = rng.randrange(lo, len(row)) if len(row) > lo else None
+            if kind == "swap" and pos is not None:
+                row[pos] = rng.choice(all_ids)
+            elif kind == "drop" and pos is not None:
+                del row[pos]
+            elif kind == "double" and pos is not None:
+                row.insert(pos, row[pos])
+            elif kind == "append":
+                row.append(rng.choice(all_ids))
+            elif kind == "invalid" and pos is not None:
+                row[pos] = rng.choice([-1, -5, max(all_ids) + 1, 2 ** 31 - 1])
+            elif kind == "bos" and skip_bos:
+                row[0] = rng.choice(all_ids)        # the skipped position is not looked at
+            new_ids += row
+            new_dto.append(len(new_ids))
+            expect.append(py_roundtrip_ok(id2tok, row, d, spm, skip_bos))
+        expect = np.array(expect)
+        assert expect.any() and not expect.all()
+        for m in (0, 1):
+            got = _roundtrip(host_sim, h, new_ids, new_dto, docs, skip_bos, m)
+            assert np.array_equal(got != 0, expect), m
+        # the wrong skip_bos setting fails every SentencePiece document (its first id is '<s>')
+        if skip_bos:
+            for m in (0, 1):
+                assert not _roundtrip(host_sim, h, ids, dto, docs, False, m).any()
         host_sim.sim_vocab_destroy(ctypes.c_void_p(h))
 
 
