@@ -498,33 +498,43 @@ class Engine:
         return EncodeResult(ids[:h[0]], lens[:nw], flags[:nw], None, counters, h[0], nw, doc_tok, doc_flags)
 
     # ---- lattice of one word (enumerate-all API) --------------------------------------------------
+    def _upload_word(self, data: bytes, unit_starts: Optional[Sequence[int]]):
+        """ONE host-to-device copy for a word's bytes and (optionally) its unit-start flags -> (text ptr, flags ptr, keep)."""
+        n = len(data)
+        host = np.zeros(2 * n if unit_starts is not None else n, dtype=np.uint8)
+        host[:n] = np.frombuffer(data, dtype=np.uint8)
+        if unit_starts is not None:
+            for p in unit_starts:
+                if p < n:
+                    host[n + p] = 1
+        d = torch.from_numpy(host).to(self.device)
+        return C.c_void_p(d.data_ptr()), (C.c_void_p(d.data_ptr() + n) if unit_starts is not None else None), d
+
     def lattice(self, data: bytes, unit_starts: Optional[Sequence[int]] = None):
-        """Returns (len_dp: list[int], preds: list[list[int]]) over unit positions 0..n_units."""
+        """Returns (len_dp: list[int], preds: list[list[int]]) over unit positions 0..n_units.  One copy in, one launch, one
+        copy out per call: the outputs are carved out of one int32 buffer and read back together."""
         n = len(data)
         dev = self.device
         with torch.cuda.device(dev):
-            text = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
-            us = None
-            if unit_starts is not None:
-                flags = np.zeros(n, dtype=np.uint8)
-                flags[[p for p in unit_starts if p < n]] = 1
-                us = torch.from_numpy(flags).to(dev)
+            p_text, p_us, _keep = self._upload_word(data, unit_starts)
             pred_cap = max(64, 8 * (n + 1))
             while True:
-                len_dp = torch.empty(n + 2, dtype=torch.int32, device=dev)
-                pred_offs = torch.empty(n + 3, dtype=torch.int32, device=dev)
-                pred = torch.empty(pred_cap, dtype=torch.int32, device=dev)
-                scratch = torch.empty(n + 2, dtype=torch.int32, device=dev)
-                n_out = torch.zeros(2, dtype=torch.int32, device=dev)
-                check(lib.dpt_lattice_word(self.vocab.handle, _ptr(text), n, _ptr(us), _ptr(len_dp), _ptr(pred_offs),
-                                           _ptr(pred), pred_cap, _ptr(n_out), _ptr(scratch), self._stream()))
-                n_units, n_pred = n_out.cpu().tolist()
+                # [n_out 2 | len_dp n+2 | pred_offs n+3 | pred pred_cap | scratch n+2]
+                o_len, o_po, o_pr = 2, 2 + (n + 2), 2 + (n + 2) + (n + 3)
+                o_sc = o_pr + pred_cap
+                buf = torch.zeros(o_sc + n + 2, dtype=torch.int32, device=dev)
+                base = buf.data_ptr()
+                at = lambda k: C.c_void_p(base + 4 * k)  # noqa: E731
+                check(lib.dpt_lattice_word(self.vocab.handle, p_text, n, p_us, at(o_len), at(o_po), at(o_pr), pred_cap,
+                                           at(0), at(o_sc), self._stream()))
+                h = buf[:o_sc].cpu().numpy()  # synchronises
+                n_units, n_pred = int(h[0]), int(h[1])
                 if n_pred <= pred_cap:
                     break
                 pred_cap = n_pred
-            ld = len_dp[:n_units + 1].cpu().tolist()
-            po = pred_offs[:n_units + 2].cpu().tolist()
-            pr = pred[:n_pred].cpu().tolist()
+        ld = h[o_len:o_len + n_units + 1].tolist()
+        po = h[o_po:o_po + n_units + 2].tolist()
+        pr = h[o_pr:o_pr + n_pred].tolist()
         preds = [pr[po[u]:po[u + 1]] for u in range(n_units + 1)]
         return ld, preds
 
@@ -535,16 +545,11 @@ class Engine:
             return 0
         dev = self.device
         with torch.cuda.device(dev):
-            text = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
-            us = None
-            if unit_starts is not None:
-                flags = np.zeros(n, dtype=np.uint8)
-                flags[[p for p in unit_starts if p < n]] = 1
-                us = torch.from_numpy(flags).to(dev)
-            out = torch.empty(1, dtype=torch.int32, device=dev)
-            scratch = torch.empty(n + 2, dtype=torch.int32, device=dev)
-            check(lib.dpt_min_tokens_word(self.vocab.handle, _ptr(text), n, _ptr(us), _ptr(out), _ptr(scratch), self._stream()))
-            v = int(out.item())
+            p_text, p_us, _keep = self._upload_word(data, unit_starts)
+            buf = torch.empty(1 + n + 2, dtype=torch.int32, device=dev)  # [out 1 | scratch n+2]
+            check(lib.dpt_min_tokens_word(self.vocab.handle, p_text, n, p_us, C.c_void_p(buf.data_ptr()),
+                                          C.c_void_p(buf.data_ptr() + 4), self._stream()))
+            v = int(buf[0].item())
         return float("inf") if v < 0 else v
 
     # ---- training-data feed on device ------------------------------------------------------------
