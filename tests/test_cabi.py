@@ -203,3 +203,37 @@ def test_spm_device_rule_gate_and_merge_table(product_lib):
     assert cv.n_merges == len(merges)
     with pytest.raises(_cabi.DptError):
         CompiledVocab.from_token_map(t2i, "spm").set_merges([(0, 1, 10 ** 6)])
+
+
+def test_integration_stub_matches_the_c_abi(product_lib):
+    """The ctypes stub INTEGRATION.md shows a maintainer of the reference: it is valid Python, every `argtypes` list in it has
+    the arity and the types the shipped binding declares (`dptok._cabi.SIGNATURES`, itself checked against the header
+    and the library above), its host-only half (dpt_vocab_create) runs here, and its compute half refuses without a GPU."""
+    from dptok import _cabi
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", doc, flags=re.S)
+    stub = next(b for b in blocks if "lib.dpt_encode_corpus.argtypes" in b)
+    stub = stub.replace('"<repo>/dp-tokenization_b200/lib/libdptok.so"', repr(product_lib))
+    ns = {}
+    exec(compile(stub, "INTEGRATION.md", "exec"), ns)
+    seen = 0
+    for name, (res, args) in _cabi.SIGNATURES.items():
+        fn = getattr(ns["lib"], name)
+        if fn.argtypes is not None:
+            assert list(fn.argtypes) == list(args), name
+            seen += 1
+        if fn.restype is not C.c_int:       # ctypes' default restype is c_int
+            assert fn.restype is res, name
+    assert seen >= 4
+    # the host-only half: compile a vocabulary through the stub's own calls
+    toks = {"a": 0, "b": 1, "ab": 2, "▁": 3}
+    items = [(t.encode("utf-8"), i) for t, i in toks.items()]
+    blob = np.frombuffer(b"".join(t for t, _ in items) + b"\0", np.uint8)
+    offs = np.zeros(len(items) + 1, np.int64)
+    offs[1:] = np.cumsum([len(t) for t, _ in items])
+    ids = np.array([i for _, i in items], np.int32)
+    h = C.c_void_p()
+    assert ns["lib"].dpt_vocab_create(blob.ctypes.data, offs.ctypes.data, ids.ctypes.data, len(items), 1, C.byref(h)) == 0
+    if not torch.cuda.is_available():
+        assert ns["lib"].dpt_vocab_upload(h, 0) != 0 and ns["lib"].dpt_last_error()
+    _cabi.lib.dpt_vocab_destroy(h)
