@@ -253,10 +253,11 @@ class Engine:
         copy-out stream over a ring of ``n_streams`` output slots: PCIe in both directions and the SMs work at the same
         time.  Returns host tensors.
 
-        Measured on the B200 box (100 MB corpus, tools/sweep_e2e.py): 3.40-3.50 ms for every chunk size from 16 to 34 MB,
-        3 or 8 slots, with or without ``overlap`` (scan / DP / emit of neighbouring ranges on three streams): the path
-        is bound by PCIe, whose two directions together move ~57 GB/s on this box (H2D alone 1.81 ms, D2H alone
-        1.69 ms, 100.5 + 95.2 MB in 3.43 ms when both run).  ``ids_dtype=torch.uint16`` (vocabularies whose ids all fit
+        Measured on the B200 box (100 MB corpus, int32 ids): 3.3 ms, about the same for every chunk size from 16 to 34 MB,
+        3 or 8 slots, with or without ``overlap`` (scan / DP / emit of neighbouring ranges on three streams).  The host
+        link moves 75 GB/s with both directions busy (H2D alone 1.8 ms, D2H alone 1.7 ms: profiles/r2_pcie_duplex.txt), so
+        2.6 ms is the floor for 100.5 + 95.2 MB; the rest is the per-range latency of the DP launches
+        (profiles/r2_e2e_timeline_n1.txt).  ``ids_dtype=torch.uint16`` (vocabularies whose ids all fit
         16 bits: Llama-2 32k, GPT-2 50k) narrows the ids on the device (``dpt_narrow_ids_u16``) so that half as many
         bytes cross PCIe on the way out; an id that does not fit raises.  ``want_ids=False``: the ids stay on the device
         and only the per-document token offsets (8 bytes per document), flags and counters come back - what the statistics
