@@ -35,6 +35,36 @@ def test_shard_bounds_balanced_and_contiguous():
     assert b[0] == 0 and b[-1] == 2 and (np.diff(b) >= 0).all()
 
 
+def test_shard_bounds_properties():
+    """Any document-length profile (one giant document, more ranks than documents, equal documents) and any world size:
+    the bounds are monotone, cover every document exactly once, and no rank gets more than its byte share plus one document
+    (cut at the nearer boundary)."""
+    from hypothesis import given, settings, strategies as st
+    from dptok.sharded import shard_bounds, take_shard
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.one_of(st.integers(1, 50), st.integers(1, 100_000)), min_size=1, max_size=200), st.integers(1, 17),
+           st.integers(0, 1000))
+    def check(lens, world, base):
+        offs = base + np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        b = shard_bounds(offs, world)
+        assert len(b) == world + 1 and b[0] == 0 and b[-1] == len(lens) and (np.diff(b) >= 0).all()
+        share = (offs[-1] - offs[0]) / world
+        sizes = [int(offs[b[r + 1]] - offs[b[r]]) for r in range(world)]
+        assert sum(sizes) == offs[-1] - offs[0]
+        assert max(sizes) <= share + max(lens) + 1
+        if base == 0:
+            text = np.zeros(int(offs[-1]), dtype=np.uint8)
+            got = 0
+            for r in range(world):
+                t, o = take_shard(text, offs, world, r)
+                assert o[0] == 0 and o[-1] == len(t) and (np.diff(o) > 0).all()
+                got += len(t)
+            assert got == len(text)
+
+    check()
+
+
 def _worker(rank, world, port, out):
     for p in (ROOT, PKG):
         sys.path.insert(0, p)
